@@ -1,0 +1,174 @@
+/* txl_b200.h — C ABI of the B200-native Transformer-XL hot path.
+ *
+ * The reference (StefanHeng/Symbolic-Music-Generation) has no FFI: its boundary for this path is the
+ * Python class musicnlp/models/transformer_xl.py:127-241 (MyTransfoXLLMHeadModel) whose arithmetic
+ * is HF transformers==4.25.1 `modeling_transfo_xl.py` (un-vendored).  Each entry
+ * point below replaces one torch-op site of that module; the HF site it replaces is cited as
+ * [A.x] = SURVEY.md Appendix A section, plus the reference call site (file:line) that reaches it.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return 0 on success, negative TXL_E* on error; `txl_last_error()` gives a thread-local message;
+ *   - no global mutable state except a per-process cache of TMA descriptors/func attributes;
+ *   - sm_100a only.  There is NO CPU fallback: without a B200 every compute entry point fails.
+ *   - activations are BATCH-MAJOR: row = b*T + t (HF is time-major inside; the Python boundary converts `mems`).
+ *   - dtype codes: TXL_F32 = 0, TXL_BF16 = 1.  Biases, LayerNorm affine, r_w_bias/r_r_bias, statistics,
+ *     losses and gradient accumulators of parameters are always fp32.
+ */
+#ifndef TXL_B200_H
+#define TXL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TXL_F32 0
+#define TXL_BF16 1
+
+#define TXL_OK 0
+#define TXL_EINVAL (-1)   /* bad argument / unsupported shape */
+#define TXL_ECUDA (-2)    /* CUDA runtime error, see txl_last_error() */
+#define TXL_ENODEV (-3)   /* no sm_100 device */
+
+/* Integer geometry of one relative-position attention call  [A.2 step 3-5, A.4, A.5]. */
+typedef struct {
+  int T;           /* qlen: query rows of this segment                               */
+  int mlen;        /* rows of cached memory actually present (keys 0..mlen-1)        */
+  int mem_len;     /* config.mem_len (defines the same_length band)                  */
+  int clamp_len;   /* config.clamp_len (<=0: no clamp)                               */
+  int same_length; /* config.same_length                                             */
+} TxlBand;
+
+int txl_version(void);
+const char* txl_last_error(void);
+/* 0 if the current device is sm_100 (B200); TXL_ENODEV otherwise. */
+int txl_device_ok(void);
+
+/* ---- integer index maps (bit-exact contract) -------------------------------------------------
+ * masked[i*klen+j] = 1 iff key j is masked for query i          (HF uint8 triu+tril mask, [A.2-4])
+ * ridx[i*klen+j]   = relative-position row used by BD at (i,j)  (HF _rel_shift + clamp, [A.4]); -1 where masked
+ * lo[i], hi[i]     = first / last live key of query i (inclusive)
+ * Computed on the device with the same inline functions the attention kernels use. */
+int txl_relattn_index_map(const TxlBand* band, uint8_t* masked, int32_t* ridx, int32_t* lo, int32_t* hi, void* stream);
+
+/* ---- embedding  [A.6 AdaptiveEmbedding, div_val=1; call site transformer_xl.py:163] -------------
+ * out[n,:] = E[ids[n],:] * scale, then inverted dropout (p, seed, site) if p>0. */
+int txl_embed_fwd(const int64_t* ids, const void* E, void* out, int64_t n_tok, int d, int V, float scale,
+                  int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
+/* dE[ids[n],:] += dOut[n,:] * scale (* dropout mask)   (fp32 atomics) */
+int txl_embed_bwd(const int64_t* ids, const void* dOut, float* dE, int64_t n_tok, int d, int V, float scale,
+                  int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
+
+/* ---- sinusoid table  [A.6 PositionalEmbedding] -------------------------------------------------
+ * out[p,:] = [sin(p*f_0..), cos(p*f_0..)], f_k = 10000^(-2k/d), p = 0..P-1, inverted dropout if p>0 */
+int txl_posemb_table(void* out, int P, int d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
+
+/* ---- generic GEMM with epilogue  [A.3 qkv_net/r_net/o_net, A.6 CoreNet.0/3, crit.out_layers] -----
+ * C[M,N] = epi( op(A)[M,K] * op(B)[K,N] ), row-major, leading dims in elements.
+ *   transA=0: A is [M,K] (lda>=K); transA=1: A is stored [K,M] (lda>=M)
+ *   transB=0: B is [K,N] (ldb>=N); transB=1: B is stored [N,K] (ldb>=K)   (nn.Linear weight => transB=1)
+ * epilogue: v = acc; if bias: v += bias[n]; if (flags&RELU) v = max(v,0); if (flags&MASK_POS) v *= (aux[m,n]>0);
+ *           if (flags&DROPOUT) v = inverted-dropout(v); if (flags&ACCUM) v += C[m,n];  C = (dtype_c) v
+ * colsum (optional, fp32[N]): colsum[n] += sum_m v (before ACCUM) — bias gradients.
+ * bf16 inputs with all of M,N,K and leading dims "nice" run on tcgen05 tensor cores; everything else on a
+ * SIMT fp32-FMA kernel (true fp32 accumulate — the fp32 parity mode). */
+#define TXL_EPI_RELU 1
+#define TXL_EPI_ACCUM 2
+#define TXL_EPI_MASK_POS 4
+#define TXL_EPI_DROPOUT 8
+typedef struct {
+  const float* bias;     /* [N] or NULL */
+  const void* aux;       /* [M,N] same dtype/ld as C, for MASK_POS */
+  float* colsum;         /* [N] fp32 accumulate or NULL */
+  float drop_p; uint64_t seed; uint32_t site;
+  int flags;
+} TxlEpilogue;
+int txl_gemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K,
+             int64_t lda, int64_t ldb, int64_t ldc, int transA, int transB,
+             int dtype_ab, int dtype_c, const TxlEpilogue* epi, void* stream);
+
+/* ---- residual + LayerNorm  [A.3 step 8, A.6 PositionwiseFF] ---------------------------------------
+ * z = x + dropout(r); y = LN(z)*gamma + beta;   mean/rstd fp32 [rows] saved for backward; z optional. */
+int txl_add_ln_fwd(const void* x, const void* r, const float* gamma, const float* beta, void* y, void* z,
+                   float* mean, float* rstd, int64_t rows, int d, float eps, int dtype,
+                   float drop_p, uint64_t seed, uint32_t site, void* stream);
+/* dz = LN'(dy);  dgamma += sum dy*xhat; dbeta += sum dy.   dx_out = dz (+ dx_out if accumulate);
+ * dr_out = dz * dropout-mask.  dx_out may alias dy. */
+int txl_add_ln_bwd(const void* dy, const void* z, const float* gamma, const float* mean, const float* rstd,
+                   void* dx_out, int accumulate_dx, void* dr_out, float* dgamma, float* dbeta,
+                   int64_t rows, int d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
+/* out[n] += sum_m X[m,n]  (fp32 accumulate; bias gradients of CoreNet.3 / crit.out_layers.0) */
+int txl_colsum(const void* X, int64_t M, int64_t N, int64_t ldx, int dtype, float* out, void* stream);
+/* y = dropout(x) (final `drop(core_out)`, [A.2-8]); backward is the same op on dy. */
+int txl_dropout(const void* x, void* y, int64_t n, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
+
+/* ---- relative-position attention  [A.3 steps 2-8 + A.4 _rel_shift + A.5 band; RelPartialLearnableMultiHeadAttn]
+ * q:      [B, T, H*dh] view with row stride ldq (elements)
+ * k/v:    keys 0..mlen-1 from k_mem/v_mem ([B, mlen, H*dh], row stride ldkv_mem),
+ *         keys mlen..mlen+T-1 from k_cur/v_cur ([B, T, H*dh], row stride ldkv_cur)
+ * r:      [P, H*dh] r_net(pos_emb) rows for relative distance p = 0..P-1, P = min(klen-1, clamp)+1
+ * rwb/rrb:[H*dh] fp32 (r_w_bias, r_r_bias)
+ * out:    [B, T, H*dh] (ld = H*dh);  lse: [B, H, T] fp32 log-sum-exp of the scaled scores
+ * score(i,j) = ((q_i+rwb).k_j + (q_i+rrb).r[min(mlen+i-j, clamp)]) / sqrt(dh) on the live band only. */
+typedef struct {
+  int B, H, dh;
+  TxlBand band;
+  int64_t ldq, ldkv_mem, ldkv_cur;
+  int dtype;
+} TxlAttnDims;
+int txl_relattn_fwd(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur,
+                    const void* r, const float* rwb, const float* rrb, void* out, float* lse,
+                    const TxlAttnDims* dims, void* stream);
+/* Backward.  dq/dk_cur/dv_cur are written with the same strides as their forward tensors (they may be
+ * slices of one [B,T,3d] buffer); dk_mem/dv_mem may be NULL (mems detached and all-zero => no wgrad term).
+ * dr [P,H*dh], drwb/drrb [H*dh] are fp32 and ACCUMULATED into.  ws: workspace of txl_relattn_bwd_workspace bytes. */
+int64_t txl_relattn_bwd_workspace(const TxlAttnDims* dims);
+int txl_relattn_bwd(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur,
+                    const void* r, const float* rwb, const float* rrb, const void* out, const float* lse,
+                    const void* dout, void* dq, void* dk_mem, void* dv_mem, void* dk_cur, void* dv_cur,
+                    float* dr, float* drwb, float* drrb, void* ws, const TxlAttnDims* dims, void* stream);
+
+/* ---- LM head: log-softmax + NLL  [A.6 ProjectedAdaptiveLogSoftmax n_clusters=0; transformer_xl.py:185,193]
+ * logits [N, ldl] (dtype) are the raw h.E^T+b produced by txl_gemm; labels int64 [N] (-100 = ignore).
+ * losses[n] = lse - logit[label] (0 where ignored); lse[n] saved; if logprobs != NULL: logprobs[n,v] = logit - lse (fp32, ld=V)
+ * argmax (optional int64 [N]) = argmax_v logit  (preprocess_logits_for_metrics, train.py:248-252). */
+int txl_logsoftmax_nll_fwd(const void* logits, int64_t ldl, const int64_t* labels, float* losses, float* lse,
+                           float* logprobs, int64_t* argmax, int64_t N, int V, int dtype, void* stream);
+/* dlogits[n,v] = (softmax - onehot(label)) * grow[n]  (0 rows where label ignored); written in place over logits. */
+int txl_logsoftmax_nll_bwd(void* logits, int64_t ldl, const int64_t* labels, const float* lse, const float* grow,
+                           int64_t N, int V, int dtype, void* stream);
+/* loss = mean(losses[losses != 0]) and grow[n] = g_loss/cnt * (losses[n]!=0) + g_losses[n]  (transformer_xl.py:197-200) */
+int txl_masked_mean(const float* losses, int64_t N, float* loss_out, float* count_out, void* stream);
+
+/* ---- parameters --------------------------------------------------------------------------------- */
+int txl_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+int txl_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+/* B[c,r] = A[r,c]  (weight transposes for dgrad operands) */
+int txl_transpose(const void* A, void* B, int64_t rows, int64_t cols, int dtype, void* stream);
+/* fused AdamW over a flat fp32 buffer (train.py:166-190 defaults): decay applied where decay_mask[i]!=0 (NULL: all).
+ * grad_scale multiplies g first (global-norm clip factor, read from device: *grad_scale_dev if non-NULL). */
+int txl_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* decay_mask, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   const float* grad_scale_dev, void* bf16_shadow, void* stream);
+/* out[0] += sum g^2 (fp32 atomics) */
+int txl_sumsq(const float* g, int64_t n, float* out, void* stream);
+
+/* ---- sampling  [A.7; HF logits warpers as used at eval.py:277-333] -------------------------------
+ * scores [B, V] fp32 log-probs of the last position.  Temperature -> TopK (ties kept) -> TopP (first token
+ * crossing p kept) -> renormalise -> draw.  u [B] uniform(0,1) supplied by the caller (so tests can pin draws);
+ * do_sample=0 => argmax.  next [B] int64.  keep (optional uint8 [B,V]) = surviving set, warped (optional fp32
+ * [B,V]) = renormalised log-probs (-inf outside keep). */
+int txl_sample(const float* scores, int B, int V, int do_sample, float temperature, int top_k, float top_p,
+               const float* u, int64_t* next, uint8_t* keep, float* warped, void* stream);
+
+/* ---- mems ring / layout helpers  [A.8' _update_mems] ----------------------------------------------
+ * time-major (L?,rows,B,d) <-> batch-major copies used at the Python boundary */
+int txl_tm_to_bm(const void* src, void* dst, int rows, int B, int d, int dtype_src, int dtype_dst, void* stream);
+int txl_bm_to_tm(const void* src, void* dst, int rows, int B, int d, int dtype_src, int dtype_dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

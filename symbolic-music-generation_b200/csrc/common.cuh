@@ -1,0 +1,99 @@
+// common.cuh — shared device/host helpers for the txl_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/txl_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ error plumbing
+void txl_set_error(const char* fmt, ...);
+#define TXL_CHECK_ARG(cond, ...)                      \
+  do {                                                \
+    if (!(cond)) {                                    \
+      txl_set_error(__VA_ARGS__);                     \
+      return TXL_EINVAL;                              \
+    }                                                 \
+  } while (0)
+#define TXL_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      txl_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return TXL_ECUDA;                                                                 \
+    }                                                                                   \
+  } while (0)
+#define TXL_LAUNCH_CHECK() TXL_CUDA(cudaGetLastError())
+
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+int txl_num_sms();
+
+// ------------------------------------------------------------------ dtype helpers
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// ------------------------------------------------------------------ integer geometry of the band  [A.2-4, A.4, A.5]
+// These four functions ARE the closed forms of HF's uint8 triu+tril mask and pad/reshape _rel_shift;
+// tests/test_index_maps.py checks them bit-exactly against the literal construction.
+struct BandGeom {
+  int T, mlen, klen, msl, clamp;  // msl = mask_shift_len (same_length) or a huge value (plain causal)
+};
+__host__ __device__ __forceinline__ BandGeom make_band(const TxlBand& b) {
+  BandGeom g;
+  g.T = b.T; g.mlen = b.mlen; g.klen = b.mlen + b.T; g.clamp = b.clamp_len;
+  if (b.same_length) {
+    int mask_len = g.klen - b.mem_len;
+    g.msl = mask_len > 0 ? b.T - mask_len : b.T;
+  } else {
+    g.msl = 1 << 29;
+  }
+  return g;
+}
+// first / last live key (inclusive) of query row i
+__host__ __device__ __forceinline__ int band_lo(const BandGeom& g, int i) {
+  long lo = (long)i - g.msl + 1;
+  return lo < 0 ? 0 : (int)lo;
+}
+__host__ __device__ __forceinline__ int band_hi(const BandGeom& g, int i) { return i + g.mlen; }
+// row of the r-table used at (i, j): relative distance, clamped
+__host__ __device__ __forceinline__ int band_ridx(const BandGeom& g, int i, int j) {
+  int p = g.mlen + i - j;
+  return (g.clamp > 0 && p > g.clamp) ? g.clamp : p;
+}
+// rows of the r-table a call needs: distances 0..P-1
+__host__ __device__ __forceinline__ int band_num_r(const BandGeom& g) {
+  int pmax = g.klen - 1;
+  if (g.clamp > 0 && pmax > g.clamp) pmax = g.clamp;
+  return pmax + 1;
+}
+
+// ------------------------------------------------------------------ counter-based dropout
+// keep-mask for logical element `idx` of dropout site `site`; identical in forward and backward.
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
+  uint64_t x = (idx + 0x9E3779B97F4A7C15ull * (uint64_t)(site + 1)) ^ seed;
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  float u = (float)(uint32_t)(x >> 40) * (1.0f / 16777216.0f);
+  return u >= p ? inv_keep : 0.0f;
+}
+
+// ------------------------------------------------------------------ warp reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}

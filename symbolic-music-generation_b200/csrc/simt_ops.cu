@@ -1,0 +1,515 @@
+// simt_ops.cu — bandwidth-bound kernels of the Transformer-XL path: embedding, sinusoid table, residual+LayerNorm,
+// dropout, log-softmax/NLL, parameter casts/transposes, AdamW, index maps.  All fp32 math, fp32 or bf16 storage.
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+void txl_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* txl_last_error(void) { return g_err; }
+extern "C" int txl_version(void) { return 100; }
+
+int txl_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+extern "C" int txl_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { txl_set_error("no CUDA device"); return TXL_ENODEV; }
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) { txl_set_error("device compute capability %d.x is not sm_100", major); return TXL_ENODEV; }
+  return TXL_OK;
+}
+
+#define DISPATCH_DTYPE(dtype, ...)                                    \
+  if ((dtype) == TXL_F32) { typedef float T; __VA_ARGS__; }           \
+  else if ((dtype) == TXL_BF16) { typedef bf16 T; __VA_ARGS__; }      \
+  else { txl_set_error("bad dtype %d", (int)(dtype)); return TXL_EINVAL; }
+
+// ------------------------------------------------------------------ index maps
+__global__ void index_map_kernel(TxlBand band, uint8_t* masked, int32_t* ridx, int32_t* lo, int32_t* hi) {
+  BandGeom g = make_band(band);
+  int64_t n = (int64_t)g.T * g.klen;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(idx / g.klen), j = (int)(idx % g.klen);
+    bool live = j >= band_lo(g, i) && j <= band_hi(g, i);
+    masked[idx] = live ? 0 : 1;
+    ridx[idx] = live ? band_ridx(g, i, j) : -1;
+    if (j == 0) { lo[i] = band_lo(g, i); hi[i] = min(band_hi(g, i), g.klen - 1); }
+  }
+}
+extern "C" int txl_relattn_index_map(const TxlBand* band, uint8_t* masked, int32_t* ridx, int32_t* lo, int32_t* hi, void* stream) {
+  TXL_CHECK_ARG(band && band->T > 0 && band->mlen >= 0, "index_map: bad band");
+  index_map_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(*band, masked, ridx, lo, hi);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
+// ------------------------------------------------------------------ embedding
+template <typename T>
+__global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ E, T* __restrict__ out, int64_t n_tok,
+                                 int d, int V, float scale, float p, float inv_keep, uint64_t seed, uint32_t site) {
+  int64_t total = n_tok * d;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = idx / d; int c = (int)(idx % d);
+    int64_t id = ids[n];
+    float v = (id >= 0 && id < V) ? to_f32(E[id * d + c]) * scale : 0.f;
+    if (p > 0.f) v *= dropout_scale(seed, site, (uint64_t)idx, p, inv_keep);
+    out[idx] = from_f32<T>(v);
+  }
+}
+template <typename T>
+__global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ dOut, float* __restrict__ dE, int64_t n_tok,
+                                 int d, int V, float scale, float p, float inv_keep, uint64_t seed, uint32_t site) {
+  int64_t total = n_tok * d;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = idx / d; int c = (int)(idx % d);
+    int64_t id = ids[n];
+    if (id < 0 || id >= V) continue;
+    float v = to_f32(dOut[idx]) * scale;
+    if (p > 0.f) v *= dropout_scale(seed, site, (uint64_t)idx, p, inv_keep);
+    atomicAdd(&dE[id * d + c], v);
+  }
+}
+extern "C" int txl_embed_fwd(const int64_t* ids, const void* E, void* out, int64_t n_tok, int d, int V, float scale,
+                             int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream) {
+  TXL_CHECK_ARG(n_tok > 0 && d > 0 && V > 0, "embed_fwd: bad sizes");
+  int grid = (int)imin64(cdiv64(n_tok * d, 256), (int64_t)txl_num_sms() * 16);
+  float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  DISPATCH_DTYPE(dtype, (embed_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(ids, (const T*)E, (T*)out, n_tok, d, V, scale, drop_p, ik, seed, site)));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+extern "C" int txl_embed_bwd(const int64_t* ids, const void* dOut, float* dE, int64_t n_tok, int d, int V, float scale,
+                             int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream) {
+  TXL_CHECK_ARG(n_tok > 0 && d > 0 && V > 0, "embed_bwd: bad sizes");
+  int grid = (int)imin64(cdiv64(n_tok * d, 256), (int64_t)txl_num_sms() * 16);
+  float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  DISPATCH_DTYPE(dtype, (embed_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(ids, (const T*)dOut, dE, n_tok, d, V, scale, drop_p, ik, seed, site)));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
+// ------------------------------------------------------------------ sinusoid table
+template <typename T>
+__global__ void posemb_kernel(T* out, int P, int d, float p, float inv_keep, uint64_t seed, uint32_t site) {
+  int half = d / 2;
+  int64_t total = (int64_t)P * d;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int pos = (int)(idx / d), c = (int)(idx % d);
+    int k = c < half ? c : c - half;
+    // inv_freq = 1 / 10000^(2k/d) evaluated like torch: fp32 pow then reciprocal; product in fp32
+    float inv_freq = 1.0f / powf(10000.0f, (float)(2 * k) / (float)d);
+    float a = (float)pos * inv_freq;
+    float v = c < half ? sinf(a) : cosf(a);
+    if (p > 0.f) v *= dropout_scale(seed, site, (uint64_t)idx, p, inv_keep);
+    out[idx] = from_f32<T>(v);
+  }
+}
+extern "C" int txl_posemb_table(void* out, int P, int d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream) {
+  TXL_CHECK_ARG(P > 0 && d > 0 && d % 2 == 0, "posemb: bad sizes");
+  int grid = (int)imin64(cdiv64((int64_t)P * d, 256), 4096);
+  float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  DISPATCH_DTYPE(dtype, (posemb_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((T*)out, P, d, drop_p, ik, seed, site)));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
+// ------------------------------------------------------------------ residual + LayerNorm (one warp per row)
+constexpr int LN_MAX_PER_LANE = 32;  // d <= 1024
+template <typename T>
+__global__ void add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ z, float* __restrict__ mean,
+                                  float* __restrict__ rstd, int64_t rows, int d, float eps, float p, float inv_keep, uint64_t seed,
+                                  uint32_t site) {
+  int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
+  int per = d / 32;
+  for (int64_t row = warp; row < rows; row += (int64_t)gridDim.x * wpb) {
+    float v[LN_MAX_PER_LANE];
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < LN_MAX_PER_LANE; ++e) {
+      if (e < per) {
+        int c = e * 32 + lane;
+        float rv = r ? to_f32(r[row * d + c]) : 0.f;
+        if (p > 0.f) rv *= dropout_scale(seed, site, (uint64_t)(row * d + c), p, inv_keep);
+        float zz = to_f32(x[row * d + c]) + rv;
+        // the stored z is what backward sees; normalise the rounded value so fwd/bwd agree
+        T zt = from_f32<T>(zz);
+        if (z) z[row * d + c] = zt;
+        v[e] = to_f32(zt);
+        s += v[e];
+      }
+    }
+    float mu = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int e = 0; e < LN_MAX_PER_LANE; ++e)
+      if (e < per) { float t = v[e] - mu; q += t * t; }
+    float rs = rsqrtf(warp_sum(q) / d + eps);
+#pragma unroll
+    for (int e = 0; e < LN_MAX_PER_LANE; ++e) {
+      if (e < per) {
+        int c = e * 32 + lane;
+        y[row * d + c] = from_f32<T>((v[e] - mu) * rs * gamma[c] + beta[c]);
+      }
+    }
+    if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
+  }
+}
+extern "C" int txl_add_ln_fwd(const void* x, const void* r, const float* gamma, const float* beta, void* y, void* z,
+                              float* mean, float* rstd, int64_t rows, int d, float eps, int dtype, float drop_p, uint64_t seed,
+                              uint32_t site, void* stream) {
+  TXL_CHECK_ARG(rows > 0 && d % 32 == 0 && d <= 32 * LN_MAX_PER_LANE, "add_ln_fwd: d=%d must be a multiple of 32, <= 1024", d);
+  int grid = (int)imin64(cdiv64(rows, 8), (int64_t)txl_num_sms() * 8);
+  float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  DISPATCH_DTYPE(dtype, (add_ln_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)r, gamma, beta, (T*)y, (T*)z, mean, rstd, rows, d, eps, drop_p, ik, seed, site)));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
+template <typename T>
+__global__ void add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __restrict__ gamma,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd, T* dx_out, int accumulate_dx,
+                                  T* dr_out, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int d, float p,
+                                  float inv_keep, uint64_t seed, uint32_t site) {
+  extern __shared__ float sm[];  // [2][d] block partials
+  int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
+  int per = d / 32;
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  float ag[LN_MAX_PER_LANE], ab[LN_MAX_PER_LANE];
+#pragma unroll
+  for (int e = 0; e < LN_MAX_PER_LANE; ++e) { ag[e] = 0.f; ab[e] = 0.f; }
+  for (int64_t row = warp; row < rows; row += (int64_t)gridDim.x * wpb) {
+    float mu = mean[row], rs = rstd[row];
+    float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < LN_MAX_PER_LANE; ++e) {
+      if (e < per) {
+        int c = e * 32 + lane;
+        float dyv = to_f32(dy[row * d + c]);
+        xh[e] = (to_f32(z[row * d + c]) - mu) * rs;
+        g[e] = dyv * gamma[c];
+        s1 += g[e]; s2 += g[e] * xh[e];
+        ag[e] += dyv * xh[e]; ab[e] += dyv;
+      }
+    }
+    s1 = warp_sum(s1) / d; s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int e = 0; e < LN_MAX_PER_LANE; ++e) {
+      if (e < per) {
+        int c = e * 32 + lane;
+        float dz = rs * (g[e] - s1 - xh[e] * s2);
+        if (dr_out) {
+          float dm = p > 0.f ? dropout_scale(seed, site, (uint64_t)(row * d + c), p, inv_keep) : 1.f;
+          dr_out[row * d + c] = from_f32<T>(dz * dm);
+        }
+        if (dx_out) {
+          float acc = accumulate_dx ? to_f32(dx_out[row * d + c]) : 0.f;
+          dx_out[row * d + c] = from_f32<T>(dz + acc);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < LN_MAX_PER_LANE; ++e) {
+    if (e < per) {
+      int c = e * 32 + lane;
+      atomicAdd(&sm[c], ag[e]);
+      atomicAdd(&sm[d + c], ab[e]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    if (dgamma) atomicAdd(&dgamma[c], sm[c]);
+    if (dbeta) atomicAdd(&dbeta[c], sm[d + c]);
+  }
+}
+extern "C" int txl_add_ln_bwd(const void* dy, const void* z, const float* gamma, const float* mean, const float* rstd,
+                              void* dx_out, int accumulate_dx, void* dr_out, float* dgamma, float* dbeta, int64_t rows, int d,
+                              int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream) {
+  TXL_CHECK_ARG(rows > 0 && d % 32 == 0 && d <= 32 * LN_MAX_PER_LANE, "add_ln_bwd: d=%d must be a multiple of 32, <= 1024", d);
+  // dx_out may alias dy only when it is the same element-for-element buffer (each element is read before written by its own lane)
+  int grid = (int)imin64(cdiv64(rows, 8), (int64_t)txl_num_sms() * 4);
+  float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  size_t smem = 2 * (size_t)d * sizeof(float);
+  DISPATCH_DTYPE(dtype, (add_ln_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)dy, (const T*)z, gamma, mean, rstd, (T*)dx_out, accumulate_dx, (T*)dr_out, dgamma, dbeta, rows, d, drop_p, ik, seed, site)));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
+// ------------------------------------------------------------------ column sums (bias gradients)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ X, int64_t M, int64_t N, int64_t ldx, float* __restrict__ out, int rows_per_block) {
+  int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int64_t m0 = (int64_t)blockIdx.y * rows_per_block, m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  float s = 0.f;
+  for (int64_t m = m0; m < m1; ++m) s += to_f32(X[m * ldx + n]);
+  atomicAdd(&out[n], s);
+}
+extern "C" int txl_colsum(const void* X, int64_t M, int64_t N, int64_t ldx, int dtype, float* out, void* stream) {
+  TXL_CHECK_ARG(X && out && M > 0 && N > 0 && ldx >= N, "colsum: bad args");
+  int rpb = 256;
+  dim3 grid((unsigned)cdiv64(N, 128), (unsigned)cdiv64(M, rpb));
+  DISPATCH_DTYPE(dtype, (colsum_kernel<T><<<grid, 128, 0, (cudaStream_t)stream>>>((const T*)X, M, N, ldx, out, rpb)));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
+// ------------------------------------------------------------------ plain dropout
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, float p, float inv_keep, uint64_t seed, uint32_t site) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x)
+    y[idx] = from_f32<T>(to_f32(x[idx]) * dropout_scale(seed, site, (uint64_t)idx, p, inv_keep));
+}
+extern "C" int txl_dropout(const void* x, void* y, int64_t n, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream) {
+  TXL_CHECK_ARG(n > 0 && drop_p >= 0.f && drop_p < 1.f, "dropout: bad args");
+  if (drop_p == 0.f) {
+    if (x != y) TXL_CUDA(cudaMemcpyAsync(y, x, n * (dtype == TXL_F32 ? 4 : 2), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TXL_OK;
+  }
+  int grid = (int)imin64(cdiv64(n, 256), (int64_t)txl_num_sms() * 16);
+  DISPATCH_DTYPE(dtype, (dropout_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, n, drop_p, 1.f / (1.f - drop_p), seed, site)));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
+// ------------------------------------------------------------------ log-softmax + NLL (one warp per row; V is the small music vocab)
+template <typename T>
+__global__ void lsm_nll_fwd_kernel(const T* __restrict__ logits, int64_t ldl, const int64_t* __restrict__ labels, float* __restrict__ losses,
+                                   float* __restrict__ lse_out, float* __restrict__ logprobs, int64_t* __restrict__ argmax, int64_t N, int V) {
+  int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
+  for (int64_t row = warp; row < N; row += (int64_t)gridDim.x * wpb) {
+    const T* l = logits + row * ldl;
+    float m = -INFINITY; int am = 0x7fffffff;
+    for (int v = lane; v < V; v += 32) {
+      float x = to_f32(l[v]);
+      if (x > m) { m = x; am = v; }   // first max per lane (v ascending)
+    }
+    float mm = warp_max(m);
+    // lowest index among lanes holding the max (torch.argmax returns the first maximal index)
+    int cand = (m == mm) ? am : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) s += expf(to_f32(l[v]) - mm);
+    float lse = mm + logf(warp_sum(s));
+    if (logprobs)
+      for (int v = lane; v < V; v += 32) logprobs[row * V + v] = to_f32(l[v]) - lse;
+    if (lane == 0) {
+      if (lse_out) lse_out[row] = lse;
+      if (argmax) argmax[row] = cand;
+      if (losses) {
+        int64_t lab = labels ? labels[row] : -100;
+        losses[row] = (lab >= 0 && lab < V) ? lse - to_f32(l[lab]) : 0.f;
+      }
+    }
+  }
+}
+extern "C" int txl_logsoftmax_nll_fwd(const void* logits, int64_t ldl, const int64_t* labels, float* losses, float* lse,
+                                      float* logprobs, int64_t* argmax, int64_t N, int V, int dtype, void* stream) {
+  TXL_CHECK_ARG(N > 0 && V > 0 && ldl >= V, "lsm_nll_fwd: bad sizes");
+  int grid = (int)imin64(cdiv64(N, 8), (int64_t)txl_num_sms() * 8);
+  DISPATCH_DTYPE(dtype, (lsm_nll_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)logits, ldl, labels, losses, lse, logprobs, argmax, N, V)));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+template <typename T>
+__global__ void lsm_nll_bwd_kernel(T* __restrict__ logits, int64_t ldl, const int64_t* __restrict__ labels, const float* __restrict__ lse,
+                                   const float* __restrict__ grow, int64_t N, int V) {
+  int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
+  for (int64_t row = warp; row < N; row += (int64_t)gridDim.x * wpb) {
+    T* l = logits + row * ldl;
+    int64_t lab = labels[row];
+    bool valid = lab >= 0 && lab < V;
+    float g = valid ? grow[row] : 0.f, ls = lse[row];
+    for (int v = lane; v < ldl; v += 32) {
+      float out = 0.f;
+      if (v < V && g != 0.f) out = (expf(to_f32(l[v]) - ls) - (v == lab ? 1.f : 0.f)) * g;
+      l[v] = from_f32<T>(out);
+    }
+  }
+}
+extern "C" int txl_logsoftmax_nll_bwd(void* logits, int64_t ldl, const int64_t* labels, const float* lse, const float* grow,
+                                      int64_t N, int V, int dtype, void* stream) {
+  TXL_CHECK_ARG(N > 0 && V > 0 && ldl >= V, "lsm_nll_bwd: bad sizes");
+  int grid = (int)imin64(cdiv64(N, 8), (int64_t)txl_num_sms() * 8);
+  DISPATCH_DTYPE(dtype, (lsm_nll_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((T*)logits, ldl, labels, lse, grow, N, V)));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
+// loss = mean(losses[losses != 0])  — single block, deterministic tree order
+__global__ void masked_mean_kernel(const float* __restrict__ losses, int64_t N, float* loss_out, float* count_out) {
+  __shared__ double ssum[32];
+  __shared__ double scnt[32];
+  double s = 0.0, c = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    float v = losses[i];
+    if (v != 0.f) { s += (double)v; c += 1.0; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+  if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; scnt[threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0.0, C = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { S += ssum[w]; C += scnt[w]; }
+    *loss_out = (float)(S / C);   // C == 0 -> NaN, as torch's empty mean
+    if (count_out) *count_out = (float)C;
+  }
+}
+extern "C" int txl_masked_mean(const float* losses, int64_t N, float* loss_out, float* count_out, void* stream) {
+  TXL_CHECK_ARG(N > 0, "masked_mean: N");
+  masked_mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(losses, N, loss_out, count_out);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
+// ------------------------------------------------------------------ casts / transposes / layout
+__global__ void cast_f2b_kernel(const float* __restrict__ s, bf16* __restrict__ d, int64_t n) {
+  int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    float4 v = *reinterpret_cast<const float4*>(s + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(d + i) = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t t = n & ~(int64_t)3; t < n; ++t) d[t] = __float2bfloat16_rn(s[t]);
+}
+__global__ void cast_b2f_kernel(const bf16* __restrict__ s, float* __restrict__ d, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = __bfloat162float(s[i]);
+}
+extern "C" int txl_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  TXL_CHECK_ARG(n > 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0), "cast: alignment");
+  int grid = (int)imin64(cdiv64(n, 1024), (int64_t)txl_num_sms() * 16);
+  cast_f2b_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+extern "C" int txl_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
+  TXL_CHECK_ARG(n > 0, "cast: n");
+  int grid = (int)imin64(cdiv64(n, 256), (int64_t)txl_num_sms() * 16);
+  cast_b2f_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+template <typename T>
+__global__ void transpose_kernel(const T* __restrict__ A, T* __restrict__ B, int64_t rows, int64_t cols) {
+  __shared__ T tile[32][33];
+  int64_t c0 = blockIdx.x * 32ll, r0 = blockIdx.y * 32ll;
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    int64_t r = r0 + dy, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[dy][threadIdx.x] = A[r * cols + c];
+  }
+  __syncthreads();
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    int64_t c = c0 + dy, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) B[c * rows + r] = tile[threadIdx.x][dy];
+  }
+}
+extern "C" int txl_transpose(const void* A, void* B, int64_t rows, int64_t cols, int dtype, void* stream) {
+  TXL_CHECK_ARG(rows > 0 && cols > 0, "transpose: sizes");
+  dim3 grid((unsigned)cdiv64(cols, 32), (unsigned)cdiv64(rows, 32)), block(32, 8);
+  DISPATCH_DTYPE(dtype, (transpose_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)A, (T*)B, rows, cols)));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+// (rows,B,d) time-major <-> (B,rows,d) batch-major, with dtype conversion
+template <typename TS, typename TD>
+__global__ void tm_bm_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int rows, int B, int d, int to_bm) {
+  int64_t total = (int64_t)rows * B * d;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(idx % d); int64_t rb = idx / d;
+    if (to_bm) {  // dst index is (b, r, c)
+      int r = (int)(rb % rows), b = (int)(rb / rows);
+      dst[idx] = from_f32<TD>(to_f32(src[((int64_t)r * B + b) * d + c]));
+    } else {      // dst index is (r, b, c)
+      int b = (int)(rb % B), r = (int)(rb / B);
+      dst[idx] = from_f32<TD>(to_f32(src[((int64_t)b * rows + r) * d + c]));
+    }
+  }
+}
+static int tm_bm(const void* src, void* dst, int rows, int B, int d, int ds, int dd, int to_bm, void* stream) {
+  TXL_CHECK_ARG(rows > 0 && B > 0 && d > 0, "tm_bm: sizes");
+  int grid = (int)imin64(cdiv64((int64_t)rows * B * d, 256), (int64_t)txl_num_sms() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ds == TXL_F32 && dd == TXL_F32) tm_bm_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, rows, B, d, to_bm);
+  else if (ds == TXL_F32 && dd == TXL_BF16) tm_bm_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, (bf16*)dst, rows, B, d, to_bm);
+  else if (ds == TXL_BF16 && dd == TXL_F32) tm_bm_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, (float*)dst, rows, B, d, to_bm);
+  else if (ds == TXL_BF16 && dd == TXL_BF16) tm_bm_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, rows, B, d, to_bm);
+  else { txl_set_error("tm_bm: bad dtype"); return TXL_EINVAL; }
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+extern "C" int txl_tm_to_bm(const void* src, void* dst, int rows, int B, int d, int ds, int dd, void* stream) { return tm_bm(src, dst, rows, B, d, ds, dd, 1, stream); }
+extern "C" int txl_bm_to_tm(const void* src, void* dst, int rows, int B, int d, int ds, int dd, void* stream) { return tm_bm(src, dst, rows, B, d, ds, dd, 0, stream); }
+
+// ------------------------------------------------------------------ optimiser
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, float* out) {
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += g[i] * g[i];
+  s = warp_sum(s);
+  __shared__ float sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+extern "C" int txl_sumsq(const float* g, int64_t n, float* out, void* stream) {
+  TXL_CHECK_ARG(n > 0, "sumsq: n");
+  int grid = (int)imin64(cdiv64(n, 1024), (int64_t)txl_num_sms() * 4);
+  sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, n, out);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             const uint8_t* __restrict__ decay_mask, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2, const float* __restrict__ grad_scale_dev, bf16* __restrict__ shadow) {
+  float gs = grad_scale_dev ? *grad_scale_dev : 1.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gs, pi = p[i];
+    if (!decay_mask || decay_mask[i]) pi *= (1.f - lr * wd);          // torch.optim.AdamW: decoupled decay first
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    pi -= (lr / bc1) * mi / denom;
+    p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+  }
+}
+extern "C" int txl_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* decay_mask, int64_t n, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_scale_dev,
+                              void* bf16_shadow, void* stream) {
+  TXL_CHECK_ARG(n > 0 && step >= 1, "adamw: bad args");
+  float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  int grid = (int)imin64(cdiv64(n, 256), (int64_t)txl_num_sms() * 16);
+  adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, decay_mask, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale_dev, (bf16*)bf16_shadow);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}

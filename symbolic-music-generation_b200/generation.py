@@ -1,0 +1,92 @@
+"""`generate` surface of the boundary: greedy search and sampling (temperature / top-k / top-p, renormalised), the
+modes `musicnlp/trainer/eval.py:277-333` drives, following HF 4.25 `GenerationMixin.greedy_search` / `sample`
+(SURVEY.md Appendix A.7): one forward per new token fed through `prepare_inputs_for_generation(input_ids, past=mems)`,
+log-prob scores of the last position, warpers in HF order, eos/pad bookkeeping, stop at `max_length`.
+
+Beam search, contrastive search, typical-p and repetition penalty are outside the measured path and raise.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_tokens: Optional[int] = None, do_sample: Optional[bool] = None,
+             early_stopping=None, top_k: Optional[int] = None, top_p: Optional[float] = None, temperature: Optional[float] = None,
+             typical_p: Optional[float] = None, repetition_penalty: Optional[float] = None, renormalize_logits: Optional[bool] = None,
+             num_beams: Optional[int] = None, num_beam_groups: Optional[int] = None, diversity_penalty=None, penalty_alpha=None,
+             num_return_sequences: Optional[int] = None, eos_token_id='config', pad_token_id='config', generator=None,
+             return_step_scores: bool = False, use_decode_cache: bool = True, **unused):
+    cfg = model.config
+    if input_ids is None:
+        raise ValueError('generate needs input_ids (the reference always passes a tokenised prompt, eval.py:276)')
+    if (num_beams or 1) > 1 or (num_beam_groups or 1) > 1 or penalty_alpha:
+        raise NotImplementedError('beam / diverse-beam / contrastive search are not on the measured path (SURVEY §8b)')
+    if (typical_p is not None and typical_p < 1.0) or (repetition_penalty is not None and repetition_penalty != 1.0):
+        raise NotImplementedError('typical_p / repetition_penalty warpers are not implemented')
+    do_sample = bool(cfg.do_sample if do_sample is None else do_sample)
+    top_k = cfg.top_k if top_k is None else top_k             # HF: config default top_k=50 applies when the caller passes none
+    top_p = cfg.top_p if top_p is None else top_p
+    temperature = cfg.temperature if temperature is None else temperature
+    nret = num_return_sequences or 1
+    if eos_token_id == 'config':
+        eos_token_id = cfg.eos_token_id
+    if pad_token_id == 'config':
+        pad_token_id = cfg.pad_token_id
+    if pad_token_id is None and eos_token_id is not None:
+        pad_token_id = eos_token_id                            # HF: "Setting pad_token_id to eos_token_id"
+    model._ensure_engine()
+    dev = model._flat.device
+    ids = input_ids.to(dev).long()
+    if nret > 1:
+        ids = ids.repeat_interleave(nret, dim=0)
+    if max_length is None:
+        max_length = ids.shape[1] + max_new_tokens if max_new_tokens is not None else cfg.max_length
+    B = ids.shape[0]
+    was_training = model.training
+    model.eval()
+    unfinished = torch.ones(B, dtype=torch.int64, device=dev)
+    out_ids = torch.empty(B, max_length, dtype=torch.int64, device=dev)
+    cur = ids.shape[1]
+    out_ids[:, :cur] = ids
+    step_scores = []
+    past = None
+    decoder = None
+    try:
+        with torch.no_grad():
+            while cur < max_length:
+                if decoder is not None:
+                    scores = decoder.step(out_ids[:, cur - 1])
+                else:
+                    inputs = model.prepare_inputs_for_generation(out_ids[:, :cur], past=past)
+                    out = model(**inputs, return_dict=True)
+                    scores = out.logits[:, -1, :].contiguous()
+                    past = out.mems
+                    if use_decode_cache and hasattr(model, '_make_decoder'):
+                        decoder = model._make_decoder(past)
+                u = torch.rand(B, device=dev, generator=generator) if do_sample else None
+                nxt, _, warped = ops.sample(scores, do_sample, temperature, top_k, top_p, u, want_warped=return_step_scores and do_sample)
+                if return_step_scores:
+                    step_scores.append(warped if do_sample else scores)
+                if eos_token_id is not None:
+                    nxt = nxt * unfinished + pad_token_id * (1 - unfinished)
+                    unfinished = unfinished * (nxt != eos_token_id).long()
+                out_ids[:, cur] = nxt
+                cur += 1
+                if eos_token_id is not None and (cur % 64 == 0 or cur == max_length) and int(unfinished.max().item()) == 0:
+                    break
+    finally:
+        if was_training:
+            model.train()
+    result = out_ids[:, :cur]
+    if eos_token_id is not None and cur > ids.shape[1]:
+        # HF stops right after the step at which every sequence has emitted eos; we only poll every 64 steps, so trim.
+        gen = result[:, ids.shape[1]:]
+        is_eos = gen == eos_token_id
+        if bool(is_eos.any(dim=1).all().item()):
+            first = torch.where(is_eos, torch.arange(gen.shape[1], device=dev).expand_as(gen), gen.shape[1]).min(dim=1).values
+            result = result[:, :ids.shape[1] + int(first.max().item()) + 1]
+    return (result, step_scores) if return_step_scores else result

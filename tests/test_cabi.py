@@ -1,0 +1,102 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads, and exports exactly what include/txl_b200.h declares;
+the Python binding table matches it; and the product fails loudly without a GPU (no CPU / oracle fallback)."""
+import ctypes
+import importlib
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = 'symbolic-music-generation_b200'
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, 'include', 'txl_b200.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return set(re.findall(r'\b(txl_[a-z0-9_]+)\s*\(', txt))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/txl_b200.h but not exported'
+
+
+def test_binding_table_matches_header(built_lib):
+    L = importlib.import_module(PKG + '._lib')
+    assert set(L.SIGNATURES) == _declared()
+    lib = L.load()
+    assert lib.txl_version() >= 100
+
+
+def test_sass_is_sm100a(built_lib):
+    import subprocess
+    out = subprocess.run(['cuobjdump', '-lelf', built_lib], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+
+
+def test_product_does_not_import_oracle():
+    pkgdir = os.path.join(ROOT, PKG)
+    for fn in os.listdir(pkgdir):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkgdir, fn)).read()
+            assert 'import oracle' not in src and 'from oracle' not in src, fn
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_fails_loudly_without_gpu(pkg, built_lib):
+    cfg = pkg.MyTransfoXLConfig('debug', vocab_size=50, cutoffs=[])
+    m = pkg.MyTransfoXLLMHeadModel(cfg)
+    with pytest.raises(pkg.TxlError):
+        m(input_ids=torch.zeros(1, 4, dtype=torch.long))
+
+
+def test_config_mirrors_reference_presets(pkg):
+    c = pkg.MyTransfoXLConfig('small', vocab_size=1190, max_length=1024, mem_len=1024, cutoffs=[])
+    assert (c.d_model, c.n_head, c.n_layer, c.d_head, c.d_inner, c.mem_len, c.clamp_len, c.div_val) == (512, 8, 12, 64, 2048, 1024, 1024, 1)
+    assert c.same_length and c.untie_r and not c.pre_lnorm and c.eos_token_id == 0 and c.dropout == 0.1
+    assert c.max_length_ == 1024 and c.model_meta['seg_len'] == 1024
+
+    class Tok:
+        vocab_size = 1190
+    assert pkg.MyTransfoXLConfig('small', tokenizer=Tok()).cutoffs == [1000]
+    Tok.vocab_size = 422
+    assert pkg.MyTransfoXLConfig('small', tokenizer=Tok()).cutoffs == []
+    with pytest.raises(NotImplementedError):
+        pkg.MyTransfoXLLMHeadModel(pkg.MyTransfoXLConfig('debug', vocab_size=1190, cutoffs=[1000]))
+
+
+def test_state_dict_roundtrip_with_oracle(pkg, tmp_path):
+    from oracle.txl_ref import RefConfig, RefTransfoXLLMHeadModel
+    kw = dict(vocab_size=37, d_model=32, n_head=4, n_layer=2, d_head=8, d_inner=48, mem_len=4, clamp_len=8)
+    ref = RefTransfoXLLMHeadModel(RefConfig(d_embed=32, **kw))
+    m = pkg.MyTransfoXLLMHeadModel(pkg.MyTransfoXLConfig('debug', cutoffs=[], d_embed=32, **kw))
+    assert set(m.state_dict()) == set(ref.state_dict())
+    assert m.num_parameters() == ref.num_parameters()
+    m.load_state_dict(ref.state_dict())
+    for k, v in ref.state_dict().items():
+        assert torch.equal(m.state_dict()[k], v), k
+    m.save_pretrained(tmp_path)
+    m2 = pkg.MyTransfoXLLMHeadModel.from_pretrained(tmp_path)
+    for k, v in m.state_dict().items():
+        assert torch.equal(m2.state_dict()[k], v), k
+    assert m2.config.mem_len == 4 and m2.config.max_length_ == m.config.max_length_
+
+
+def test_output_container(pkg):
+    o = pkg.TransfoXLLMHeadModelOutput(loss=torch.tensor(1.0), prediction_scores=(), losses=torch.zeros(2, 3), mems=[1])
+    assert o['loss'] == 1.0 and o.logits == () and list(o.keys()) == ['losses', 'prediction_scores', 'mems', 'loss']
+    assert o[0] is o.losses
+
+
+def test_prepare_inputs_for_generation(pkg):
+    m = pkg.MyTransfoXLLMHeadModel(pkg.MyTransfoXLConfig('debug', vocab_size=50, cutoffs=[]))
+    ids = torch.arange(10).view(2, 5)
+    assert m.prepare_inputs_for_generation(ids)['input_ids'] is ids
+    past = [torch.zeros(3, 2, 4)]
+    out = m.prepare_inputs_for_generation(ids, past=past)
+    assert out['mems'] is past and out['input_ids'].tolist() == [[4], [9]]

@@ -1,0 +1,160 @@
+"""GPU parity of the full hot path (forward, loss, backward, mems, generation) against the CPU oracle on identical
+synthetic ids and identical random-init weights (north_star): 1e-4 relative in fp32 mode, 1e-2 relative in bf16,
+greedy decode token-identical in fp32 mode."""
+import pytest
+import torch
+
+from conftest import make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(V, B, T, seed=77, pad=True):
+    g = torch.Generator().manual_seed(seed)            # musicnlp/util/config.json:135
+    ids = torch.randint(0, V, (B, T), generator=g)
+    labels = ids.clone()
+    if pad and B > 1:
+        labels[1, T - T // 4:] = -100
+    return ids, labels
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-6)).item()
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 1e-2)])
+def test_forward_loss_logits_mems(pkg, mode, tol):
+    ref, model = make_pair(pkg, mode)
+    ids, labels = _batch(422, 3, 48)
+    ref.eval(); model.eval()
+    with torch.no_grad():
+        ro = ref(input_ids=ids, labels=labels.clone())
+        out = model(input_ids=ids.cuda(), labels=labels.cuda())
+    assert out.losses.shape == (3, 47) and out.logits.shape == (3, 48, 422)
+    valid = ro.losses != 0
+    assert torch.equal(out.losses.cpu() != 0, valid)
+    rel = ((out.losses.cpu() - ro.losses).abs() / ro.losses.abs().clamp(min=1e-3))[valid].max().item()
+    assert rel < tol, rel
+    assert abs(out.loss.item() - ro.loss.item()) / ro.loss.item() < tol
+    lrel = ((out.logits.float().cpu() - ro.logits).abs() / ro.logits.abs()).max().item()     # log-probs are ~ -6, never 0
+    assert lrel < tol, lrel
+    assert len(out.mems) == 2 and tuple(out.mems[0].shape) == (32, 3, 128)
+    assert _rel(out.mems[1].float().cpu(), ro.mems[1]) < tol * 3
+    # second segment with carried mems (both our own mems object and plain HF-style tensors)
+    ids2, _ = _batch(422, 3, 20, seed=78)
+    with torch.no_grad():
+        r2 = ref(input_ids=ids2, mems=ro.mems)
+        o2 = model(input_ids=ids2.cuda(), mems=out.mems)
+        o3 = model(input_ids=ids2.cuda(), mems=[m.cuda() for m in ro.mems])
+    assert ((o2.logits.float().cpu() - r2.logits).abs() / r2.logits.abs()).max().item() < tol * 2
+    assert ((o3.logits.float().cpu() - r2.logits).abs() / r2.logits.abs()).max().item() < tol * 2
+    assert _rel(o2.mems[0].float().cpu(), r2.mems[0]) < tol * 3
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 2e-4), ('bf16', 3e-2)])
+def test_backward_grads(pkg, mode, tol):
+    ref, model = make_pair(pkg, mode)
+    ref.train(); model.train()
+    ids, labels = _batch(422, 3, 40)
+    mems = [0.5 * torch.randn(32, 3, 128) for _ in range(2)]
+    ro = ref(input_ids=ids, mems=mems, labels=labels.clone())
+    ro.loss.backward()
+    out = model(input_ids=ids.cuda(), mems=[m.cuda() for m in mems], labels=labels.cuda())
+    assert out.logits == ()                                 # training mode returns no prediction scores (reference :194)
+    out.loss.backward()
+    assert abs(out.loss.item() - ro.loss.item()) / ro.loss.item() < tol
+    got = dict(model.named_parameters())
+    worst = 0.0
+    for name, p in ref.named_parameters():
+        g = got[name].grad
+        assert g is not None, name
+        r = _rel(g.float().cpu(), p.grad)
+        worst = max(worst, r)
+        assert r < tol * (3 if 'bias' in name or 'layer_norm' in name else 1) + (0.02 if mode == 'bf16' else 0), (name, r)
+    # second backward accumulates into .grad like autograd does
+    out2 = model(input_ids=ids.cuda(), mems=[m.cuda() for m in mems], labels=labels.cuda())
+    out2.loss.backward()
+    name = 'transformer.layers.0.pos_ff.CoreNet.0.weight'
+    assert _rel(got[name].grad.float().cpu(), 2 * dict(ref.named_parameters())[name].grad) < tol * 2 + (0.02 if mode == 'bf16' else 0)
+
+
+def test_backward_no_mems_and_losses_grad(pkg):
+    """mems=None (zero mems, the reference's training behaviour) and gradients flowing through `losses` rather than `loss`."""
+    ref, model = make_pair(pkg, 'fp32', n_layer=1)
+    ref.train(); model.train()
+    ids, labels = _batch(422, 2, 24)
+    w = torch.rand(2, 23)
+    (ref(input_ids=ids, labels=labels.clone()).losses * w).sum().backward()
+    (model(input_ids=ids.cuda(), labels=labels.cuda()).losses * w.cuda()).sum().backward()
+    got = dict(model.named_parameters())
+    for name, p in ref.named_parameters():
+        assert _rel(got[name].grad.cpu(), p.grad) < 5e-4, name
+
+
+def test_all_pad_first_row_fixup(pkg):
+    ref, model = make_pair(pkg, 'fp32', n_layer=1)
+    ids, labels = _batch(422, 2, 12, pad=False)
+    labels[0, 1:] = -100
+    lab_gpu = labels.cuda()
+    model.train()
+    out = model(input_ids=ids.cuda(), labels=lab_gpu)
+    assert lab_gpu[0, 1].item() == model.config.eos_token_id      # caller's labels mutated in place (reference :179-182)
+    ro = ref.train()(input_ids=ids, labels=labels)
+    assert abs(out.loss.item() - ro.loss.item()) < 1e-4 * ro.loss.item()
+
+
+def test_errors(pkg):
+    _, model = make_pair(pkg, 'fp32', n_layer=1)
+    with pytest.raises(ValueError):
+        model()
+    with pytest.raises(NotImplementedError):
+        model(input_ids=torch.zeros(1, 4, dtype=torch.long).cuda(), output_attentions=True)
+    with pytest.raises(RuntimeError):
+        model(input_ids=torch.zeros(2, 4, dtype=torch.long).cuda(), labels=torch.zeros(2, 5, dtype=torch.long).cuda())
+    with pytest.raises(pkg.TxlError):
+        model.cpu()(input_ids=torch.zeros(1, 4, dtype=torch.long))
+
+
+def test_tuple_outputs(pkg):
+    _, model = make_pair(pkg, 'fp32', n_layer=1)
+    ids, labels = _batch(422, 2, 10)
+    model.eval()
+    with torch.no_grad():
+        tup = model(input_ids=ids.cuda(), labels=labels.cuda(), return_dict=False)
+    assert len(tup) == 4 and tup[0].shape == (2, 9) and tup[1].shape == (2, 10, 422) and tup[3].dim() == 0   # (losses, scores, mems, loss)
+
+
+def test_greedy_decode_token_identical_fp32(pkg):
+    """north_star: greedy decode token-identical for 256 tokens in fp32 mode."""
+    ref, model = make_pair(pkg, 'fp32', mem_len=64, n_layer=2)
+    ids, _ = _batch(422, 2, 8, pad=False)
+    want = ref.generate(ids, max_length=8 + 256, eos_token_id=None)
+    got = model.generate(input_ids=ids.cuda(), max_length=8 + 256, do_sample=False, eos_token_id=None)
+    assert got.shape == want.shape
+    assert torch.equal(got.cpu(), want)
+
+
+def test_generate_sampling_and_eos(pkg):
+    ref, model = make_pair(pkg, 'fp32', mem_len=16, n_layer=1)
+    ids, _ = _batch(422, 4, 5, pad=False)
+    g = torch.Generator(device='cuda').manual_seed(3)
+    out, scores = model.generate(input_ids=ids.cuda(), max_length=40, do_sample=True, top_k=8, top_p=0.9, temperature=0.9,
+                                 renormalize_logits=True, generator=g, return_step_scores=True, eos_token_id=None)
+    assert out.shape == (4, 40) and torch.equal(out[:, :5].cpu(), ids)
+    for s in scores[:5]:
+        kept = (s > -float('inf')).sum(-1)
+        assert (kept >= 1).all() and (kept <= 8).all()
+        torch.testing.assert_close(s.exp().sum(-1), torch.ones(4, device='cuda'), rtol=1e-4, atol=1e-4)
+    # first-step warped scores equal the oracle's warpers applied to the oracle's log-probs
+    ref.eval()
+    with torch.no_grad():
+        r = ref(input_ids=ids).logits[:, -1]
+    rw = ref.warp_scores(r, 0.9, 8, 0.9, True)
+    assert torch.equal(rw > -float('inf'), scores[0].cpu() > -float('inf'))
+    # eos handling: default eos_token_id = config.eos_token_id = 0; finished rows emit pad (= eos)
+    out2 = model.generate(input_ids=ids.cuda(), max_length=200, do_sample=True, top_k=0, temperature=3.0)
+    gen = out2[:, 5:].cpu()
+    for row in gen:
+        z = (row == 0).nonzero()
+        if len(z):
+            assert (row[z[0, 0]:] == 0).all()

@@ -1,0 +1,279 @@
+"""GPU parity tests of the individual C-ABI ops against plain torch fp32 / the oracle's literal constructions."""
+import math
+
+import pytest
+import torch
+
+from oracle.txl_ref import RefTransfoXLLMHeadModel, literal_index_maps
+
+pytestmark = pytest.mark.gpu
+DT = {'fp32': torch.float32, 'bf16': torch.bfloat16}
+
+
+@pytest.mark.parametrize('T,M,ML,C,same', [(7, 5, 5, 3, 1), (6, 6, 6, 100, 1), (1, 8, 8, 4, 1), (5, 0, 4, 2, 1), (4, 2, 6, 3, 1), (9, 4, 4, 6, 1),
+                                            (3, 9, 4, 0, 1), (1, 1024, 1024, 1024, 1), (64, 64, 64, 16, 1), (256, 256, 256, 128, 1), (8, 4, 4, 2, 0),
+                                            (512, 512, 512, 1024, 1), (128, 0, 128, 64, 1)])
+def test_index_maps_bit_exact(ops, T, M, ML, C, same):
+    """Integer mask / rel-shift indexing of the CUDA kernels == HF's pad/reshape + triu/tril, bit for bit."""
+    masked, ridx, lo, hi = ops.relattn_index_map(T, M, ML, C, same)
+    mask_ref, ridx_ref = literal_index_maps(T, M, ML, C, bool(same))
+    masked, ridx = masked.cpu(), ridx.cpu().long()
+    assert torch.equal(masked != 0, mask_ref != 0)
+    live = mask_ref == 0
+    assert torch.equal(ridx[live], ridx_ref[live])
+    assert (ridx[~live] == -1).all()
+    first = torch.where(live, torch.arange(M + T).expand(T, -1), M + T).min(1).values
+    last = torch.where(live, torch.arange(M + T).expand(T, -1), -1).max(1).values
+    assert torch.equal(lo.cpu().long(), first) and torch.equal(hi.cpu().long(), last)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('M,N,K,tA,tB', [(70, 50, 33, 0, 1), (128, 96, 64, 0, 0), (65, 130, 17, 1, 0), (64, 64, 128, 1, 1), (300, 257, 100, 0, 1)])
+def test_gemm_simt_shapes(ops, mode, M, N, K, tA, tB):
+    torch.manual_seed(0)
+    dt = DT[mode]
+    A = torch.randn((K, M) if tA else (M, K), device='cuda').to(dt)
+    B = torch.randn((N, K) if tB else (K, N), device='cuda').to(dt)
+    ref = (A.float().t() if tA else A.float()) @ (B.float().t() if tB else B.float())
+    out = ops.gemm(A, B, transA=bool(tA), transB=bool(tB), out_dtype=torch.float32)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-3 if mode == 'fp32' else 1e-3)
+
+
+def test_gemm_epilogues(ops):
+    torch.manual_seed(1)
+    A, B = torch.randn(100, 48, device='cuda'), torch.randn(72, 48, device='cuda')
+    bias = torch.randn(72, device='cuda')
+    ref = torch.relu(A @ B.t() + bias)
+    cs = torch.zeros(72, device='cuda')
+    out = ops.gemm(A, B, transB=True, bias=bias, relu=True, colsum=cs)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(cs, ref.sum(0), rtol=1e-4, atol=1e-3)
+    acc = torch.ones(100, 72, device='cuda')
+    ops.gemm(A, B, transB=True, out=acc, accumulate=True)
+    torch.testing.assert_close(acc, 1 + A @ B.t(), rtol=1e-4, atol=1e-4)
+    aux = torch.randn(100, 72, device='cuda')
+    out = ops.gemm(A, B, transB=True, mask_pos_aux=aux)
+    torch.testing.assert_close(out, (A @ B.t()) * (aux > 0), rtol=1e-4, atol=1e-4)
+    # strided views (column slices) as operands/outputs
+    big = torch.zeros(100, 200, device='cuda')
+    ops.gemm(A, B, transB=True, out=big[:, 64:136])
+    torch.testing.assert_close(big[:, 64:136], A @ B.t(), rtol=1e-4, atol=1e-4)
+    assert big[:, :64].abs().sum() == 0 and big[:, 136:].abs().sum() == 0
+    # dropout: same seed/site reproduces, keeps ~1-p, scales by 1/(1-p)
+    d1 = ops.gemm(A, B, transB=True, drop_p=0.25, seed=5, site=3)
+    d2 = ops.gemm(A, B, transB=True, drop_p=0.25, seed=5, site=3)
+    assert torch.equal(d1, d2)
+    kept = d1 != 0
+    assert 0.68 < kept.float().mean().item() < 0.82
+    torch.testing.assert_close(d1[kept], ((A @ B.t()) / 0.75)[kept], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_add_ln_fwd_bwd(ops, mode):
+    torch.manual_seed(2)
+    dt = DT[mode]
+    rows, d = 77, 256
+    x = torch.randn(rows, d, device='cuda').to(dt)
+    r = torch.randn(rows, d, device='cuda').to(dt)
+    gamma = (1 + 0.1 * torch.randn(d, device='cuda')).requires_grad_()
+    beta = (0.1 * torch.randn(d, device='cuda')).requires_grad_()
+    y, z, mean, rstd = ops.add_ln_fwd(x, r, gamma.detach(), beta.detach(), 1e-5)
+    zr = (x.float() + r.float()).to(dt).float().requires_grad_()
+    yr = torch.nn.functional.layer_norm(zr, (d,), gamma, beta, 1e-5)
+    tol = dict(rtol=1e-4, atol=1e-4) if mode == 'fp32' else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(y.float(), yr, **tol)
+    dy = torch.randn(rows, d, device='cuda').to(dt)
+    yr.backward(dy.float())
+    dg, db = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
+    dx, dr = ops.add_ln_bwd(dy, z, gamma.detach(), mean, rstd, dg, db)
+    torch.testing.assert_close(dx.float(), zr.grad, **tol)
+    torch.testing.assert_close(dr.float(), zr.grad, **tol)
+    torch.testing.assert_close(dg, gamma.grad, rtol=1e-3, atol=1e-2 if mode == 'bf16' else 1e-3)
+    torch.testing.assert_close(db, beta.grad, rtol=1e-3, atol=1e-2 if mode == 'bf16' else 1e-3)
+
+
+def test_embed_posemb(ops):
+    torch.manual_seed(3)
+    E = torch.randn(50, 64, device='cuda')
+    ids = torch.randint(0, 50, (3, 7), device='cuda')
+    out = ops.embed_fwd(ids.view(-1), E, 8.0)
+    torch.testing.assert_close(out, E[ids.view(-1)] * 8.0)
+    dE = torch.zeros_like(E)
+    dout = torch.randn(21, 64, device='cuda')
+    ops.embed_bwd(ids.view(-1), dout, dE, 8.0)
+    ref = torch.zeros_like(E).index_add_(0, ids.view(-1), dout * 8.0)
+    torch.testing.assert_close(dE, ref, rtol=1e-5, atol=1e-5)
+    pos = ops.posemb_table(40, 64, torch.float32, 'cuda')
+    inv = 1 / (10000 ** (torch.arange(0.0, 64, 2.0) / 64))
+    s = torch.outer(torch.arange(40.0), inv)
+    torch.testing.assert_close(pos.cpu(), torch.cat([s.sin(), s.cos()], -1), rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_logsoftmax_nll(ops, mode):
+    torch.manual_seed(4)
+    dt = DT[mode]
+    N, V, Vp = 37, 1190, 1192
+    logits = torch.zeros(N, Vp, device='cuda', dtype=dt)
+    logits[:, :V] = torch.randn(N, V, device='cuda').to(dt)
+    labels = torch.randint(0, V, (N,), device='cuda')
+    labels[::5] = -100
+    losses, lse, lp, am = ops.logsoftmax_nll_fwd(logits, V, labels, True, True)
+    ref_lp = torch.log_softmax(logits[:, :V].float(), -1)
+    torch.testing.assert_close(lp, ref_lp, rtol=1e-5, atol=1e-5)
+    ref_loss = torch.where(labels >= 0, -ref_lp.gather(1, labels.clamp(min=0)[:, None])[:, 0], torch.zeros(N, device='cuda'))
+    torch.testing.assert_close(losses, ref_loss, rtol=1e-5, atol=1e-5)
+    assert torch.equal(am, logits[:, :V].float().argmax(-1))
+    loss, cnt = ops.masked_mean(losses)
+    torch.testing.assert_close(loss, ref_loss[ref_loss != 0].mean())
+    grow = torch.rand(N, device='cuda')
+    l2 = logits.clone()
+    ops.logsoftmax_nll_bwd(l2, V, labels, lse, grow)
+    onehot = torch.zeros(N, V, device='cuda').scatter_(1, labels.clamp(min=0)[:, None], 1.0)
+    ref = (ref_lp.exp() - onehot) * (grow * (labels >= 0))[:, None]
+    torch.testing.assert_close(l2[:, :V].float(), ref, rtol=2e-2 if mode == 'bf16' else 1e-5, atol=1e-2 if mode == 'bf16' else 1e-6)
+    assert l2[:, V:].abs().sum() == 0
+
+
+def _ref_attention(q, k, v, r, rwb, rrb, T, M, ML, C, same):
+    """Literal HF math on (B, *, H, dh) fp32 tensors, via the oracle's pad/reshape shift and uint8 mask."""
+    from oracle.txl_ref import literal_attn_mask, literal_rel_shift
+    B, _, H, dh = q.shape
+    klen = M + T
+    P = r.shape[0]
+    pos = torch.arange(klen - 1, -1, -1)
+    if C > 0:
+        pos = pos.clamp(max=C)
+    rk = r[pos]                                           # (klen, H, dh) as r_head_k
+    qi = q.permute(1, 0, 2, 3)                            # (T, B, H, dh)
+    kj, vj = k.permute(1, 0, 2, 3), v.permute(1, 0, 2, 3)
+    AC = torch.einsum('ibnd,jbnd->ijbn', qi + rwb, kj)
+    BD = literal_rel_shift(torch.einsum('ibnd,jnd->ijbn', qi + rrb, rk))
+    score = (AC + BD) / math.sqrt(dh)
+    mask = literal_attn_mask(T, M, ML, bool(same)).bool()
+    score = score.masked_fill(mask[:, :, None, None], torch.finfo(score.dtype).min)
+    prob = torch.softmax(score, dim=1)
+    vec = torch.einsum('ijbn,jbnd->ibnd', prob, vj)
+    return vec.permute(1, 0, 2, 3).reshape(B, T, H * dh)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+@pytest.mark.parametrize('B,H,dh,T,M,ML,C,same', [(2, 2, 32, 40, 40, 40, 1024, 1), (1, 3, 64, 33, 20, 20, 8, 1), (2, 2, 16, 5, 0, 4, 2, 1),
+                                                   (3, 2, 32, 1, 48, 48, 16, 1), (1, 2, 64, 70, 10, 30, 1024, 1), (2, 1, 32, 24, 8, 8, 4, 0),
+                                                   (1, 2, 128, 16, 16, 16, 64, 1)])
+def test_relattn_fwd_bwd(ops, mode, B, H, dh, T, M, ML, C, same):
+    torch.manual_seed(5)
+    dt = DT[mode]
+    d = H * dh
+    klen = M + T
+    P = ops.num_r(T, M, C)
+    qkv = (0.5 * torch.randn(B * T, 3 * d, device='cuda')).to(dt)
+    kvm = (0.5 * torch.randn(B * M, 2 * d, device='cuda')).to(dt) if M > 0 else None
+    r = (0.5 * torch.randn(P, d, device='cuda')).to(dt)
+    rwb, rrb = 0.3 * torch.randn(d, device='cuda'), 0.3 * torch.randn(d, device='cuda')
+    band = ops.make_band(T, M, ML, C, same)
+    km = kvm[:, :d] if M > 0 else None
+    vm = kvm[:, d:] if M > 0 else None
+    out, lse = ops.relattn_fwd(qkv[:, :d], km, vm, qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, B, T, H, dh, band)
+    # reference on CPU fp32 from the same (rounded) inputs
+    f = lambda t: t.float().cpu()
+    q = f(qkv[:, :d]).view(B, T, H, dh).requires_grad_()
+    kc = f(qkv[:, d:2 * d]).view(B, T, H, dh).requires_grad_()
+    vc = f(qkv[:, 2 * d:]).view(B, T, H, dh).requires_grad_()
+    if M > 0:
+        kmr = f(km).reshape(B, M, H, dh).requires_grad_()
+        vmr = f(vm).reshape(B, M, H, dh).requires_grad_()
+        k, v = torch.cat([kmr, kc], 1), torch.cat([vmr, vc], 1)
+    else:
+        k, v = kc, vc
+    rr = f(r).view(P, H, dh).requires_grad_()
+    wb, rb = f(rwb).view(H, dh).requires_grad_(), f(rrb).view(H, dh).requires_grad_()
+    ref = _ref_attention(q, k, v, rr, wb, rb, T, M, ML, C, same)
+    tol = dict(rtol=2e-4, atol=2e-5) if mode == 'fp32' else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(out.float().cpu().view(B, T, d), ref, **tol)
+    # backward
+    dout = torch.randn(B * T, d, device='cuda').to(dt)
+    ref.backward(f(dout).view(B, T, d))
+    dqkv = torch.full_like(qkv, float('nan'))
+    dkvm = torch.full_like(kvm, float('nan')) if M > 0 else None
+    dr = torch.zeros(P, d, device='cuda')
+    drwb, drrb = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
+    ops.relattn_bwd(qkv[:, :d], km, vm, qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, out, lse, dout, dqkv[:, :d],
+                    dkvm[:, :d] if M > 0 else None, dkvm[:, d:] if M > 0 else None, dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, drwb, drrb,
+                    B, T, H, dh, band)
+    btol = dict(rtol=1e-3, atol=1e-4) if mode == 'fp32' else dict(rtol=5e-2, atol=5e-2)
+    torch.testing.assert_close(f(dqkv[:, :d]).view(B, T, H, dh), q.grad, **btol)
+    torch.testing.assert_close(f(dqkv[:, d:2 * d]).view(B, T, H, dh), kc.grad, **btol)
+    torch.testing.assert_close(f(dqkv[:, 2 * d:]).view(B, T, H, dh), vc.grad, **btol)
+    if M > 0:
+        torch.testing.assert_close(f(dkvm[:, :d]).reshape(B, M, H, dh), kmr.grad, **btol)
+        torch.testing.assert_close(f(dkvm[:, d:]).reshape(B, M, H, dh), vmr.grad, **btol)
+    torch.testing.assert_close(f(dr).view(P, H, dh), rr.grad, **btol)
+    torch.testing.assert_close(f(drwb).view(H, dh), wb.grad, **btol)
+    torch.testing.assert_close(f(drrb).view(H, dh), rb.grad, **btol)
+
+
+@pytest.mark.parametrize('top_k,top_p,temp', [(0, 1.0, 1.0), (8, 1.0, 1.0), (32, 0.9, 1.0), (50, 0.5, 0.7), (0, 0.3, 1.3), (1, 1.0, 1.0)])
+def test_sampler_keep_set_and_distribution(ops, top_k, top_p, temp):
+    torch.manual_seed(6)
+    B, V = 16, 1190
+    scores = torch.log_softmax(2.0 * torch.randn(B, V, device='cuda'), -1)
+    scores[:, 7] = scores[:, 3]                        # exact ties
+    u = torch.rand(B, device='cuda')
+    nxt, keep, warped = ops.sample(scores, True, temp, top_k, top_p, u, want_keep=True, want_warped=True)
+    ref = RefTransfoXLLMHeadModel.warp_scores(scores.cpu(), temp, top_k, top_p, True)
+    ref_keep = ref > -float('inf')
+    assert torch.equal(keep.cpu().bool(), ref_keep)
+    torch.testing.assert_close(warped.cpu()[ref_keep], ref[ref_keep], rtol=1e-4, atol=1e-4)
+    assert ref_keep[torch.arange(B), nxt.cpu()].all()
+    # chi-square of many draws for one row against the warped distribution
+    n = 20000
+    row = scores[:1].expand(n, V).contiguous()
+    draws, _, _ = ops.sample(row, True, temp, top_k, top_p, torch.rand(n, device='cuda'))
+    p = ref[0].exp()
+    cnt = torch.bincount(draws.cpu(), minlength=V).float()
+    sel = p * n >= 5
+    chi2 = (((cnt - p * n) ** 2) / (p * n))[sel].sum().item()
+    dof = max(int(sel.sum().item()) - 1, 1)
+    assert cnt[~ref_keep[0]].sum() == 0
+    assert chi2 < dof + 6 * math.sqrt(2 * dof) + 10, (chi2, dof)
+
+
+def test_sampler_greedy(ops):
+    torch.manual_seed(7)
+    scores = torch.log_softmax(torch.randn(9, 422, device='cuda'), -1)
+    scores[2, 100] = scores[2].max()
+    scores[2, 50] = scores[2].max()
+    nxt, _, _ = ops.sample(scores, False)
+    assert torch.equal(nxt, scores.argmax(-1))
+
+
+def test_layout_and_casts(ops):
+    torch.manual_seed(8)
+    x = torch.randn(5, 3, 16, device='cuda')
+    bm = ops.tm_to_bm(x, torch.bfloat16)
+    torch.testing.assert_close(bm.float(), x.transpose(0, 1).to(torch.bfloat16).float())
+    tm = ops.bm_to_tm(bm, torch.float32)
+    torch.testing.assert_close(tm, x.to(torch.bfloat16).float())
+    a = torch.randn(1031, device='cuda')
+    # cast needs 16-byte aligned fp32 source: torch allocations are
+    b = torch.empty(1031, device='cuda', dtype=torch.bfloat16)
+    ops.cast_f32_to_bf16(a, b)
+    assert torch.equal(b, a.to(torch.bfloat16))
+    t = ops.transpose(torch.arange(35 * 70, device='cuda', dtype=torch.float32).view(35, 70))
+    assert torch.equal(t, torch.arange(35 * 70, device='cuda', dtype=torch.float32).view(35, 70).t().contiguous())
+
+
+def test_adamw_matches_torch(ops):
+    torch.manual_seed(9)
+    n = 1000
+    p0 = torch.randn(n, device='cuda')
+    p_ref = p0.clone().requires_grad_()
+    opt = torch.optim.AdamW([p_ref], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
+    p, m, v = p0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    for step in range(1, 4):
+        g = torch.randn(n, device='cuda')
+        p_ref.grad = g.clone()
+        opt.step()
+        ops.adamw_step(p, g, m, v, None, 3e-3, 0.9, 0.999, 1e-8, 0.1, step)
+    torch.testing.assert_close(p, p_ref.detach(), rtol=1e-5, atol=1e-6)
