@@ -22,6 +22,10 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp(min=1e-6)).item()
 
 
+def _fro(a, b):
+    return ((a - b).norm() / b.norm().clamp(min=1e-12)).item()
+
+
 @pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 1e-2)])
 def test_forward_loss_logits_mems(pkg, mode, tol):
     ref, model = make_pair(pkg, mode)
@@ -68,14 +72,16 @@ def test_backward_grads(pkg, mode, tol):
     for name, p in ref.named_parameters():
         g = got[name].grad
         assert g is not None, name
-        r = _rel(g.float().cpu(), p.grad)
+        # bf16: a ReLU pre-activation within rounding distance of 0 flips its mask relative to the fp32 oracle, which moves single
+        # entries of a 120-token weight gradient by O(10%) — so bf16 is judged in Frobenius norm, fp32 entry-wise.
+        r = _rel(g.float().cpu(), p.grad) if mode == 'fp32' else _fro(g.float().cpu(), p.grad)
         worst = max(worst, r)
-        assert r < tol * (3 if 'bias' in name or 'layer_norm' in name else 1) + (0.02 if mode == 'bf16' else 0), (name, r)
+        assert r < tol * (3 if 'bias' in name or 'layer_norm' in name else 1), (name, r)
     # second backward accumulates into .grad like autograd does
     out2 = model(input_ids=ids.cuda(), mems=[m.cuda() for m in mems], labels=labels.cuda())
     out2.loss.backward()
     name = 'transformer.layers.0.pos_ff.CoreNet.0.weight'
-    assert _rel(got[name].grad.float().cpu(), 2 * dict(ref.named_parameters())[name].grad) < tol * 2 + (0.02 if mode == 'bf16' else 0)
+    assert _fro(got[name].grad.float().cpu(), 2 * dict(ref.named_parameters())[name].grad) < tol * 2
 
 
 def test_backward_no_mems_and_losses_grad(pkg):
