@@ -1,3 +1,351 @@
-#include "common.cuh"
-int txl_gemm_tc(const void*, const void*, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, int, const TxlEpilogue*, void*, int* handled) { *handled = 0; return 0; }
-int txl_relattn_fwd_tc(const void*, const void*, const void*, const void*, const void*, const void*, const float*, const float*, void*, float*, const TxlAttnDims*, void*, int* handled) { *handled = 0; return 0; }
+// tc_gemm.cu — bf16 GEMM on the 5th-gen tensor cores: TMA (SWIZZLE_128B) -> shared-memory ring -> tcgen05.mma (one elected
+// thread) -> fp32 accumulators in TMEM (double-buffered) -> tcgen05.ld epilogue (bias / ReLU / mask / dropout / accumulate /
+// column sums) -> global.  Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..5 = epilogue (one TMEM lane quadrant each).  All four operand layouts (K-major / MN-major for A and B) are taken
+// straight from row-major tensors, so forward (x W^T), dgrad (dy W) and wgrad (dy^T x, split-K with fp32 reductions) need no
+// transposed copies.   [A.3 qkv_net / r_net / o_net, A.6 CoreNet.0 / CoreNet.3, crit.out_layers.0]
+#include "tc_common.cuh"
+#include <stdlib.h>
+#include <mutex>
+
+// ------------------------------------------------------------------ host: tensor maps through the driver entry point
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+int txl_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { txl_set_error("cuTensorMapEncodeTiled not available from the driver"); return TXL_ECUDA; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { txl_set_error("cuTensorMapEncodeTiled(2d rows=%llu cols=%llu ld=%llu box=%ux%u) failed: %d", (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols, (int)r); return TXL_ECUDA; }
+  return TXL_OK;
+}
+int txl_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld2, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { txl_set_error("cuTensorMapEncodeTiled not available from the driver"); return TXL_ECUDA; }
+  cuuint64_t dims[3] = {cols, rows, d2};
+  cuuint64_t strides[2] = {ld * 2, ld2 * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { txl_set_error("cuTensorMapEncodeTiled(3d) failed: %d", (int)r); return TXL_ECUDA; }
+  return TXL_OK;
+}
+
+namespace {
+constexpr int BM = 128, BK = 64;
+constexpr int THREADS = 192;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+
+struct GemmParams {
+  int64_t M, N, K, ldc;
+  void* C;
+  int dtype_c;
+  TxlEpilogue epi;
+  float inv_keep;
+  int tiles_m, tiles_n, ksplits, nkb, kb_per_split;
+  int a_mn, b_mn;
+};
+
+template <int BN, int STAGES>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int SMEM = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+// butterfly transpose-reduce: on return v[0] of lane l holds sum over the warp's 32 rows of column l (31 shuffles)
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      bool up = lane & off;
+      float send = up ? v[i] : v[i + off];
+      float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN, int STAGES, typename TC>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using C_ = Cfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + C_::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_units = p.tiles_m * p.tiles_n * p.ksplits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer
+      int s = 0; uint32_t ph = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int tm = unit % p.tiles_m, tn = (unit / p.tiles_m) % p.tiles_n, ks = unit / (p.tiles_m * p.tiles_n);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.nkb);
+        const int m0 = tm * BM, n0 = tn * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* a_s = sm + s * C_::STAGE_BYTES;
+          uint8_t* b_s = a_s + A_BYTES;
+          mbar_expect_tx(&full[s], C_::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_2d(a_s, &tmA, &full[s], k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(a_s + i * 8192, &tmA, &full[s], m0 + 64 * i, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(b_s, &tmB, &full[s], k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(b_s + i * 8192, &tmB, &full[s], n0 + 64 * i, k0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      int s = 0; uint32_t ph = 0; int it = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+        const int ks = unit / (p.tiles_m * p.tiles_n);
+        const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.nkb);
+        const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sm + s * C_::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t ad = p.a_mn ? umma_smem_desc(a_addr + kk * 2048, 8192, 1024) : umma_smem_desc(a_addr + kk * 32, 16, 1024);
+            const uint64_t bd = p.b_mn ? umma_smem_desc(b_addr + kk * 2048, 8192, 1024) : umma_smem_desc(b_addr + kk * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5; TMEM lane quadrant = warp % 4)
+    const int q = warp & 3;
+    const TxlEpilogue& e = p.epi;
+    TC* __restrict__ C = reinterpret_cast<TC*>(p.C);
+    int it = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+      const int tm = unit % p.tiles_m, tn = (unit / p.tiles_m) % p.tiles_n;
+      const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+      const int64_t row = (int64_t)tm * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {   // accumulator fully drained into registers: hand TMEM back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        const int64_t col0 = (int64_t)tn * BN + c * 32;
+        if (col0 >= p.N) continue;
+        const bool full_cols = col0 + 32 <= p.N;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int64_t col = col0 + i;
+          float x = v[i];
+          if (e.bias && col < p.N) x += e.bias[col];
+          if (e.flags & TXL_EPI_RELU) x = fmaxf(x, 0.f);
+          if ((e.flags & TXL_EPI_MASK_POS) && row_ok && col < p.N)
+            x = to_f32(reinterpret_cast<const TC*>(e.aux)[row * p.ldc + col]) > 0.f ? x : 0.f;
+          if (e.flags & TXL_EPI_DROPOUT) x *= dropout_scale(e.seed, e.site, (uint64_t)(row * p.N + col), e.drop_p, p.inv_keep);
+          v[i] = (row_ok && col < p.N) ? x : 0.f;
+        }
+        if (e.colsum) {
+          float t[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t[i] = v[i];
+          float cs = warp_colsum32(t, lane);
+          if (col0 + lane < p.N) atomicAdd(&e.colsum[col0 + lane], cs);
+        }
+        if (!row_ok) continue;
+        TC* crow = C + row * p.ldc + col0;
+        if (p.ksplits > 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) atomicAdd(reinterpret_cast<float*>(crow) + i, v[i]);
+        } else if (full_cols) {
+          if constexpr (sizeof(TC) == 2) {
+            uint4* dst = reinterpret_cast<uint4*>(crow);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float a[8];
+              if (e.flags & TXL_EPI_ACCUM) {
+                uint4 old = dst[g];
+                const bf16* ob = reinterpret_cast<const bf16*>(&old);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = v[g * 8 + i] + __bfloat162float(ob[i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = v[g * 8 + i];
+              }
+              uint4 o;
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0], a[1]), p1 = __floats2bfloat162_rn(a[2], a[3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(a[4], a[5]), p3 = __floats2bfloat162_rn(a[6], a[7]);
+              o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+              o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+              dst[g] = o;
+            }
+          } else {
+            float4* dst = reinterpret_cast<float4*>(crow);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              if (e.flags & TXL_EPI_ACCUM) { float4 old = dst[g]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+              dst[g] = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (col0 + i < p.N) {
+              float x = v[i];
+              if (e.flags & TXL_EPI_ACCUM) x += to_f32(crow[i]);
+              crow[i] = from_f32<TC>(x);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C_::TMEM_COLS>(tmem_base);
+}
+
+template <int BN, int STAGES, typename TC>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+  using C_ = Cfg<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TXL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
+    attr_set = true;
+  }
+  tc_gemm_kernel<BN, STAGES, TC><<<grid, THREADS, C_::SMEM, st>>>(tmA, tmB, p);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+}  // namespace
+
+// handled=1 when the tensor-core kernel took the call; 0 => caller uses the SIMT kernel.
+int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int transA,
+                int transB, int dtype_c, const TxlEpilogue* epi, void* stream, int* handled) {
+  *handled = 0;
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("TXL_DISABLE_TC"); disabled = (e && e[0] == '1') ? 1 : 0; }
+  if (disabled) return TXL_OK;
+  // TMA needs 16-byte aligned bases and row pitches; C vector stores need the same
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  const int csz = dtype_c == TXL_F32 ? 4 : 2;
+  if (!al16(A) || !al16(B) || !al16(C) || (lda % 8) || (ldb % 8) || ((ldc * csz) % 16) || K < 16 || N < 8) return TXL_OK;
+  if ((epi->flags & TXL_EPI_MASK_POS) && !epi->aux) return TXL_OK;
+  if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return TXL_OK;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.C = C; p.dtype_c = dtype_c; p.epi = *epi;
+  p.inv_keep = (epi->flags & TXL_EPI_DROPOUT) ? 1.f / (1.f - epi->drop_p) : 1.f;
+  p.a_mn = transA ? 1 : 0;   // transA: A stored [K, M] => M contiguous
+  p.b_mn = transB ? 0 : 1;   // transB: B stored [N, K] => K contiguous
+  const int BN = N >= 256 ? 256 : 128;
+  p.tiles_m = (int)cdiv64(M, BM); p.tiles_n = (int)cdiv64(N, BN);
+  p.nkb = (int)cdiv64(K, BK);
+  p.ksplits = 1;
+  const int sms = txl_num_sms();
+  const bool pure_accum = dtype_c == TXL_F32 && epi->flags == TXL_EPI_ACCUM && !epi->bias && !epi->colsum;
+  const int tiles = p.tiles_m * p.tiles_n;
+  if (pure_accum && tiles < sms && p.nkb >= 8) {
+    int want = sms / tiles;
+    int maxs = p.nkb / 4;
+    p.ksplits = want < maxs ? want : maxs;
+    if (p.ksplits < 1) p.ksplits = 1;
+  }
+  p.kb_per_split = (int)cdiv64(p.nkb, p.ksplits);
+  p.ksplits = (int)cdiv64(p.nkb, p.kb_per_split);   // no empty split
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!p.a_mn) rc = txl_make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
+  else rc = txl_make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 64);
+  if (rc) return rc;
+  if (!p.b_mn) rc = txl_make_tmap_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, BK);
+  else rc = txl_make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, 64);
+  if (rc) return rc;
+
+  const int total = tiles * p.ksplits;
+  const int grid = total < sms ? total : sms;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 256) {
+    if (dtype_c == TXL_F32) rc = launch<256, 4, float>(tmA, tmB, p, grid, st); else rc = launch<256, 4, bf16>(tmA, tmB, p, grid, st);
+  } else {
+    if (dtype_c == TXL_F32) rc = launch<128, 6, float>(tmA, tmB, p, grid, st); else rc = launch<128, 6, bf16>(tmA, tmB, p, grid, st);
+  }
+  if (rc) return rc;
+  *handled = 1;
+  return TXL_OK;
+}
+
+int txl_relattn_fwd_tc(const void*, const void*, const void*, const void*, const void*, const void*, const float*, const float*, void*, float*,
+                       const TxlAttnDims*, void*, int* handled) {
+  *handled = 0;
+  return TXL_OK;
+}
