@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — Transformer-XL training-step throughput on the BASELINE.json configuration.
+
+A "step" = one full training pass of the hot path over one batch: forward (embedding, 12 layers of relative-position band
+attention + position-wise FF, LM head + log-softmax + NLL) with CARRIED NON-ZERO mems, backward, bucketed gradient
+all-reduce (N > 1), global-norm clip + AdamW.  Workload = BASELINE.json configs[1]:
+  Transformer-XL music LM, 12 layers, d_model 512, 8 heads, d_inner 2048, seq 1024, mem_len 1024, vocab 1190, bf16,
+  per-GPU batch 32 (weak scaling), dropout 0.1, synthetic uniform token ids (seed 77), random-init weights.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+`--impl reference` times the reference's CPU implementation of the same path (the oracle restatement of HF 4.25.1
+TransfoXL — the reference's own dependency cannot be installed here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = 'symbolic-music-generation_b200'
+
+CFG2 = dict(model_size='small', vocab_size=1190, max_length=1024, mem_len=1024, cutoffs=[])      # reference train.py:521-527 override
+FLOP_PER_TOKEN = {  # SURVEY §8d, band-aware, fwd+bwd with real (carried) mems
+    'cfg2': 3.6856e8,
+}
+
+
+def flop_per_token(L, d, di, T, M, V, Kb):
+    fwd_seq = L * (2 * T * d * d + 4 * (T + M) * d * d + 2 * T * d * d + 4 * T * d * di + 6 * T * Kb * d) + 2 * T * d * V
+    bwd_seq = 2 * fwd_seq - L * 4 * M * d * d
+    return (fwd_seq + bwd_seq) / T, fwd_seq / T
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                    power_w_max=max(pw) if pw else None, samples=len(sm))
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return dict(tf=p['bf16_tflops_sustained'], tf_burst=p['bf16_tflops'], hbm=p['hbm_gbs'], src='measured (MEASURED_PEAKS.json)')
+    except Exception:
+        return dict(tf=1400.0, tf_burst=1590.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
+
+
+# ----------------------------------------------------------------------------- CPU baseline / reference arm
+def cpu_reference_tokens_per_s(steps, warmup, budget_s=25.0, train=True):
+    """The reference's CPU path (oracle restatement) on this box's host cores: cfg2 training step on a bounded sample
+    (B=1 sequence of T=1024 with mem_len 1024 carried mems) — same model, same shapes per sequence as the GPU arm."""
+    import torch
+    from oracle.txl_ref import RefConfig, RefTransfoXLLMHeadModel
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(77)
+    cfg = RefConfig.from_preset('small', vocab_size=1190, max_length=1024, mem_len=1024, cutoffs=[])
+    model = RefTransfoXLLMHeadModel(cfg).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=0.01)
+    g = torch.Generator().manual_seed(77)
+    B, T = 1, 1024
+    ids = torch.randint(0, cfg.vocab_size, (B, T), generator=g)
+    mems = [0.5 * torch.randn(cfg.mem_len, B, cfg.d_model) for _ in range(cfg.n_layer)]
+    times = []
+    t_start = time.time()
+    for i in range(warmup + steps):
+        t0 = time.time()
+        out = model(input_ids=ids, mems=mems, labels=ids.clone())
+        out.loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step(); opt.zero_grad(set_to_none=True)
+        mems = [m.detach() for m in out.mems]
+        dt = time.time() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.time() - t_start > budget_s and len(times) >= 1:
+            break
+    ms = 1000 * sum(times) / len(times)
+    return dict(value=B * T / (ms / 1000), ms_per_step=ms, cores=cores, steps=len(times),
+                sample=f'cfg2 model (12L d512 T1024 mem1024 V1190) fp32 train step fwd+bwd+clip+AdamW, B=1 sequence with carried mems, '
+                       f'{len(times)} timed steps, torch {torch.__version__} CPU, {cores} threads')
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    r = cpu_reference_tokens_per_s(max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)), budget_s=60.0)
+    line = {
+        'impl': 'reference', 'metric': 'TXL train tokens/s', 'value': r['value'], 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': r['steps'],
+        'warmup': min(args.warmup, 1), 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'cfg2: Transformer-XL 12L d512 H8 di2048 T1024 mem1024 V1190 training step (CPU reference arm, bounded sample B=1)'},
+        'cpu_baseline': {'value': r['value'], 'unit': 'tokens/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
+        'e2e': {'value': r['value'], 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'note': 'reference dependency transformers==4.25.1 is not installable here; this is the oracle restatement (kind=port)',
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module(PKG)
+    ops = importlib.import_module(PKG + '.ops')
+    L_ = importlib.import_module(PKG + '._lib')
+    optim = importlib.import_module(PKG + '.optim')
+    pdist = importlib.import_module(PKG + '.dist')
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    lib = L_.load()
+
+    B, T = args.batch, args.seq
+    kw = dict(CFG2)
+    kw.update(max_length=T, mem_len=args.mem_len)
+    cfg = pkg.MyTransfoXLConfig(compute_dtype=args.dtype, dropout=args.dropout, **kw)
+    torch.manual_seed(77)
+    model = pkg.MyTransfoXLLMHeadModel(cfg).to(dev).train()
+    model._ensure_engine()
+    if world > 1:       # identical replicas: broadcast rank 0's flat parameters
+        dist.broadcast(model._flat, 0)
+    opt = optim.FusedAdamW(model, lr=3e-4, weight_decay=0.01, max_grad_norm=1.0)
+    bucketer = pdist.GradBucketer(model, bucket_mb=25.0) if world > 1 else None
+
+    V = cfg.vocab_size
+    g = torch.Generator().manual_seed(77 + rank)
+    n_batches = 4
+    host_ids = [torch.randint(0, V, (B, T), generator=g).pin_memory() for _ in range(n_batches)]
+    host_lab = []
+    for ids in host_ids:        # padded variant: 25 % of rows end in a pad tail (-100 labels)
+        lab = ids.clone()
+        for b in range(0, B, 4):
+            tail = int(torch.randint(1, T // 4, (1,), generator=g))
+            lab[b, T - tail:] = -100
+        host_lab.append(lab.pin_memory())
+    dev_ids = [x.to(dev) for x in host_ids]
+    dev_lab = [x.to(dev) for x in host_lab]
+
+    state = {'mems': None}
+
+    def step_resident(i):
+        out = model(input_ids=dev_ids[i % n_batches], mems=state['mems'], labels=dev_lab[i % n_batches])
+        out.loss.backward()
+        opt.step()
+        opt.zero_grad()
+        state['mems'] = out.mems           # carried, non-zero mems (SURVEY §8d zero-mems caveat)
+        return out.loss
+
+    def step_e2e(i):
+        ids = host_ids[i % n_batches].to(dev, non_blocking=True)
+        lab = host_lab[i % n_batches].to(dev, non_blocking=True)
+        out = model(input_ids=ids, mems=state['mems'], labels=lab)
+        out.loss.backward()
+        opt.step()
+        opt.zero_grad()
+        state['mems'] = out.mems
+        return float(out.loss.item())      # device->host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        l0 = lib.txl_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(steps):
+            last = fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.txl_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, launches, last
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_step, launches, last_loss = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _, last_e2e = timed(step_e2e, max(3, args.steps // 2), 3)
+
+    tokens = B * T * world
+    value = tokens / (ms_step / 1000)
+    e2e_value = tokens / (ms_e2e / 1000)
+    fpt, fpt_fwd = flop_per_token(cfg.n_layer, cfg.d_model, cfg.d_inner, T, args.mem_len, V, min(args.mem_len, T + args.mem_len))
+    peaks = measured_peaks()
+    step_tf = value / world * fpt / 1e12
+
+    # ---- dominant kernel, timed alone with CUDA events on the launching stream
+    dom = dominant_kernel_probe(torch, ops, model, cfg, B, T, args.mem_len, dev)
+
+    line = {
+        'metric': 'TXL train tokens/s', 'value': value, 'unit': 'tokens/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+        'config': {'workload': f'cfg2: Transformer-XL 12L d512 H8 dh64 di2048 T{T} mem{args.mem_len} V{V} bf16 training step '
+                               f'(fwd+bwd+clip+AdamW, carried non-zero mems, dropout {args.dropout})',
+                   'batch_per_gpu': B, 'global_batch': B * world, 'seq_len': T, 'mem_len': args.mem_len, 'parallelism': f'dp{world}',
+                   'l2_policy': 'inputs larger than L2: ~5 GB of activations and 4 rotating batches per step; no explicit flush',
+                   'flop_per_token': fpt, 'final_loss': float(last_loss.item()) if last_loss is not None else None},
+        'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': 2 * B * T * 8, 'd2h_bytes_per_step': 4,
+                'api': 'MyTransfoXLLMHeadModel.forward(input_ids, mems, labels) from pinned host ids/labels -> loss.backward() -> FusedAdamW.step() -> loss.item()'},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': dom,
+        'roofline_step': {'bound': 'tensor', 'achieved': step_tf, 'peak': peaks['tf'], 'unit': 'TFLOP/s', 'frac': step_tf / peaks['tf'],
+                          'note': f'whole step, algorithmic FLOP/token {fpt:.4e} (SURVEY §8d) / per-GPU tokens/s; peak = sustained bf16, {peaks["src"]}'},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_tokens_per_s(1, 1, budget_s=25.0)
+        line['cpu_baseline'] = {'value': r['value'], 'unit': 'tokens/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_probe(torch, ops, model, cfg, B, T, M, dev):
+    """Times the relative-position attention forward kernel (the largest single kernel of the step) alone, 10 launches between
+    CUDA events on the current stream, inputs sized far beyond L2 (q/k/v for 32 sequences = 300 MB)."""
+    peaks = measured_peaks()
+    d, H, dh = cfg.d_model, cfg.n_head, cfg.d_head
+    dt = torch.bfloat16 if cfg.compute_dtype == 'bf16' else torch.float32
+    torch.manual_seed(1)
+    qkv = (0.5 * torch.randn(B * T, 3 * d, device=dev)).to(dt)
+    kvm = (0.5 * torch.randn(B * M, 2 * d, device=dev)).to(dt)
+    P = ops.num_r(T, M, cfg.clamp_len)
+    r = (0.5 * torch.randn(P, d, device=dev)).to(dt)
+    rwb = 0.1 * torch.randn(d, device=dev)
+    rrb = 0.1 * torch.randn(d, device=dev)
+    band = ops.make_band(T, M, cfg.mem_len, cfg.clamp_len, cfg.same_length)
+
+    def run():
+        return ops.relattn_fwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, B, T, H, dh, band)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    Kb = min(M, T + M)
+    flops = 6.0 * T * Kb * d * B       # AC + BD + PV on the live band, per launch
+    ach = flops / (ms / 1000) / 1e12
+    return {'kernel': 'relattn_fwd (AC+BD+rel_shift+band mask+softmax+PV)', 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tf_burst'],
+            'unit': 'TFLOP/s', 'frac': ach / peaks['tf_burst'], 'traffic': None, 'ms_per_launch': ms,
+            'algorithmic_flops_per_launch': flops, 'peak_source': 'burst bf16, ' + peaks['src']}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=32)
+    ap.add_argument('--seq', type=int, default=1024)
+    ap.add_argument('--mem-len', type=int, default=1024)
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--dropout', type=float, default=0.1)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -45,6 +45,8 @@ int txl_version(void);
 const char* txl_last_error(void);
 /* 0 if the current device is sm_100 (B200); TXL_ENODEV otherwise. */
 int txl_device_ok(void);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+unsigned long long txl_launch_count(void);
 
 /* ---- integer index maps (bit-exact contract) -------------------------------------------------
  * masked[i*klen+j] = 1 iff key j is masked for query i          (HF uint8 triu+tril mask, [A.2-4])

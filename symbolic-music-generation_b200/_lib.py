@@ -42,6 +42,7 @@ SIGNATURES = {
     'txl_version': (_i, []),
     'txl_last_error': (C.c_char_p, []),
     'txl_device_ok': (_i, []),
+    'txl_launch_count': (C.c_ulonglong, []),
     'txl_relattn_index_map': (_i, [C.POINTER(TxlBand), _vp, _vp, _vp, _vp, _vp]),
     'txl_embed_fwd': (_i, [_vp, _vp, _vp, _i64, _i, _i, _f, _i, _f, _u64, _u32, _vp]),
     'txl_embed_bwd': (_i, [_vp, _vp, _vp, _i64, _i, _i, _f, _i, _f, _u64, _u32, _vp]),

@@ -26,7 +26,12 @@ void txl_set_error(const char* fmt, ...);
       return TXL_ECUDA;                                                                 \
     }                                                                                   \
   } while (0)
-#define TXL_LAUNCH_CHECK() TXL_CUDA(cudaGetLastError())
+extern unsigned long long g_txl_launches;
+#define TXL_LAUNCH_CHECK()          \
+  do {                              \
+    ++g_txl_launches;               \
+    TXL_CUDA(cudaGetLastError());   \
+  } while (0)
 
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }

@@ -389,6 +389,7 @@ extern "C" int txl_relattn_bwd(const void* q, const void* k_mem, const void* v_m
     TXL_CUDA(cudaFuncSetAttribute(relattn_bwd_kernel<T, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     relattn_bwd_kernel<T, DH><<<grid, 128, smem, st>>>(P, (const T*)out, lse, (const T*)dout, (T*)dq, dk_ws, dv_ws, dr, drwb, drrb, *D);
     int g2 = (int)imin64(cdiv64(n, 256), (int64_t)txl_num_sms() * 16);
+    ++g_txl_launches;
     scatter_dkv_kernel<T><<<g2, 256, 0, st>>>(dk_ws, dv_ws, (T*)dk_mem, (T*)dv_mem, (T*)dk_cur, (T*)dv_cur, D->B, D->band.T, D->band.mlen, HD, D->ldkv_mem, D->ldkv_cur);
   });
   TXL_LAUNCH_CHECK();
