@@ -63,9 +63,10 @@ int txl_embed_fwd(const int64_t* ids, const void* E, void* out, int64_t n_tok, i
 int txl_embed_bwd(const int64_t* ids, const void* dOut, float* dE, int64_t n_tok, int d, int V, float scale,
                   int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
 
-/* ---- sinusoid table  [A.6 PositionalEmbedding] -------------------------------------------------
- * out[p,:] = [sin(p*f_0..), cos(p*f_0..)], f_k = 10000^(-2k/d), p = 0..P-1, inverted dropout if p>0 */
-int txl_posemb_table(void* out, int P, int d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
+/* ---- sinusoid table  [A.2 step 5 pos_seq + A.6 PositionalEmbedding] --------------------------------
+ * HF's `pos_emb` literally: row x (0..klen-1) holds position pos = min(klen-1-x, clamp_len) (no clamp if clamp_len<=0):
+ * out[x,:] = [sin(pos*f_0..), cos(pos*f_0..)], f_k = 10000^(-2k/d); inverted dropout if drop_p>0 */
+int txl_posemb_table(void* out, int klen, int clamp_len, int d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
 
 /* ---- generic GEMM with epilogue  [A.3 qkv_net/r_net/o_net, A.6 CoreNet.0/3, crit.out_layers] -----
  * C[M,N] = epi( op(A)[M,K] * op(B)[K,N] ), row-major, leading dims in elements.
@@ -110,10 +111,11 @@ int txl_dropout(const void* x, void* y, int64_t n, int dtype, float drop_p, uint
  * q:      [B, T, H*dh] view with row stride ldq (elements)
  * k/v:    keys 0..mlen-1 from k_mem/v_mem ([B, mlen, H*dh], row stride ldkv_mem),
  *         keys mlen..mlen+T-1 from k_cur/v_cur ([B, T, H*dh], row stride ldkv_cur)
- * r:      [P, H*dh] r_net(pos_emb) rows for relative distance p = 0..P-1, P = min(klen-1, clamp)+1
+ * r:      [klen, H*dh] = HF's r_head_k = r_net(pos_emb): row x encodes relative distance min(klen-1-x, clamp).
+ *         Query i / key j use row x = (T-1-i) + j, which IS the pad/reshape `_rel_shift` (BD[i,j] = BD0[i, j+T-1-i], [A.4])
  * rwb/rrb:[H*dh] fp32 (r_w_bias, r_r_bias)
  * out:    [B, T, H*dh] (ld = H*dh);  lse: [B, H, T] fp32 log-sum-exp of the scaled scores
- * score(i,j) = ((q_i+rwb).k_j + (q_i+rrb).r[min(mlen+i-j, clamp)]) / sqrt(dh) on the live band only. */
+ * score(i,j) = ((q_i+rwb).k_j + (q_i+rrb).r[T-1-i+j]) / sqrt(dh) on the live band only. */
 typedef struct {
   int B, H, dh;
   TxlBand band;
@@ -125,7 +127,7 @@ int txl_relattn_fwd(const void* q, const void* k_mem, const void* v_mem, const v
                     const TxlAttnDims* dims, void* stream);
 /* Backward.  dq/dk_cur/dv_cur are written with the same strides as their forward tensors (they may be
  * slices of one [B,T,3d] buffer); dk_mem/dv_mem may be NULL (mems detached and all-zero => no wgrad term).
- * dr [P,H*dh], drwb/drrb [H*dh] are fp32 and ACCUMULATED into.  ws: workspace of txl_relattn_bwd_workspace bytes. */
+ * dr [klen,H*dh], drwb/drrb [H*dh] are fp32 and ACCUMULATED into.  ws: workspace of txl_relattn_bwd_workspace bytes. */
 int64_t txl_relattn_bwd_workspace(const TxlAttnDims* dims);
 int txl_relattn_bwd(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur,
                     const void* r, const float* rwb, const float* rrb, const void* out, const float* lse,

@@ -106,11 +106,13 @@ extern "C" int txl_embed_bwd(const int64_t* ids, const void* dOut, float* dE, in
 
 // ------------------------------------------------------------------ sinusoid table
 template <typename T>
-__global__ void posemb_kernel(T* out, int P, int d, float p, float inv_keep, uint64_t seed, uint32_t site) {
+__global__ void posemb_kernel(T* out, int klen, int clamp, int d, float p, float inv_keep, uint64_t seed, uint32_t site) {
   int half = d / 2;
-  int64_t total = (int64_t)P * d;
+  int64_t total = (int64_t)klen * d;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    int pos = (int)(idx / d), c = (int)(idx % d);
+    int x = (int)(idx / d), c = (int)(idx % d);
+    int pos = klen - 1 - x;                       // pos_seq = arange(klen-1, -1, -1)
+    if (clamp > 0 && pos > clamp) pos = clamp;    // .clamp_(max=clamp_len)
     int k = c < half ? c : c - half;
     // inv_freq = 1 / 10000^(2k/d) evaluated like torch: fp32 pow then reciprocal; product in fp32
     float inv_freq = 1.0f / powf(10000.0f, (float)(2 * k) / (float)d);
@@ -120,11 +122,11 @@ __global__ void posemb_kernel(T* out, int P, int d, float p, float inv_keep, uin
     out[idx] = from_f32<T>(v);
   }
 }
-extern "C" int txl_posemb_table(void* out, int P, int d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream) {
-  TXL_CHECK_ARG(P > 0 && d > 0 && d % 2 == 0, "posemb: bad sizes");
-  int grid = (int)imin64(cdiv64((int64_t)P * d, 256), 4096);
+extern "C" int txl_posemb_table(void* out, int klen, int clamp_len, int d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream) {
+  TXL_CHECK_ARG(klen > 0 && d > 0 && d % 2 == 0, "posemb: bad sizes");
+  int grid = (int)imin64(cdiv64((int64_t)klen * d, 256), 4096);
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  DISPATCH_DTYPE(dtype, (posemb_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((T*)out, P, d, drop_p, ik, seed, site)));
+  DISPATCH_DTYPE(dtype, (posemb_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((T*)out, klen, clamp_len, d, drop_p, ik, seed, site)));
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }

@@ -54,15 +54,12 @@ __device__ __forceinline__ void load_chunk(Smem<T, DH>& s, const AttnPtrs& P, co
     s.Ks[jj][c] = kv; s.Vs[jj][c] = vv;
   }
   // window w <-> distance p = mlen + i0 - jc - (BKC-1) + w   (w = rr - jj + BKC-1)
+  // r row of distance p is x = klen-1-p (HF r_head_k order; the clamp is baked into the table)
   int pbase = g.mlen + i0 - jc - (BKC - 1);
-  int nr = band_num_r(g);
   for (int e = threadIdx.x; e < (BQ + BKC - 1) * DH; e += blockDim.x) {
-    int w = e / DH, c = e % DH, p = pbase + w;
+    int w = e / DH, c = e % DH, x = g.klen - 1 - (pbase + w);
     float rv = 0.f;
-    if (p >= 0) {
-      int row = (g.clamp > 0 && p > g.clamp) ? g.clamp : p;
-      if (row < nr) rv = to_f32(((const T*)P.r)[(int64_t)row * D.H * DH + h * DH + c]);
-    }
+    if (x >= 0 && x < g.klen) rv = to_f32(((const T*)P.r)[(int64_t)x * D.H * DH + h * DH + c]);
     s.Rs[w][c] = rv;
   }
 }
@@ -166,7 +163,6 @@ __global__ void __launch_bounds__(128) relattn_bwd_kernel(AttnPtrs P, const T* _
   constexpr int DPL = (DH + 31) / 32;
   const float scale = rsqrtf((float)DH);
   const int HD = D.H * DH;
-  const int nr = band_num_r(g);
 
   load_q<T, DH>(s.f, P, D, g, b, h, i0);
   for (int e = threadIdx.x; e < BQ * DH; e += blockDim.x) {
@@ -262,12 +258,9 @@ __global__ void __launch_bounds__(128) relattn_bwd_kernel(AttnPtrs P, const T* _
     }
     int pbase = g.mlen + i0 - jc - (BKC - 1);
     for (int e = threadIdx.x; e < (BQ + BKC - 1) * DH; e += blockDim.x) {
-      int w = e / DH, c = e % DH, p = pbase + w;
+      int w = e / DH, c = e % DH, x = g.klen - 1 - (pbase + w);
       float v = s.dRs[w][c];
-      if (p >= 0 && v != 0.f) {
-        int row = (g.clamp > 0 && p > g.clamp) ? g.clamp : p;
-        if (row < nr) atomicAdd(&dr[(int64_t)row * HD + h * DH + c], v);
-      }
+      if (x >= 0 && x < g.klen && v != 0.f) atomicAdd(&dr[(int64_t)x * HD + h * DH + c], v);
     }
   }
   __syncthreads();

@@ -344,8 +344,3 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
   return TXL_OK;
 }
 
-int txl_relattn_fwd_tc(const void*, const void*, const void*, const void*, const void*, const void*, const float*, const float*, void*, float*,
-                       const TxlAttnDims*, void*, int* handled) {
-  *handled = 0;
-  return TXL_OK;
-}

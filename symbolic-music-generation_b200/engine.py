@@ -85,7 +85,7 @@ def forward(cfg, W: List[LayerW], E, out_bias, ids, mems_bm, labels_shift, *, dr
     sv = Saved(ids=ids, labels=labels_shift, seed=seed, drop_p=drop_p, mems_real=mems_real, B=B, T=T, mlen=mlen) if save else None
 
     x = ops.embed_fwd(ids.reshape(-1), E, math.sqrt(d), drop_p, seed, SITE_EMB)
-    pos = ops.posemb_table(g.P, d, dt, dev, drop_p, seed, SITE_POS)
+    pos = ops.posemb_table(g.P, cfg.clamp_len, d, dt, dev, drop_p, seed, SITE_POS)
     if save:
         sv.pos = pos
         sv.mems = mems_bm
@@ -172,7 +172,7 @@ def backward(cfg, W: List[LayerW], G: List[LayerW], E, gE, g_out_bias, sv: Saved
                         dqkv[:, :d], dkvm[:, :d] if dkvm is not None else None, dkvm[:, d:] if dkvm is not None else None,
                         dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, gw.rwb, gw.rrb, B, T, H, dh, g.band)
         # r_net:  r = pos Wr^T
-        dr_c = dr if dt == torch.float32 else dr.to(dt)
+        dr_c = dr if dt == torch.float32 else ops.cast_f32_to_bf16(dr, torch.empty_like(dr, dtype=dt))
         ops.gemm(dr_c, sv.pos, transA=True, out=gw.r, accumulate=True)
         # qkv_net
         ops.gemm(dqkv, s['x'], transA=True, out=gw.qkv, accumulate=True)                              # dWqkv += dqkv^T x

@@ -25,11 +25,9 @@ def make_band(T, mlen, mem_len, clamp_len, same_length) -> TxlBand:
     return TxlBand(int(T), int(mlen), int(mem_len), int(clamp_len), int(bool(same_length)))
 
 
-def num_r(T, mlen, clamp_len) -> int:
-    pmax = mlen + T - 1
-    if clamp_len > 0:
-        pmax = min(pmax, clamp_len)
-    return pmax + 1
+def num_r(T, mlen, clamp_len=0) -> int:
+    """rows of the r table = klen (HF's r_head_k; the clamp is baked into the position table)."""
+    return mlen + T
 
 
 # ----------------------------------------------------------------------------- index maps
@@ -60,9 +58,10 @@ def embed_bwd(ids, dOut, dE, scale, drop_p=0.0, seed=0, site=0):
                                float(drop_p), int(seed), int(site), stream_ptr()), 'embed_bwd')
 
 
-def posemb_table(P, d, dtype, device, drop_p=0.0, seed=0, site=0):
-    out = torch.empty(P, d, dtype=dtype, device=device)
-    check(_lib().txl_posemb_table(ptr(out), P, d, dtype_code(dtype), float(drop_p), int(seed), int(site), stream_ptr()), 'posemb_table')
+def posemb_table(klen, clamp_len, d, dtype, device, drop_p=0.0, seed=0, site=0):
+    """HF pos_emb: row x <-> position min(klen-1-x, clamp_len)."""
+    out = torch.empty(klen, d, dtype=dtype, device=device)
+    check(_lib().txl_posemb_table(ptr(out), klen, int(clamp_len), d, dtype_code(dtype), float(drop_p), int(seed), int(site), stream_ptr()), 'posemb_table')
     return out
 
 

@@ -103,10 +103,14 @@ def test_embed_posemb(ops):
     ops.embed_bwd(ids.view(-1), dout, dE, 8.0)
     ref = torch.zeros_like(E).index_add_(0, ids.view(-1), dout * 8.0)
     torch.testing.assert_close(dE, ref, rtol=1e-5, atol=1e-5)
-    pos = ops.posemb_table(40, 64, torch.float32, 'cuda')
-    inv = 1 / (10000 ** (torch.arange(0.0, 64, 2.0) / 64))
-    s = torch.outer(torch.arange(40.0), inv)
-    torch.testing.assert_close(pos.cpu(), torch.cat([s.sin(), s.cos()], -1), rtol=1e-5, atol=2e-5)
+    for klen, clamp in ((40, 0), (40, 16), (300, 1024)):
+        pos = ops.posemb_table(klen, clamp, 64, torch.float32, 'cuda')
+        inv = 1 / (10000 ** (torch.arange(0.0, 64, 2.0) / 64))
+        pos_seq = torch.arange(klen - 1, -1, -1.0)
+        if clamp > 0:
+            pos_seq.clamp_(max=clamp)
+        s = torch.outer(pos_seq, inv)
+        torch.testing.assert_close(pos.cpu(), torch.cat([s.sin(), s.cos()], -1), rtol=1e-5, atol=5e-5)
 
 
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
@@ -140,11 +144,7 @@ def _ref_attention(q, k, v, r, rwb, rrb, T, M, ML, C, same):
     from oracle.txl_ref import literal_attn_mask, literal_rel_shift
     B, _, H, dh = q.shape
     klen = M + T
-    P = r.shape[0]
-    pos = torch.arange(klen - 1, -1, -1)
-    if C > 0:
-        pos = pos.clamp(max=C)
-    rk = r[pos]                                           # (klen, H, dh) as r_head_k
+    rk = r                                                # (klen, H, dh) = r_head_k (clamp is baked into the position table)
     qi = q.permute(1, 0, 2, 3)                            # (T, B, H, dh)
     kj, vj = k.permute(1, 0, 2, 3), v.permute(1, 0, 2, 3)
     AC = torch.einsum('ibnd,jbnd->ijbn', qi + rwb, kj)
@@ -160,7 +160,11 @@ def _ref_attention(q, k, v, r, rwb, rrb, T, M, ML, C, same):
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
 @pytest.mark.parametrize('B,H,dh,T,M,ML,C,same', [(2, 2, 32, 40, 40, 40, 1024, 1), (1, 3, 64, 33, 20, 20, 8, 1), (2, 2, 16, 5, 0, 4, 2, 1),
                                                    (3, 2, 32, 1, 48, 48, 16, 1), (1, 2, 64, 70, 10, 30, 1024, 1), (2, 1, 32, 24, 8, 8, 4, 0),
-                                                   (1, 2, 128, 16, 16, 16, 64, 1)])
+                                                   (1, 2, 128, 16, 16, 16, 64, 1),
+                                                   # shapes the tcgen05 kernel takes in bf16 (d_head 64, T and mlen multiples of 64, klen >= 192)
+                                                   (2, 2, 64, 128, 128, 128, 1024, 1), (1, 1, 64, 256, 256, 256, 64, 1), (2, 1, 64, 192, 64, 64, 1024, 1),
+                                                   (1, 2, 64, 64, 192, 192, 1024, 1), (1, 2, 64, 128, 128, 128, 1024, 0), (1, 1, 64, 256, 0, 256, 1024, 1),
+                                                   (1, 2, 64, 320, 128, 128, 16, 1), (1, 1, 64, 512, 512, 512, 1024, 1)])
 def test_relattn_fwd_bwd(ops, mode, B, H, dh, T, M, ML, C, same):
     torch.manual_seed(5)
     dt = DT[mode]
