@@ -6,6 +6,11 @@
 int txl_relattn_fwd_tc(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur, const void* r,
                        const float* rwb, const float* rrb, void* out, float* lse, const TxlAttnDims* dims, void* stream, int* handled);
 
+int64_t txl_relattn_bwd_tc_workspace(const TxlAttnDims* D);
+int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur, const void* r, const float* rwb,
+                       const float* rrb, const void* out, const float* lse, const void* dout, void* dq, void* dk_mem, void* dv_mem, void* dk_cur,
+                       void* dv_cur, float* dr, float* drwb, float* drrb, void* ws, const TxlAttnDims* D, void* stream, int* handled);
+
 namespace {
 constexpr int BQ = 32;   // query rows per CTA
 constexpr int BKC = 32;  // keys per chunk (= one lane per key)
@@ -358,7 +363,9 @@ extern "C" int txl_relattn_fwd(const void* q, const void* k_mem, const void* v_m
 
 extern "C" int64_t txl_relattn_bwd_workspace(const TxlAttnDims* D) {
   if (!D) return 0;
-  return 2ll * D->B * (D->band.mlen + D->band.T) * D->H * D->dh * (int64_t)sizeof(float);
+  int64_t simt = 2ll * D->B * (D->band.mlen + D->band.T) * D->H * D->dh * (int64_t)sizeof(float);
+  int64_t tc = txl_relattn_bwd_tc_workspace(D);
+  return simt > tc ? simt : tc;
 }
 
 extern "C" int txl_relattn_bwd(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur,
@@ -370,6 +377,12 @@ extern "C" int txl_relattn_bwd(const void* q, const void* k_mem, const void* v_m
   TXL_CHECK_ARG(q && k_cur && v_cur && r && rwb && rrb && out && lse && dout && dq && dk_cur && dv_cur && dr && drwb && drrb && ws,
                 "relattn_bwd: null pointer");
   TXL_CHECK_ARG((dk_mem == nullptr) == (dv_mem == nullptr), "relattn_bwd: dk_mem/dv_mem must both be given or both NULL");
+  if (D->dtype == TXL_BF16) {
+    int handled = 0;
+    rc = txl_relattn_bwd_tc(q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb, out, lse, dout, dq, dk_mem, dv_mem, dk_cur, dv_cur, dr, drwb, drrb, ws, D, stream, &handled);
+    if (rc) return rc;
+    if (handled) return TXL_OK;
+  }
   AttnPtrs P{q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb};
   cudaStream_t st = (cudaStream_t)stream;
   const int klen = D->band.mlen + D->band.T, HD = D->H * D->dh;

@@ -1,0 +1,537 @@
+// tc_relattn_bwd.cu — relative-position band attention BACKWARD on tcgen05 tensor cores (bf16, d_head 64).
+//
+// One kernel template, three accumulation orders over the same (batch b, 128-query tile I, 64-key tile J) band tiles:
+//   MODE_DQ : CTA = (b, h, I), loops J.   acc0 = dQw = sum_J dS.K        acc1 = dQr = sum_J dBD0.Rwin   -> dq, d r_w_bias, d r_r_bias
+//   MODE_DKV: CTA = (b, h, J), loops I.   acc0 = dK  = sum_I dS^T.Qw     acc1 = dV  = sum_I P^T.dO      -> dk, dv
+//   MODE_DR : CTA = (h, diagonal J-2I), loops (I, b) — the R window is the same for all of them.
+//                                          acc0/acc1 = dRwin = sum dBD0^T.Qr                             -> dr (fp32 atomics, ~2 M per layer)
+// Every tile recomputes, on the tensor cores, S = Qw.K^T, BD0 = Qr.Rwin^T and dP = dO.V^T into TMEM; 256 "softmax" threads
+// (2 per query row, 32 keys each) apply HF's `_rel_shift` exactly as the forward kernel does (TMEM column offset + register
+// barrel shifter), rebuild P = exp2(score - lse) from the saved log-sum-exp, form dS = P (dP - delta) / sqrt(dh), and hand the
+// tensor cores bf16 tiles in shared memory: P and dS K-major (also read transposed, MN-major, for dV/dK), and dBD0 — dS
+// un-shifted back into window space by a per-row element offset on the shared-memory store (the inverse skew costs no ALU).
+// No atomics are used for dq/dk/dv; nothing of size T x klen touches HBM.
+// Operands arrive by TMA through a 2-stage ring (warp 8), one thread of warp 9 issues all tcgen05.mma.
+// Supported: mlen == mem_len with same_length (every query sees exactly mem_len keys — the training configuration);
+// anything else takes the SIMT kernel.   [A.3, A.4, A.5 backward]
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace {
+constexpr int BQ = 128, BKV = 64, DH = 64, WIN = 192;
+constexpr int MODE_DQ = 0, MODE_DKV = 1, MODE_DR = 2;
+constexpr int N_SOFTMAX = 256, NTHREADS = 320;
+constexpr int TM_S = 0, TM_DP = 64, TM_BD = 128, TM_ACC0 = 320, TM_ACC1 = 384, TMEM_COLS = 512;
+constexpr int SZ_Q = 16384, SZ_KV = 8192, SZ_R = 24576, SZ_DBD = 49152;
+
+// shared-memory plan per mode: resident operands, a 2-stage ring of streamed operands, work tiles written by the softmax threads
+template <int MODE> struct Plan;
+template <> struct Plan<MODE_DQ> {   // resident Qw Qr dO | ring {K V R} | dS dBD
+  static constexpr int QW = 0, QR = 16384, DO = 32768, RING = 49152, STAGE = SZ_KV * 2 + SZ_R;
+  static constexpr int K = 0, V = SZ_KV, R = 2 * SZ_KV;                     // offsets inside a stage
+  static constexpr int DS = RING + 2 * STAGE, DBD = DS + SZ_Q, P = -1, BAR = DBD + SZ_DBD;
+  static constexpr int RES_BYTES = 3 * SZ_Q, STAGE_TX = STAGE;
+};
+template <> struct Plan<MODE_DKV> {  // resident K V | ring {Qw Qr dO R} | P dS pad
+  static constexpr int K = 0, V = 8192, RING = 16384, STAGE = 3 * SZ_Q + SZ_R;
+  static constexpr int QW = 0, QR = SZ_Q, DO = 2 * SZ_Q, R = 3 * SZ_Q;
+  static constexpr int P = RING + 2 * STAGE, DS = P + SZ_Q, DBD = -1, BAR = DS + 2 * SZ_Q;   // 16 KB pad after dS: 2nd MN atom of dS^T
+  static constexpr int RES_BYTES = 2 * SZ_KV, STAGE_TX = STAGE;
+};
+template <> struct Plan<MODE_DR> {   // resident R | ring {Qw Qr dO K V} | dBD
+  static constexpr int R = 0, RING = 24576, STAGE = 3 * SZ_Q + 2 * SZ_KV;
+  static constexpr int QW = 0, QR = SZ_Q, DO = 2 * SZ_Q, K = 3 * SZ_Q, V = 3 * SZ_Q + SZ_KV;
+  static constexpr int DBD = RING + 2 * STAGE, DS = -1, P = -1, BAR = DBD + SZ_DBD;
+  static constexpr int RES_BYTES = SZ_R, STAGE_TX = STAGE;
+};
+template <int MODE> constexpr int smem_bytes() { return Plan<MODE>::BAR + 128 + 1024; }
+
+struct BwdArgs {
+  const float *lse, *delta;      // [B, H, T]
+  bf16 *dq, *dk_mem, *dv_mem, *dk_cur, *dv_cur;
+  float *dr, *drwb, *drrb;
+  int B, H;
+  TxlBand band;
+  int64_t ldq, ldkv_mem, ldkv_cur;
+  float scale, scale_log2;
+  int delta_min, n_delta;        // MODE_DR: diagonals J - 2I
+};
+
+struct Tile { int b, I, J; };
+
+template <int OUT>
+__device__ __forceinline__ void barrel_shift(float* w, int sh) {
+  const bool b16 = sh & 16, b8 = sh & 8, b4 = sh & 4, b2 = sh & 2, b1 = sh & 1;
+#pragma unroll
+  for (int c = 0; c < OUT + 15; ++c) w[c] = b16 ? w[c + 16] : w[c];
+#pragma unroll
+  for (int c = 0; c < OUT + 7; ++c) w[c] = b8 ? w[c + 8] : w[c];
+#pragma unroll
+  for (int c = 0; c < OUT + 3; ++c) w[c] = b4 ? w[c + 4] : w[c];
+#pragma unroll
+  for (int c = 0; c < OUT + 1; ++c) w[c] = b2 ? w[c + 2] : w[c];
+#pragma unroll
+  for (int c = 0; c < OUT; ++c) w[c] = b1 ? w[c + 1] : w[c];
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ int q_tile_first_kt(const BandGeom& g, int I) { return band_lo(g, I * BQ) / BKV; }
+__device__ __forceinline__ int q_tile_last_kt(const BandGeom& g, int I) {
+  return min(band_hi(g, min(I * BQ + BQ - 1, g.T - 1)), g.klen - 1) / BKV;
+}
+
+// tile enumeration of one CTA
+template <int MODE>
+struct TileIter {
+  int count, b, h, I, J, Ilo, delta, nI;
+  __device__ void init(const BwdArgs& a, const BandGeom& g) {
+    nI = (g.T + BQ - 1) / BQ;
+    if (MODE == MODE_DQ) {
+      I = blockIdx.x; h = blockIdx.y; b = blockIdx.z;
+      J = q_tile_first_kt(g, I);
+      count = q_tile_last_kt(g, I) - J + 1;
+    } else if (MODE == MODE_DKV) {
+      J = blockIdx.x; h = blockIdx.y; b = blockIdx.z;
+      Ilo = -1; count = 0;
+      for (int i = 0; i < nI; ++i)
+        if (q_tile_first_kt(g, i) <= J && J <= q_tile_last_kt(g, i)) { if (Ilo < 0) Ilo = i; ++count; }
+    } else {
+      delta = a.delta_min + (int)blockIdx.x; h = blockIdx.y; b = 0;
+      Ilo = -1; count = 0;
+      for (int i = 0; i < nI; ++i) {
+        int j = 2 * i + delta;
+        if (q_tile_first_kt(g, i) <= j && j <= q_tile_last_kt(g, i)) { if (Ilo < 0) Ilo = i; ++count; }
+      }
+      count *= a.B;
+    }
+  }
+  __device__ Tile get(int n, const BwdArgs& a) const {
+    Tile t;
+    if (MODE == MODE_DQ) { t.b = b; t.I = I; t.J = J + n; }
+    else if (MODE == MODE_DKV) { t.b = b; t.I = Ilo + n; t.J = J; }
+    else { t.I = Ilo + n / a.B; t.b = n % a.B; t.J = 2 * t.I + delta; }
+    return t;
+  }
+};
+
+struct Maps { CUtensorMap qw, qr, dO, km, vm, kc, vc, r; };
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
+  using PL = Plan<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + PL::BAR);
+  uint64_t *full = bars, *empty = bars + 2, *res_full = bars + 4, *f_full = bars + 5, *b_ready = bars + 6, *b_done = bars + 7, *acc_full = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BandGeom g = make_band(a.band);
+  const int HD = a.H * DH;
+  TileIter<MODE> it;
+  it.init(a, g);
+  const int h = it.h;
+  if (MODE == MODE_DKV && it.J * BKV < g.mlen && a.dk_mem == nullptr) return;   // gradients of detached all-zero mems are not needed
+  if (it.count == 0) {
+    if (MODE == MODE_DKV && tid < BKV) {   // key tile outside every band: zero gradient
+      const int j = it.J * BKV + tid;
+      bf16* dk = j < g.mlen ? a.dk_mem + ((int64_t)it.b * g.mlen + j) * a.ldkv_mem : a.dk_cur + ((int64_t)it.b * g.T + (j - g.mlen)) * a.ldkv_cur;
+      bf16* dv = j < g.mlen ? a.dv_mem + ((int64_t)it.b * g.mlen + j) * a.ldkv_mem : a.dv_cur + ((int64_t)it.b * g.T + (j - g.mlen)) * a.ldkv_cur;
+      for (int c = 0; c < DH; ++c) { dk[h * DH + c] = __float2bfloat16(0.f); dv[h * DH + c] = __float2bfloat16(0.f); }
+    }
+    return;
+  }
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+    mbar_init(res_full, 1); mbar_init(f_full, 1); mbar_init(b_ready, N_SOFTMAX); mbar_init(b_done, 1); mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (PL::DBD >= 0) {   // window-space tile: only positions [127-r+32hh, +32) of row r are ever written, the rest must read as 0
+    for (int e = tid; e < SZ_DBD / 16; e += NTHREADS) reinterpret_cast<uint4*>(sm + PL::DBD)[e] = make_uint4(0, 0, 0, 0);
+  }
+  if (MODE == MODE_DKV) {   // pad behind dS (second MN atom of dS^T): finite values only
+    for (int e = tid; e < SZ_Q / 16; e += NTHREADS) reinterpret_cast<uint4*>(sm + PL::DS + SZ_Q)[e] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto k_coords = [&](const Tile& t, const CUtensorMap*& mk, const CUtensorMap*& mv, int& row) {
+    const int j0 = t.J * BKV;
+    if (j0 < g.mlen) { mk = &M.km; mv = &M.vm; row = t.b * g.mlen + j0; }
+    else { mk = &M.kc; mv = &M.vc; row = t.b * g.T + (j0 - g.mlen); }
+  };
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // ======================= TMA producer
+      {
+        const Tile t0 = it.get(0, a);
+        mbar_expect_tx(res_full, PL::RES_BYTES);
+        if (MODE == MODE_DQ) {
+          const int row = t0.b * g.T + t0.I * BQ;
+          tma_load_2d(sm + PL::QW, &M.qw, res_full, h * DH, row);
+          tma_load_2d(sm + PL::QR, &M.qr, res_full, h * DH, row);
+          tma_load_2d(sm + PL::DO, &M.dO, res_full, h * DH, row);
+        } else if (MODE == MODE_DKV) {
+          const CUtensorMap *mk, *mv; int row;
+          k_coords(t0, mk, mv, row);
+          tma_load_2d(sm + PL::K, mk, res_full, h * DH, row);
+          tma_load_2d(sm + PL::V, mv, res_full, h * DH, row);
+        } else {
+          tma_load_2d(sm + PL::R, &M.r, res_full, h * DH, g.T - BQ + BKV * it.delta);   // x0 = T-128-128 I+64 J = T-128+64 delta
+        }
+      }
+      for (int n = 0; n < it.count; ++n) {
+        const int s = n & 1; const uint32_t rph = (n >> 1) & 1;
+        const Tile t = it.get(n, a);
+        mbar_wait(&empty[s], rph ^ 1);
+        uint8_t* st = sm + PL::RING + s * PL::STAGE;
+        mbar_expect_tx(&full[s], PL::STAGE_TX);
+        if (MODE != MODE_DQ) {
+          const int row = t.b * g.T + t.I * BQ;
+          tma_load_2d(st + PL::QW, &M.qw, &full[s], h * DH, row);
+          tma_load_2d(st + PL::QR, &M.qr, &full[s], h * DH, row);
+          tma_load_2d(st + PL::DO, &M.dO, &full[s], h * DH, row);
+        }
+        if (MODE != MODE_DKV) {
+          const CUtensorMap *mk, *mv; int row;
+          k_coords(t, mk, mv, row);
+          tma_load_2d(st + PL::K, mk, &full[s], h * DH, row);
+          tma_load_2d(st + PL::V, mv, &full[s], h * DH, row);
+        }
+        if (MODE != MODE_DR) tma_load_2d(st + PL::R, &M.r, &full[s], h * DH, g.T - BQ - t.I * BQ + t.J * BKV);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      // ======================= MMA issuer
+      const uint32_t id_s = umma_idesc_bf16(BQ, BKV, 0, 0), id_bd = umma_idesc_bf16(BQ, WIN, 0, 0);
+      const uint32_t id_kn = umma_idesc_bf16(BQ, DH, 0, 1);   // A K-major, B MN-major
+      const uint32_t id_nn = umma_idesc_bf16(BQ, DH, 1, 1);   // A MN-major (transposed tile), B MN-major
+      const uint32_t base = smem_u32(sm);
+      mbar_wait(res_full, 0);
+      for (int n = 0; n < it.count; ++n) {
+        const int s = n & 1; const uint32_t rph = (n >> 1) & 1, ph = n & 1;
+        const uint32_t st = base + PL::RING + s * PL::STAGE;
+        const uint32_t qw = (MODE == MODE_DQ ? base : st) + PL::QW, qr = (MODE == MODE_DQ ? base : st) + PL::QR;
+        const uint32_t dO = (MODE == MODE_DQ ? base : st) + PL::DO;
+        const uint32_t kk_ = (MODE == MODE_DKV ? base : st) + PL::K, vv = (MODE == MODE_DKV ? base : st) + PL::V;
+        const uint32_t rr = (MODE == MODE_DR ? base : st) + PL::R;
+        mbar_wait(&full[s], rph);
+        tc_fence_after();
+        // ---- front end: S, dP, BD0
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_S, umma_smem_desc(qw + k * 32, 16, 1024), umma_smem_desc(kk_ + k * 32, 16, 1024), id_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_DP, umma_smem_desc(dO + k * 32, 16, 1024), umma_smem_desc(vv + k * 32, 16, 1024), id_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_BD, umma_smem_desc(qr + k * 32, 16, 1024), umma_smem_desc(rr + k * 32, 16, 1024), id_bd, k > 0);
+        umma_commit(f_full);
+        // ---- back end, once the softmax threads have published the bf16 tiles of this band tile
+        mbar_wait(b_ready, ph);
+        tc_fence_after();
+        const uint32_t accum0 = n > 0;
+        if (MODE == MODE_DQ) {
+          const uint32_t ds = base + PL::DS, dbd = base + PL::DBD;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)      // dQw += dS . K
+            umma_bf16(tmem_base + TM_ACC0, umma_smem_desc(ds + k * 32, 16, 1024), umma_smem_desc(kk_ + k * 2048, 8192, 1024), id_kn, accum0 | (k > 0));
+#pragma unroll
+          for (int k = 0; k < 12; ++k)     // dQr += dBD0 . Rwin
+            umma_bf16(tmem_base + TM_ACC1, umma_smem_desc(dbd + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), umma_smem_desc(rr + k * 2048, 8192, 1024), id_kn, accum0 | (k > 0));
+        } else if (MODE == MODE_DKV) {
+          const uint32_t ds = base + PL::DS, pp = base + PL::P;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)      // dK += dS^T . Qw   (rows 64..127 of the accumulator are a second, ignored MN atom)
+            umma_bf16(tmem_base + TM_ACC0, umma_smem_desc(ds + k * 2048, 16384, 1024), umma_smem_desc(qw + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)      // dV += P^T . dO
+            umma_bf16(tmem_base + TM_ACC1, umma_smem_desc(pp + k * 2048, 16384, 1024), umma_smem_desc(dO + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
+        } else {
+          const uint32_t dbd = base + PL::DBD;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)      // dRwin[0..127]   += dBD0[:, 0..127]^T . Qr
+            umma_bf16(tmem_base + TM_ACC0, umma_smem_desc(dbd + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)      // dRwin[64..191]  += dBD0[:, 64..191]^T . Qr   (lanes 64..127 hold window rows 128..191)
+            umma_bf16(tmem_base + TM_ACC1, umma_smem_desc(dbd + 16384 + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
+        }
+        umma_commit(b_done);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ======================= softmax threads: row r = 32*(warp%4)+lane, keys [32*hh, 32*hh+32) of the tile, hh = warp/4
+    const int r = 32 * (warp & 3) + lane, hh = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    const int sh = 31 - lane;
+    const int c0 = 127 - r + 32 * hh;     // first window column this thread writes in the dBD0 tile
+    Tile t = it.get(0, a);
+    float lse2 = 0.f, dlt = 0.f;
+    auto load_row = [&](const Tile& tt, float& l2, float& dl) {
+      const int i = tt.I * BQ + r;
+      l2 = 0.f; dl = 0.f;
+      if (i < g.T) {
+        const int64_t o = ((int64_t)tt.b * a.H + h) * g.T + i;
+        l2 = a.lse[o] * 1.4426950408889634f; dl = a.delta[o];
+      }
+    };
+    load_row(t, lse2, dlt);
+    for (int n = 0; n < it.count; ++n) {
+      const uint32_t ph = n & 1;
+      Tile tn = t; float lse2n = 0.f, dltn = 0.f;
+      if (n + 1 < it.count) { tn = it.get(n + 1, a); if (MODE != MODE_DQ) load_row(tn, lse2n, dltn); else { lse2n = lse2; dltn = dlt; } }
+      const int i0 = t.I * BQ, j0 = t.J * BKV, i = i0 + r;
+      int lo_i = 1, hi_i = 0;
+      if (i < g.T) { lo_i = band_lo(g, i); hi_i = min(band_hi(g, i), g.klen - 1); }
+      const int ilast = min(i0 + BQ - 1, g.T - 1);
+      const bool tile_full = (i0 + BQ <= g.T) && j0 >= band_lo(g, ilast) && j0 + BKV - 1 <= band_hi(g, i0);
+
+      mbar_wait(f_full, ph);
+      tc_fence_after();
+      float p[32], ds[32];
+      tmem_ld_32x32(tmem_base + lane_base + TM_S + 32 * hh, p);
+      tmem_ld_wait();
+#pragma unroll
+      for (int qq = 0; qq < 2; ++qq) {
+        const int qd = 2 * hh + qq;
+        float w[48];
+        const uint32_t cb = TM_BD + 32 * (3 - (warp & 3)) + 16 * qd;
+        tmem_ld_32x16(tmem_base + lane_base + cb, w);
+        tmem_ld_32x16(tmem_base + lane_base + cb + 16, w + 16);
+        tmem_ld_32x16(tmem_base + lane_base + cb + 32, w + 32);
+        tmem_ld_wait();
+        barrel_shift<16>(w, sh);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) p[16 * qq + jj] += w[jj];
+      }
+      tmem_ld_32x32(tmem_base + lane_base + TM_DP + 32 * hh, ds);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const int j = j0 + 32 * hh + jj;
+        const bool valid = tile_full || (j >= lo_i && j <= hi_i);
+        const float pj = valid ? exp2f(fmaf(p[jj], a.scale_log2, -lse2)) : 0.f;
+        p[jj] = pj;
+        ds[jj] = pj * (ds[jj] - dlt) * a.scale;
+      }
+      // previous tile's back-end MMAs must have finished reading the work tiles before they are overwritten
+      if (n > 0) mbar_wait(b_done, (n - 1) & 1);
+      if (PL::P >= 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 o; o.x = pack2(p[c * 8], p[c * 8 + 1]); o.y = pack2(p[c * 8 + 2], p[c * 8 + 3]); o.z = pack2(p[c * 8 + 4], p[c * 8 + 5]); o.w = pack2(p[c * 8 + 6], p[c * 8 + 7]);
+          *reinterpret_cast<uint4*>(sm + PL::P + r * 128 + (((4 * hh + c) ^ (r & 7)) << 4)) = o;
+        }
+      }
+      if (PL::DS >= 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 o; o.x = pack2(ds[c * 8], ds[c * 8 + 1]); o.y = pack2(ds[c * 8 + 2], ds[c * 8 + 3]); o.z = pack2(ds[c * 8 + 4], ds[c * 8 + 5]); o.w = pack2(ds[c * 8 + 6], ds[c * 8 + 7]);
+          *reinterpret_cast<uint4*>(sm + PL::DS + r * 128 + (((4 * hh + c) ^ (r & 7)) << 4)) = o;
+        }
+      }
+      if (PL::DBD >= 0) {
+        // inverse _rel_shift: dBD0[r, c0 + jj] = dS[r, 32 hh + jj]  (bf16 pairs; element address = block, row, swizzled 16-byte chunk)
+        uint8_t* dbd = sm + PL::DBD;
+        auto addr = [&](int c) -> uint8_t* { return dbd + (c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
+        if ((c0 & 1) == 0) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) *reinterpret_cast<uint32_t*>(addr(c0 + 2 * k)) = pack2(ds[2 * k], ds[2 * k + 1]);
+        } else {
+          *reinterpret_cast<bf16*>(addr(c0)) = __float2bfloat16_rn(ds[0]);
+#pragma unroll
+          for (int k = 0; k < 15; ++k) *reinterpret_cast<uint32_t*>(addr(c0 + 1 + 2 * k)) = pack2(ds[2 * k + 1], ds[2 * k + 2]);
+          *reinterpret_cast<bf16*>(addr(c0 + 31)) = __float2bfloat16_rn(ds[31]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(b_ready);
+      t = tn; lse2 = lse2n; dlt = dltn;
+    }
+    // ======================= drain the accumulators
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float v0[32], v1[32];
+    tmem_ld_32x32(tmem_base + lane_base + TM_ACC0 + 32 * hh, v0);
+    tmem_ld_32x32(tmem_base + lane_base + TM_ACC1 + 32 * hh, v1);
+    tmem_ld_wait();
+    const Tile tl = it.get(0, a);
+    if (MODE == MODE_DQ) {
+      const int i = tl.I * BQ + r;
+      if (i < g.T) {
+        uint4* dst = reinterpret_cast<uint4*>(a.dq + ((int64_t)tl.b * g.T + i) * a.ldq + h * DH + 32 * hh);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 o;
+          o.x = pack2(v0[c * 8] + v1[c * 8], v0[c * 8 + 1] + v1[c * 8 + 1]); o.y = pack2(v0[c * 8 + 2] + v1[c * 8 + 2], v0[c * 8 + 3] + v1[c * 8 + 3]);
+          o.z = pack2(v0[c * 8 + 4] + v1[c * 8 + 4], v0[c * 8 + 5] + v1[c * 8 + 5]); o.w = pack2(v0[c * 8 + 6] + v1[c * 8 + 6], v0[c * 8 + 7] + v1[c * 8 + 7]);
+          dst[c] = o;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { v0[c] = 0.f; v1[c] = 0.f; }
+      }
+      // bias gradients: column sums over this warp's 32 rows, one atomic per column per warp
+      float s0 = 0.f, s1 = 0.f;
+      {
+        float tmp[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tmp[c] = v0[c];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+          for (int c = 0; c < off; ++c) { bool up = lane & off; float send = up ? tmp[c] : tmp[c + off]; float keep = up ? tmp[c + off] : tmp[c]; tmp[c] = keep + __shfl_xor_sync(0xffffffffu, send, off); }
+        s0 = tmp[0];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tmp[c] = v1[c];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+          for (int c = 0; c < off; ++c) { bool up = lane & off; float send = up ? tmp[c] : tmp[c + off]; float keep = up ? tmp[c + off] : tmp[c]; tmp[c] = keep + __shfl_xor_sync(0xffffffffu, send, off); }
+        s1 = tmp[0];
+      }
+      atomicAdd(&a.drwb[h * DH + 32 * hh + lane], s0);
+      atomicAdd(&a.drrb[h * DH + 32 * hh + lane], s1);
+    } else if (MODE == MODE_DKV) {
+      if (r < BKV) {
+        const int j = tl.J * BKV + r;
+        bf16 *dk, *dv;
+        if (j < g.mlen) { dk = a.dk_mem + ((int64_t)tl.b * g.mlen + j) * a.ldkv_mem; dv = a.dv_mem + ((int64_t)tl.b * g.mlen + j) * a.ldkv_mem; }
+        else { dk = a.dk_cur + ((int64_t)tl.b * g.T + (j - g.mlen)) * a.ldkv_cur; dv = a.dv_cur + ((int64_t)tl.b * g.T + (j - g.mlen)) * a.ldkv_cur; }
+        uint4* pk = reinterpret_cast<uint4*>(dk + h * DH + 32 * hh);
+        uint4* pv = reinterpret_cast<uint4*>(dv + h * DH + 32 * hh);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 o; o.x = pack2(v0[c * 8], v0[c * 8 + 1]); o.y = pack2(v0[c * 8 + 2], v0[c * 8 + 3]); o.z = pack2(v0[c * 8 + 4], v0[c * 8 + 5]); o.w = pack2(v0[c * 8 + 6], v0[c * 8 + 7]);
+          pk[c] = o;
+          uint4 u; u.x = pack2(v1[c * 8], v1[c * 8 + 1]); u.y = pack2(v1[c * 8 + 2], v1[c * 8 + 3]); u.z = pack2(v1[c * 8 + 4], v1[c * 8 + 5]); u.w = pack2(v1[c * 8 + 6], v1[c * 8 + 7]);
+          pv[c] = u;
+        }
+      }
+    } else {
+      const int x0 = g.T - BQ + BKV * it.delta;
+      const int xa = x0 + r;                 // acc0: window row r
+      if (xa >= 0 && xa < g.klen) {
+        float* d = a.dr + (int64_t)xa * HD + h * DH + 32 * hh;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) atomicAdd(d + c, v0[c]);
+      }
+      const int xb = x0 + 64 + r;            // acc1: lanes 64..127 hold window rows 128..191
+      if (r >= 64 && xb >= 0 && xb < g.klen) {
+        float* d = a.dr + (int64_t)xb * HD + h * DH + 32 * hh;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) atomicAdd(d + c, v1[c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// qw = q + r_w_bias, qr = q + r_r_bias (bf16, [B*T, HD]); delta[b,h,i] = sum_c dO.O
+__global__ void relattn_bwd_prep_kernel(const bf16* __restrict__ q, int64_t ldq, const float* __restrict__ rwb, const float* __restrict__ rrb,
+                                        const bf16* __restrict__ out, const bf16* __restrict__ dout, bf16* __restrict__ qw, bf16* __restrict__ qr,
+                                        float* __restrict__ delta, int B, int T, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t total = (int64_t)B * T * H;
+  if (gw >= total) return;
+  const int h = (int)(gw % H); const int64_t n = gw / H;     // n = b*T + i
+  const int HD = H * DH, c = h * DH + 2 * lane;
+  const __nv_bfloat162 qv = *reinterpret_cast<const __nv_bfloat162*>(q + n * ldq + c);
+  const float q0 = __bfloat162float(qv.x), q1 = __bfloat162float(qv.y);
+  *reinterpret_cast<__nv_bfloat162*>(qw + n * HD + c) = __floats2bfloat162_rn(q0 + rwb[c], q1 + rwb[c + 1]);
+  *reinterpret_cast<__nv_bfloat162*>(qr + n * HD + c) = __floats2bfloat162_rn(q0 + rrb[c], q1 + rrb[c + 1]);
+  const __nv_bfloat162 ov = *reinterpret_cast<const __nv_bfloat162*>(out + n * HD + c);
+  const __nv_bfloat162 dv = *reinterpret_cast<const __nv_bfloat162*>(dout + n * HD + c);
+  float s = __bfloat162float(ov.x) * __bfloat162float(dv.x) + __bfloat162float(ov.y) * __bfloat162float(dv.y);
+  s = warp_sum(s);
+  if (lane == 0) { const int64_t b = n / T, i = n % T; delta[(b * H + h) * T + i] = s; }
+}
+
+template <int MODE>
+int launch_mode(const Maps& M, const BwdArgs& a, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TXL_CUDA(cudaFuncSetAttribute(relattn_bwd_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<MODE>()));
+    attr_set = true;
+  }
+  relattn_bwd_tc_kernel<MODE><<<grid, NTHREADS, smem_bytes<MODE>(), st>>>(M, a);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+}  // namespace
+
+int64_t txl_relattn_bwd_tc_workspace(const TxlAttnDims* D) {
+  const int64_t n = (int64_t)D->B * D->band.T * D->H * D->dh;
+  return 2 * n * 2 + (int64_t)D->B * D->H * D->band.T * 4 + 1024;
+}
+
+int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur, const void* r, const float* rwb,
+                       const float* rrb, const void* out, const float* lse, const void* dout, void* dq, void* dk_mem, void* dv_mem, void* dk_cur,
+                       void* dv_cur, float* dr, float* drwb, float* drrb, void* ws, const TxlAttnDims* D, void* stream, int* handled) {
+  *handled = 0;
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("TXL_DISABLE_TC_ATTN_BWD"); const char* e2 = getenv("TXL_DISABLE_TC"); disabled = ((e && e[0] == '1') || (e2 && e2[0] == '1')) ? 1 : 0; }
+  if (disabled) return TXL_OK;
+  const int T = D->band.T, mlen = D->band.mlen, klen = T + mlen, HD = D->H * D->dh;
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if (D->dh != DH || (T % BKV) || (mlen % BKV) || klen < WIN || mlen <= 0) return TXL_OK;
+  if (!(D->band.same_length && mlen == D->band.mem_len)) return TXL_OK;       // dense distance-space band only
+  if ((D->ldq % 8) || (D->ldkv_cur % 8) || (D->ldkv_mem % 8)) return TXL_OK;
+  if (!al16(q) || !al16(k_cur) || !al16(v_cur) || !al16(k_mem) || !al16(v_mem) || !al16(r) || !al16(out) || !al16(dout) || !al16(dq) || !al16(dk_cur) ||
+      !al16(dv_cur) || !al16(ws) || (dk_mem && (!al16(dk_mem) || !al16(dv_mem))))
+    return TXL_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)D->B * T * HD;
+  bf16* qw = (bf16*)ws; bf16* qr = qw + n; float* delta = (float*)(qr + n);
+  {
+    const int64_t warps = (int64_t)D->B * T * D->H;
+    relattn_bwd_prep_kernel<<<(unsigned)cdiv64(warps, 8), 256, 0, st>>>((const bf16*)q, D->ldq, rwb, rrb, (const bf16*)out, (const bf16*)dout, qw, qr, delta, D->B, T, D->H);
+    TXL_LAUNCH_CHECK();
+  }
+  Maps M;
+  int rc;
+  if ((rc = txl_make_tmap_2d(&M.qw, qw, (uint64_t)D->B * T, (uint64_t)HD, (uint64_t)HD, BQ, DH))) return rc;
+  if ((rc = txl_make_tmap_2d(&M.qr, qr, (uint64_t)D->B * T, (uint64_t)HD, (uint64_t)HD, BQ, DH))) return rc;
+  if ((rc = txl_make_tmap_2d(&M.dO, dout, (uint64_t)D->B * T, (uint64_t)HD, (uint64_t)HD, BQ, DH))) return rc;
+  if ((rc = txl_make_tmap_2d(&M.kc, k_cur, (uint64_t)D->B * T, (uint64_t)HD, (uint64_t)D->ldkv_cur, BKV, DH))) return rc;
+  if ((rc = txl_make_tmap_2d(&M.vc, v_cur, (uint64_t)D->B * T, (uint64_t)HD, (uint64_t)D->ldkv_cur, BKV, DH))) return rc;
+  if ((rc = txl_make_tmap_2d(&M.km, k_mem, (uint64_t)D->B * mlen, (uint64_t)HD, (uint64_t)D->ldkv_mem, BKV, DH))) return rc;
+  if ((rc = txl_make_tmap_2d(&M.vm, v_mem, (uint64_t)D->B * mlen, (uint64_t)HD, (uint64_t)D->ldkv_mem, BKV, DH))) return rc;
+  if ((rc = txl_make_tmap_2d(&M.r, r, (uint64_t)klen, (uint64_t)HD, (uint64_t)HD, WIN, DH))) return rc;
+
+  BwdArgs a;
+  a.lse = lse; a.delta = delta; a.dq = (bf16*)dq; a.dk_mem = (bf16*)dk_mem; a.dv_mem = (bf16*)dv_mem; a.dk_cur = (bf16*)dk_cur; a.dv_cur = (bf16*)dv_cur;
+  a.dr = dr; a.drwb = drwb; a.drrb = drrb; a.B = D->B; a.H = D->H; a.band = D->band; a.ldq = D->ldq; a.ldkv_mem = D->ldkv_mem; a.ldkv_cur = D->ldkv_cur;
+  a.scale = 1.f / sqrtf((float)DH); a.scale_log2 = a.scale * 1.4426950408889634f;
+  // diagonals J - 2I touched by the band
+  const BandGeom g = make_band(D->band);
+  const int nI = (T + BQ - 1) / BQ;
+  int dmin = 1 << 30, dmax = -(1 << 30);
+  for (int I = 0; I < nI; ++I) {
+    int j0 = band_lo(g, I * BQ) / BKV;
+    int ilast = I * BQ + BQ - 1 < T - 1 ? I * BQ + BQ - 1 : T - 1;
+    int hi = band_hi(g, ilast) < klen - 1 ? band_hi(g, ilast) : klen - 1;
+    int j1 = hi / BKV;
+    if (j0 - 2 * I < dmin) dmin = j0 - 2 * I;
+    if (j1 - 2 * I > dmax) dmax = j1 - 2 * I;
+  }
+  a.delta_min = dmin; a.n_delta = dmax - dmin + 1;
+  if ((rc = launch_mode<MODE_DQ>(M, a, dim3(nI, D->H, D->B), st))) return rc;
+  if ((rc = launch_mode<MODE_DKV>(M, a, dim3(klen / BKV, D->H, D->B), st))) return rc;
+  if ((rc = launch_mode<MODE_DR>(M, a, dim3(a.n_delta, D->H, 1), st))) return rc;
+  *handled = 1;
+  return TXL_OK;
+}
