@@ -59,8 +59,8 @@ int txl_relattn_index_map(const TxlBand* band, uint8_t* masked, int32_t* ridx, i
  * out[n,:] = E[ids[n],:] * scale, then inverted dropout (p, seed, site) if p>0. */
 int txl_embed_fwd(const int64_t* ids, const void* E, void* out, int64_t n_tok, int d, int V, float scale,
                   int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
-/* dE[ids[n],:] += dOut[n,:] * scale (* dropout mask)   (fp32 atomics) */
-int txl_embed_bwd(const int64_t* ids, const void* dOut, float* dE, int64_t n_tok, int d, int V, float scale,
+/* dE[ids[n],:] += (dOut[n,:] + dOut2[n,:]) * scale (* dropout mask)   (fp32 atomics; dOut2 may be NULL) */
+int txl_embed_bwd(const int64_t* ids, const void* dOut, const void* dOut2, float* dE, int64_t n_tok, int d, int V, float scale,
                   int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
 
 /* ---- sinusoid table  [A.2 step 5 pos_seq + A.6 PositionalEmbedding] --------------------------------
@@ -97,9 +97,9 @@ int txl_gemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_
 int txl_add_ln_fwd(const void* x, const void* r, const float* gamma, const float* beta, void* y, void* z,
                    float* mean, float* rstd, int64_t rows, int d, float eps, int dtype,
                    float drop_p, uint64_t seed, uint32_t site, void* stream);
-/* dz = LN'(dy);  dgamma += sum dy*xhat; dbeta += sum dy.   dx_out = dz (+ dx_out if accumulate);
- * dr_out = dz * dropout-mask.  dx_out may alias dy. */
-int txl_add_ln_bwd(const void* dy, const void* z, const float* gamma, const float* mean, const float* rstd,
+/* dyt = dy (+ dy2 if non-NULL: the two branches that meet at a residual node);  dz = LN'(dyt);
+ * dgamma += sum dyt*xhat; dbeta += sum dyt.   dx_out = dz (+ dx_out if accumulate);  dr_out = dz * dropout-mask.  dx_out may alias dy. */
+int txl_add_ln_bwd(const void* dy, const void* dy2, const void* z, const float* gamma, const float* mean, const float* rstd,
                    void* dx_out, int accumulate_dx, void* dr_out, float* dgamma, float* dbeta,
                    int64_t rows, int d, int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream);
 /* out[n] += sum_m X[m,n]  (fp32 accumulate; bias gradients of CoreNet.3 / crit.out_layers.0) */

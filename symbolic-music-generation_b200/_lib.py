@@ -45,11 +45,11 @@ SIGNATURES = {
     'txl_launch_count': (C.c_ulonglong, []),
     'txl_relattn_index_map': (_i, [C.POINTER(TxlBand), _vp, _vp, _vp, _vp, _vp]),
     'txl_embed_fwd': (_i, [_vp, _vp, _vp, _i64, _i, _i, _f, _i, _f, _u64, _u32, _vp]),
-    'txl_embed_bwd': (_i, [_vp, _vp, _vp, _i64, _i, _i, _f, _i, _f, _u64, _u32, _vp]),
+    'txl_embed_bwd': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _f, _u64, _u32, _vp]),
     'txl_posemb_table': (_i, [_vp, _i, _i, _i, _i, _f, _u64, _u32, _vp]),
     'txl_gemm': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i, _i, _i, _i, C.POINTER(TxlEpilogue), _vp]),
     'txl_add_ln_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _i, _f, _u64, _u32, _vp]),
-    'txl_add_ln_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _i, _f, _u64, _u32, _vp]),
+    'txl_add_ln_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _i, _f, _u64, _u32, _vp]),
     'txl_colsum': (_i, [_vp, _i64, _i64, _i64, _i, _vp, _vp]),
     'txl_dropout': (_i, [_vp, _vp, _i64, _i, _f, _u64, _u32, _vp]),
     'txl_relattn_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(TxlAttnDims), _vp]),

@@ -81,14 +81,23 @@ __host__ __device__ __forceinline__ int band_num_r(const BandGeom& g) {
 }
 
 // ------------------------------------------------------------------ counter-based dropout
-// keep-mask for logical element `idx` of dropout site `site`; identical in forward and backward.
+// keep-mask for logical element `idx` of dropout site `site`; identical in forward and backward and in every kernel.
+// One 32-bit avalanche hash (lowbias32) serves two neighbouring elements (16 random bits each).
+__device__ __forceinline__ uint32_t dropout_key(uint64_t seed, uint32_t site) {
+  return (uint32_t)seed * 0x9E3779B1u + (uint32_t)(seed >> 32) * 0x85EBCA77u + (site + 1u) * 0xC2B2AE3Du;
+}
+__device__ __forceinline__ uint32_t dropout_hash(uint32_t key, uint64_t pair_idx) {
+  uint32_t x = (uint32_t)pair_idx + key + (uint32_t)(pair_idx >> 32) * 0x27D4EB2Fu;
+  x ^= x >> 16; x *= 0x7FEB352Du;
+  x ^= x >> 15; x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t dropout_threshold(float p) { return (uint32_t)(p * 65536.0f); }
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
-  uint64_t x = (idx + 0x9E3779B97F4A7C15ull * (uint64_t)(site + 1)) ^ seed;
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
-  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
-  x ^= x >> 33;
-  float u = (float)(uint32_t)(x >> 40) * (1.0f / 16777216.0f);
-  return u >= p ? inv_keep : 0.0f;
+  const uint32_t h = dropout_hash(dropout_key(seed, site), idx >> 1);
+  const uint32_t u = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+  return u >= dropout_threshold(p) ? inv_keep : 0.0f;
 }
 
 // ------------------------------------------------------------------ warp reductions

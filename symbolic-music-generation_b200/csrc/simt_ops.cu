@@ -73,14 +73,16 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const T* __res
   }
 }
 template <typename T>
-__global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ dOut, float* __restrict__ dE, int64_t n_tok,
+__global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ dOut, const T* __restrict__ dOut2, float* __restrict__ dE, int64_t n_tok,
                                  int d, int V, float scale, float p, float inv_keep, uint64_t seed, uint32_t site) {
   int64_t total = n_tok * d;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t n = idx / d; int c = (int)(idx % d);
     int64_t id = ids[n];
     if (id < 0 || id >= V) continue;
-    float v = to_f32(dOut[idx]) * scale;
+    float v = to_f32(dOut[idx]);
+    if (dOut2) v += to_f32(dOut2[idx]);
+    v *= scale;
     if (p > 0.f) v *= dropout_scale(seed, site, (uint64_t)idx, p, inv_keep);
     atomicAdd(&dE[id * d + c], v);
   }
@@ -94,12 +96,12 @@ extern "C" int txl_embed_fwd(const int64_t* ids, const void* E, void* out, int64
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }
-extern "C" int txl_embed_bwd(const int64_t* ids, const void* dOut, float* dE, int64_t n_tok, int d, int V, float scale,
+extern "C" int txl_embed_bwd(const int64_t* ids, const void* dOut, const void* dOut2, float* dE, int64_t n_tok, int d, int V, float scale,
                              int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream) {
   TXL_CHECK_ARG(n_tok > 0 && d > 0 && V > 0, "embed_bwd: bad sizes");
   int grid = (int)imin64(cdiv64(n_tok * d, 256), (int64_t)txl_num_sms() * 16);
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  DISPATCH_DTYPE(dtype, (embed_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(ids, (const T*)dOut, dE, n_tok, d, V, scale, drop_p, ik, seed, site)));
+  DISPATCH_DTYPE(dtype, (embed_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(ids, (const T*)dOut, (const T*)dOut2, dE, n_tok, d, V, scale, drop_p, ik, seed, site)));
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }
@@ -131,44 +133,82 @@ extern "C" int txl_posemb_table(void* out, int klen, int clamp_len, int d, int d
   return TXL_OK;
 }
 
-// ------------------------------------------------------------------ residual + LayerNorm (one warp per row)
-constexpr int LN_MAX_PER_LANE = 32;  // d <= 1024
+// ------------------------------------------------------------------ residual + LayerNorm (one warp per row, 16-byte vectors)
+constexpr int LN_VEC = 8;           // elements per lane per vector step
+constexpr int LN_MAX_STEPS = 4;     // d <= 1024
+template <typename T> struct Vec8 { T v[LN_VEC]; };
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float* f) {
+  if constexpr (sizeof(T) == 2) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const bf16* e = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = __bfloat162float(e[k]);
+  } else {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float* f) {
+  if constexpr (sizeof(T) == 2) {
+    uint4 u;
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]), c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b); u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(p) = u;
+  } else {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+// rounds through the storage type so that forward statistics and backward see the same z
+template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f32(from_f32<T>(v)); }
+
 template <typename T>
-__global__ void add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ z, float* __restrict__ mean,
                                   float* __restrict__ rstd, int64_t rows, int d, float eps, float p, float inv_keep, uint64_t seed,
                                   uint32_t site) {
-  int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
-  int per = d / 32;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
   for (int64_t row = warp; row < rows; row += (int64_t)gridDim.x * wpb) {
-    float v[LN_MAX_PER_LANE];
+    float v[LN_MAX_STEPS][LN_VEC];
     float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < LN_MAX_PER_LANE; ++e) {
-      if (e < per) {
-        int c = e * 32 + lane;
-        float rv = r ? to_f32(r[row * d + c]) : 0.f;
-        if (p > 0.f) rv *= dropout_scale(seed, site, (uint64_t)(row * d + c), p, inv_keep);
-        float zz = to_f32(x[row * d + c]) + rv;
-        // the stored z is what backward sees; normalise the rounded value so fwd/bwd agree
-        T zt = from_f32<T>(zz);
-        if (z) z[row * d + c] = zt;
-        v[e] = to_f32(zt);
-        s += v[e];
+    for (int e = 0; e < LN_MAX_STEPS; ++e) {
+      const int c = (e * 32 + lane) * LN_VEC;
+      if (c < d) {
+        float xv[LN_VEC], rv[LN_VEC];
+        ld8(x + row * d + c, xv);
+        if (r) ld8(r + row * d + c, rv);
+#pragma unroll
+        for (int k = 0; k < LN_VEC; ++k) {
+          float rr = r ? rv[k] : 0.f;
+          if (p > 0.f) rr *= dropout_scale(seed, site, (uint64_t)(row * d + c + k), p, inv_keep);
+          v[e][k] = round_to<T>(xv[k] + rr);
+          s += v[e][k];
+        }
+        if (z) st8(z + row * d + c, v[e]);
       }
     }
-    float mu = warp_sum(s) / d;
+    const float mu = warp_sum(s) / d;
     float q = 0.f;
 #pragma unroll
-    for (int e = 0; e < LN_MAX_PER_LANE; ++e)
-      if (e < per) { float t = v[e] - mu; q += t * t; }
-    float rs = rsqrtf(warp_sum(q) / d + eps);
+    for (int e = 0; e < LN_MAX_STEPS; ++e) {
+      const int c = (e * 32 + lane) * LN_VEC;
+      if (c < d) {
 #pragma unroll
-    for (int e = 0; e < LN_MAX_PER_LANE; ++e) {
-      if (e < per) {
-        int c = e * 32 + lane;
-        y[row * d + c] = from_f32<T>((v[e] - mu) * rs * gamma[c] + beta[c]);
+        for (int k = 0; k < LN_VEC; ++k) { float t = v[e][k] - mu; q += t * t; }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) / d + eps);
+#pragma unroll
+    for (int e = 0; e < LN_MAX_STEPS; ++e) {
+      const int c = (e * 32 + lane) * LN_VEC;
+      if (c < d) {
+        float gm[LN_VEC], bt[LN_VEC], o[LN_VEC];
+        ld8(gamma + c, gm); ld8(beta + c, bt);
+#pragma unroll
+        for (int k = 0; k < LN_VEC; ++k) o[k] = (v[e][k] - mu) * rs * gm[k] + bt[k];
+        st8(y + row * d + c, o);
       }
     }
     if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
@@ -177,7 +217,7 @@ __global__ void add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__
 extern "C" int txl_add_ln_fwd(const void* x, const void* r, const float* gamma, const float* beta, void* y, void* z,
                               float* mean, float* rstd, int64_t rows, int d, float eps, int dtype, float drop_p, uint64_t seed,
                               uint32_t site, void* stream) {
-  TXL_CHECK_ARG(rows > 0 && d % 32 == 0 && d <= 32 * LN_MAX_PER_LANE, "add_ln_fwd: d=%d must be a multiple of 32, <= 1024", d);
+  TXL_CHECK_ARG(rows > 0 && d % LN_VEC == 0 && d <= 32 * LN_VEC * LN_MAX_STEPS, "add_ln_fwd: d=%d must be a multiple of 8, <= 1024", d);
   int grid = (int)imin64(cdiv64(rows, 8), (int64_t)txl_num_sms() * 8);
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   DISPATCH_DTYPE(dtype, (add_ln_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)r, gamma, beta, (T*)y, (T*)z, mean, rstd, rows, d, eps, drop_p, ik, seed, site)));
@@ -185,58 +225,74 @@ extern "C" int txl_add_ln_fwd(const void* x, const void* r, const float* gamma, 
   return TXL_OK;
 }
 
+// dy_total = dy (+ dy2);  dz = LN'(dy_total)
 template <typename T>
-__global__ void add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, const T* __restrict__ z, const float* __restrict__ gamma,
                                   const float* __restrict__ mean, const float* __restrict__ rstd, T* dx_out, int accumulate_dx,
                                   T* dr_out, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int d, float p,
                                   float inv_keep, uint64_t seed, uint32_t site) {
   extern __shared__ float sm[];  // [2][d] block partials
-  int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
-  int per = d / 32;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
   for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
   __syncthreads();
-  float ag[LN_MAX_PER_LANE], ab[LN_MAX_PER_LANE];
+  float ag[LN_MAX_STEPS][LN_VEC], ab[LN_MAX_STEPS][LN_VEC];
 #pragma unroll
-  for (int e = 0; e < LN_MAX_PER_LANE; ++e) { ag[e] = 0.f; ab[e] = 0.f; }
+  for (int e = 0; e < LN_MAX_STEPS; ++e)
+#pragma unroll
+    for (int k = 0; k < LN_VEC; ++k) { ag[e][k] = 0.f; ab[e][k] = 0.f; }
   for (int64_t row = warp; row < rows; row += (int64_t)gridDim.x * wpb) {
-    float mu = mean[row], rs = rstd[row];
-    float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
+    const float mu = mean[row], rs = rstd[row];
+    float g[LN_MAX_STEPS][LN_VEC], xh[LN_MAX_STEPS][LN_VEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int e = 0; e < LN_MAX_PER_LANE; ++e) {
-      if (e < per) {
-        int c = e * 32 + lane;
-        float dyv = to_f32(dy[row * d + c]);
-        xh[e] = (to_f32(z[row * d + c]) - mu) * rs;
-        g[e] = dyv * gamma[c];
-        s1 += g[e]; s2 += g[e] * xh[e];
-        ag[e] += dyv * xh[e]; ab[e] += dyv;
+    for (int e = 0; e < LN_MAX_STEPS; ++e) {
+      const int c = (e * 32 + lane) * LN_VEC;
+      if (c < d) {
+        float dyv[LN_VEC], zv[LN_VEC], gm[LN_VEC];
+        ld8(dy + row * d + c, dyv);
+        if (dy2) { float t2[LN_VEC]; ld8(dy2 + row * d + c, t2);
+#pragma unroll
+          for (int k = 0; k < LN_VEC; ++k) dyv[k] += t2[k]; }
+        ld8(z + row * d + c, zv); ld8(gamma + c, gm);
+#pragma unroll
+        for (int k = 0; k < LN_VEC; ++k) {
+          xh[e][k] = (zv[k] - mu) * rs;
+          g[e][k] = dyv[k] * gm[k];
+          s1 += g[e][k]; s2 += g[e][k] * xh[e][k];
+          ag[e][k] += dyv[k] * xh[e][k]; ab[e][k] += dyv[k];
+        }
       }
     }
     s1 = warp_sum(s1) / d; s2 = warp_sum(s2) / d;
 #pragma unroll
-    for (int e = 0; e < LN_MAX_PER_LANE; ++e) {
-      if (e < per) {
-        int c = e * 32 + lane;
-        float dz = rs * (g[e] - s1 - xh[e] * s2);
+    for (int e = 0; e < LN_MAX_STEPS; ++e) {
+      const int c = (e * 32 + lane) * LN_VEC;
+      if (c < d) {
+        float dz[LN_VEC];
+#pragma unroll
+        for (int k = 0; k < LN_VEC; ++k) dz[k] = rs * (g[e][k] - s1 - xh[e][k] * s2);
         if (dr_out) {
-          float dm = p > 0.f ? dropout_scale(seed, site, (uint64_t)(row * d + c), p, inv_keep) : 1.f;
-          dr_out[row * d + c] = from_f32<T>(dz * dm);
+          float o[LN_VEC];
+#pragma unroll
+          for (int k = 0; k < LN_VEC; ++k) o[k] = dz[k] * (p > 0.f ? dropout_scale(seed, site, (uint64_t)(row * d + c + k), p, inv_keep) : 1.f);
+          st8(dr_out + row * d + c, o);
         }
         if (dx_out) {
-          float acc = accumulate_dx ? to_f32(dx_out[row * d + c]) : 0.f;
-          dx_out[row * d + c] = from_f32<T>(dz + acc);
+          if (accumulate_dx) { float old[LN_VEC]; ld8(dx_out + row * d + c, old);
+#pragma unroll
+            for (int k = 0; k < LN_VEC; ++k) dz[k] += old[k]; }
+          st8(dx_out + row * d + c, dz);
         }
       }
     }
   }
 #pragma unroll
-  for (int e = 0; e < LN_MAX_PER_LANE; ++e) {
-    if (e < per) {
-      int c = e * 32 + lane;
-      atomicAdd(&sm[c], ag[e]);
-      atomicAdd(&sm[d + c], ab[e]);
+  for (int e = 0; e < LN_MAX_STEPS; ++e) {
+    const int c = (e * 32 + lane) * LN_VEC;
+    if (c < d) {
+#pragma unroll
+      for (int k = 0; k < LN_VEC; ++k) { atomicAdd(&sm[c + k], ag[e][k]); atomicAdd(&sm[d + c + k], ab[e][k]); }
     }
   }
   __syncthreads();
@@ -245,15 +301,15 @@ __global__ void add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict_
     if (dbeta) atomicAdd(&dbeta[c], sm[d + c]);
   }
 }
-extern "C" int txl_add_ln_bwd(const void* dy, const void* z, const float* gamma, const float* mean, const float* rstd,
+extern "C" int txl_add_ln_bwd(const void* dy, const void* dy2, const void* z, const float* gamma, const float* mean, const float* rstd,
                               void* dx_out, int accumulate_dx, void* dr_out, float* dgamma, float* dbeta, int64_t rows, int d,
                               int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream) {
-  TXL_CHECK_ARG(rows > 0 && d % 32 == 0 && d <= 32 * LN_MAX_PER_LANE, "add_ln_bwd: d=%d must be a multiple of 32, <= 1024", d);
-  // dx_out may alias dy only when it is the same element-for-element buffer (each element is read before written by its own lane)
+  TXL_CHECK_ARG(rows > 0 && d % LN_VEC == 0 && d <= 32 * LN_VEC * LN_MAX_STEPS, "add_ln_bwd: d=%d must be a multiple of 8, <= 1024", d);
+  // dx_out may alias dy: each lane reads its elements of a row before any lane of the warp writes them
   int grid = (int)imin64(cdiv64(rows, 8), (int64_t)txl_num_sms() * 4);
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   size_t smem = 2 * (size_t)d * sizeof(float);
-  DISPATCH_DTYPE(dtype, (add_ln_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)dy, (const T*)z, gamma, mean, rstd, (T*)dx_out, accumulate_dx, (T*)dr_out, dgamma, dbeta, rows, d, drop_p, ik, seed, site)));
+  DISPATCH_DTYPE(dtype, (add_ln_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)dy, (const T*)dy2, (const T*)z, gamma, mean, rstd, (T*)dx_out, accumulate_dx, (T*)dr_out, dgamma, dbeta, rows, d, drop_p, ik, seed, site)));
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }

@@ -146,19 +146,20 @@ def backward(cfg, W: List[LayerW], G: List[LayerW], E, gE, g_out_bias, sv: Saved
     dcore = ops.gemm(dl, E)                                                                           # (N, d)
     sv.logits = None
     dx = ops.dropout(dcore, p, seed, SITE_FINAL, out=dcore) if p > 0 else dcore
+    dx2 = None      # second branch meeting dx at the residual node (summed on read by the next LayerNorm backward)
     for li in range(len(W) - 1, -1, -1):
         w, gw, s = W[li], G[li], sv.layers[li]
         site = SITE_LAYER0 + 8 * li
         # LN2 / FF
-        dy1, df = ops.add_ln_bwd(dx, s['z2'], w.ln2_w, s['mean2'], s['rstd2'], gw.ln2_w, gw.ln2_b, drop_p=p, seed=seed, site=site + S_FF_OUT)
+        dy1, df = ops.add_ln_bwd(dx, s['z2'], w.ln2_w, s['mean2'], s['rstd2'], gw.ln2_w, gw.ln2_b, drop_p=p, seed=seed, site=site + S_FF_OUT, dy2=dx2)
         ops.colsum(df, gw.b2)
         ops.gemm(df, s['h'], transA=True, out=gw.w2, accumulate=True)                                 # dW2 += df^T h
         dh_ = ops.gemm(df, w.w2, mask_pos_aux=s['h'], colsum=gw.b1, drop_p=p, seed=seed, site=site + S_FF_INNER)   # (N, di)
         ops.gemm(dh_, s['y1'], transA=True, out=gw.w1, accumulate=True)                               # dW1 += dh^T y1
-        ops.gemm(dh_, w.w1, out=dy1, accumulate=True)                                                 # dy1 += dh W1
+        dff = ops.gemm(dh_, w.w1)                                                                     # dh W1  (N, d)
         del dh_, df
         # LN1 / o_net
-        dxn, dao = ops.add_ln_bwd(dy1, s['z1'], w.ln1_w, s['mean1'], s['rstd1'], gw.ln1_w, gw.ln1_b, drop_p=p, seed=seed, site=site + S_ATTN_OUT)
+        dxn, dao = ops.add_ln_bwd(dy1, s['z1'], w.ln1_w, s['mean1'], s['rstd1'], gw.ln1_w, gw.ln1_b, drop_p=p, seed=seed, site=site + S_ATTN_OUT, dy2=dff)
         ops.gemm(dao, s['vec'], transA=True, out=gw.o, accumulate=True)                               # dWo += dao^T vec
         dvec = ops.gemm(dao, w.o)                                                                     # (N, d)
         # attention
@@ -176,11 +177,11 @@ def backward(cfg, W: List[LayerW], G: List[LayerW], E, gE, g_out_bias, sv: Saved
         ops.gemm(dr_c, sv.pos, transA=True, out=gw.r, accumulate=True)
         # qkv_net
         ops.gemm(dqkv, s['x'], transA=True, out=gw.qkv, accumulate=True)                              # dWqkv += dqkv^T x
-        ops.gemm(dqkv, w.qkv, out=dxn, accumulate=True)                                               # dx += dqkv Wqkv
+        dx2 = ops.gemm(dqkv, w.qkv)                                                                   # dqkv Wqkv  (N, d)
         if dkvm is not None:
             ops.gemm(dkvm, sv.mems[li].reshape(B * mlen, d), transA=True, out=gw.qkv[d:], accumulate=True)
         dx = dxn
         sv.layers[li] = None
         if on_layer_done is not None:
             on_layer_done(li)
-    ops.embed_bwd(sv.ids.reshape(-1), dx, gE, math.sqrt(d), p, seed, SITE_EMB)
+    ops.embed_bwd(sv.ids.reshape(-1), dx, gE, math.sqrt(d), p, seed, SITE_EMB, dOut2=dx2)

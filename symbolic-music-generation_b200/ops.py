@@ -51,10 +51,10 @@ def embed_fwd(ids, E, scale, drop_p=0.0, seed=0, site=0):
     return out
 
 
-def embed_bwd(ids, dOut, dE, scale, drop_p=0.0, seed=0, site=0):
+def embed_bwd(ids, dOut, dE, scale, drop_p=0.0, seed=0, site=0, dOut2=None):
     V, d = dE.shape
     assert dE.dtype == torch.float32
-    check(_lib().txl_embed_bwd(ptr(ids), ptr(dOut), ptr(dE), ids.numel(), d, V, float(scale), dtype_code(dOut.dtype),
+    check(_lib().txl_embed_bwd(ptr(ids), ptr(dOut), ptr(dOut2), ptr(dE), ids.numel(), d, V, float(scale), dtype_code(dOut.dtype),
                                float(drop_p), int(seed), int(site), stream_ptr()), 'embed_bwd')
 
 
@@ -103,12 +103,12 @@ def add_ln_fwd(x, r, gamma, beta, eps, drop_p=0.0, seed=0, site=0, save=True):
     return y, z, mean, rstd
 
 
-def add_ln_bwd(dy, z, gamma, mean, rstd, dgamma, dbeta, dx_out=None, accumulate_dx=False, want_dr=True, drop_p=0.0, seed=0, site=0):
+def add_ln_bwd(dy, z, gamma, mean, rstd, dgamma, dbeta, dx_out=None, accumulate_dx=False, want_dr=True, drop_p=0.0, seed=0, site=0, dy2=None):
     rows, d = dy.shape
     if dx_out is None:
         dx_out = torch.empty_like(dy)
     dr = torch.empty_like(dy) if want_dr else None
-    check(_lib().txl_add_ln_bwd(ptr(dy), ptr(z), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx_out), int(accumulate_dx), ptr(dr),
+    check(_lib().txl_add_ln_bwd(ptr(dy), ptr(dy2), ptr(z), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx_out), int(accumulate_dx), ptr(dr),
                                 ptr(dgamma), ptr(dbeta), rows, d, dtype_code(dy.dtype), float(drop_p), int(seed), int(site),
                                 stream_ptr()), 'add_ln_bwd')
     return dx_out, dr

@@ -85,7 +85,9 @@ def test_add_ln_fwd_bwd(ops, mode):
     dy = torch.randn(rows, d, device='cuda').to(dt)
     yr.backward(dy.float())
     dg, db = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
-    dx, dr = ops.add_ln_bwd(dy, z, gamma.detach(), mean, rstd, dg, db)
+    half = (dy.float() * 0.25).to(dt)
+    rest = (dy.float() - half.float()).to(dt)
+    dx, dr = ops.add_ln_bwd(rest, z, gamma.detach(), mean, rstd, dg, db, dy2=half)      # two branches summed on read
     torch.testing.assert_close(dx.float(), zr.grad, **tol)
     torch.testing.assert_close(dr.float(), zr.grad, **tol)
     torch.testing.assert_close(dg, gamma.grad, rtol=1e-3, atol=1e-2 if mode == 'bf16' else 1e-3)
