@@ -50,8 +50,9 @@ int txl_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t r
 
 namespace {
 constexpr int BM = 128, BK = 64;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups of four lane-quadrant warps)
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int STAGE_C_BYTES = BM * 128;  // one 64-column bf16 block of the output tile, SWIZZLE_128B
 
 struct GemmParams {
   int64_t M, N, K, ldc;
@@ -61,13 +62,15 @@ struct GemmParams {
   float inv_keep;
   int tiles_m, tiles_n, ksplits, nkb, kb_per_split;
   int a_mn, b_mn;
+  int tma_store;
 };
 
 template <int BN, int STAGES>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int CSTAGE_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = CSTAGE_OFF + 2 * STAGE_C_BYTES;
   static constexpr int SMEM = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -86,10 +89,19 @@ __device__ __forceinline__ float warp_colsum32(float* v, int lane) {
   }
   return v[0];
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int BN, int STAGES, typename TC>
 __global__ void __launch_bounds__(THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using C_ = Cfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -103,7 +115,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -175,98 +187,172 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ================= epilogue (warps 2..5; TMEM lane quadrant = warp % 4)
-    const int q = warp & 3;
+    // ================= epilogue: group g = (warp-2)/4 owns 64-column blocks g, g+2, ...; TMEM lane quadrant = warp % 4
+    const int q = warp & 3, grp = (warp - 2) >> 2;
+    const int r_in_tile = q * 32 + lane;
+    const bool leader = (warp - 2) % 4 == 0 && lane == 0;      // issues this group's TMA stores
     const TxlEpilogue& e = p.epi;
     TC* __restrict__ C = reinterpret_cast<TC*>(p.C);
+    uint8_t* cst = sm + C_::CSTAGE_OFF + grp * STAGE_C_BYTES;
+    const uint32_t dkey = dropout_key(e.seed, e.site);
+    const uint32_t dthr = dropout_threshold(e.drop_p);
+    const bool pair_hash = (p.N & 1) == 0;
     int it = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
       const int tm = unit % p.tiles_m, tn = (unit / p.tiles_m) % p.tiles_n;
       const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-      const int64_t row = (int64_t)tm * BM + q * 32 + lane;
+      const int64_t row = (int64_t)tm * BM + r_in_tile;
       const bool row_ok = row < p.M;
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
+      constexpr int NBLK = BN / 64;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
-        tmem_ld_wait();
-        if (c == BN / 32 - 1) {   // accumulator fully drained into registers: hand TMEM back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+      for (int bi = grp; bi < NBLK; bi += 2) {
+        const int64_t blk_col0 = (int64_t)tn * BN + bi * 64;
+        if (p.tma_store) {
+          if (leader) tma_store_wait_read();            // previous store out of this staging buffer has been read
+          named_bar_sync(1 + grp, 128);
         }
-        const int64_t col0 = (int64_t)tn * BN + c * 32;
-        if (col0 >= p.N) continue;
-        const bool full_cols = col0 + 32 <= p.N;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int c = bi * 2 + half;
+          float v[32];
+          tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld_wait();
+          if (bi + 2 >= NBLK && half == 1) {   // this warp's last read of the accumulator: hand TMEM back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          const int64_t col0 = blk_col0 + half * 32;
+          const bool any_col = col0 < p.N;
+          const bool full_cols = col0 + 32 <= p.N;
+          if (any_col) {
+            if (e.flags & TXL_EPI_MASK_POS) {
+              if (row_ok && full_cols) {
+                const TC* arow = reinterpret_cast<const TC*>(e.aux) + row * p.ldc + col0;
+                if constexpr (sizeof(TC) == 2) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int64_t col = col0 + i;
-          float x = v[i];
-          if (e.bias && col < p.N) x += e.bias[col];
-          if (e.flags & TXL_EPI_RELU) x = fmaxf(x, 0.f);
-          if ((e.flags & TXL_EPI_MASK_POS) && row_ok && col < p.N)
-            x = to_f32(reinterpret_cast<const TC*>(e.aux)[row * p.ldc + col]) > 0.f ? x : 0.f;
-          if (e.flags & TXL_EPI_DROPOUT) x *= dropout_scale(e.seed, e.site, (uint64_t)(row * p.N + col), e.drop_p, p.inv_keep);
-          v[i] = (row_ok && col < p.N) ? x : 0.f;
-        }
-        if (e.colsum) {
-          float t[32];
+                  for (int g4 = 0; g4 < 4; ++g4) {
+                    uint4 u = reinterpret_cast<const uint4*>(arow)[g4];
+                    const bf16* ab = reinterpret_cast<const bf16*>(&u);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) t[i] = v[i];
-          float cs = warp_colsum32(t, lane);
-          if (col0 + lane < p.N) atomicAdd(&e.colsum[col0 + lane], cs);
-        }
-        if (!row_ok) continue;
-        TC* crow = C + row * p.ldc + col0;
-        if (p.ksplits > 1) {
+                    for (int k = 0; k < 8; ++k) v[g4 * 8 + k] = __bfloat162float(ab[k]) > 0.f ? v[g4 * 8 + k] : 0.f;
+                  }
+                } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) atomicAdd(reinterpret_cast<float*>(crow) + i, v[i]);
-        } else if (full_cols) {
-          if constexpr (sizeof(TC) == 2) {
-            uint4* dst = reinterpret_cast<uint4*>(crow);
+                  for (int i = 0; i < 32; ++i) v[i] = to_f32(arow[i]) > 0.f ? v[i] : 0.f;
+                }
+              } else if (row_ok) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float a[8];
-              if (e.flags & TXL_EPI_ACCUM) {
-                uint4 old = dst[g];
-                const bf16* ob = reinterpret_cast<const bf16*>(&old);
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) v[i] = to_f32(reinterpret_cast<const TC*>(e.aux)[row * p.ldc + col0 + i]) > 0.f ? v[i] : 0.f;
+              }
+            }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = v[g * 8 + i] + __bfloat162float(ob[i]);
+            for (int i = 0; i < 32; ++i) {
+              float x = v[i];
+              if (e.bias && col0 + i < p.N) x += e.bias[col0 + i];
+              if (e.flags & TXL_EPI_RELU) x = fmaxf(x, 0.f);
+              v[i] = x;
+            }
+            if (e.flags & TXL_EPI_DROPOUT) {
+              const uint64_t base_idx = (uint64_t)row * (uint64_t)p.N + (uint64_t)col0;
+              if (pair_hash) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  const uint32_t hsh = dropout_hash(dkey, (base_idx + i) >> 1);
+                  v[i] *= (hsh & 0xFFFFu) >= dthr ? p.inv_keep : 0.f;
+                  v[i + 1] *= (hsh >> 16) >= dthr ? p.inv_keep : 0.f;
+                }
               } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = v[g * 8 + i];
+                for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(e.seed, e.site, base_idx + i, e.drop_p, p.inv_keep);
               }
-              uint4 o;
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0], a[1]), p1 = __floats2bfloat162_rn(a[2], a[3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(a[4], a[5]), p3 = __floats2bfloat162_rn(a[6], a[7]);
-              o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-              o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-              dst[g] = o;
             }
-          } else {
-            float4* dst = reinterpret_cast<float4*>(crow);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-              if (e.flags & TXL_EPI_ACCUM) { float4 old = dst[g]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-              dst[g] = o;
+            for (int i = 0; i < 32; ++i) v[i] = (row_ok && col0 + i < p.N) ? v[i] : 0.f;
+            if (e.colsum) {
+              float t[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) t[i] = v[i];
+              float cs = warp_colsum32(t, lane);
+              if (col0 + lane < p.N) atomicAdd(&e.colsum[col0 + lane], cs);
             }
           }
-        } else {
+          if (p.tma_store) {
+            if constexpr (sizeof(TC) == 2) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (col0 + i < p.N) {
-              float x = v[i];
-              if (e.flags & TXL_EPI_ACCUM) x += to_f32(crow[i]);
-              crow[i] = from_f32<TC>(x);
+              for (int g4 = 0; g4 < 4; ++g4) {
+                uint4 o;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[g4 * 8], v[g4 * 8 + 1]), p1 = __floats2bfloat162_rn(v[g4 * 8 + 2], v[g4 * 8 + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[g4 * 8 + 4], v[g4 * 8 + 5]), p3 = __floats2bfloat162_rn(v[g4 * 8 + 6], v[g4 * 8 + 7]);
+                o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                *reinterpret_cast<uint4*>(cst + r_in_tile * 128 + (((half * 4 + g4) ^ (r_in_tile & 7)) << 4)) = o;
+              }
             }
+            continue;
+          }
+          if (!row_ok || !any_col) continue;
+          TC* crow = C + row * p.ldc + col0;
+          if (p.ksplits > 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) atomicAdd(reinterpret_cast<float*>(crow) + i, v[i]);
+          } else if (full_cols) {
+            if constexpr (sizeof(TC) == 2) {
+              uint4* dst = reinterpret_cast<uint4*>(crow);
+#pragma unroll
+              for (int g4 = 0; g4 < 4; ++g4) {
+                float a8[8];
+                if (e.flags & TXL_EPI_ACCUM) {
+                  uint4 old = dst[g4];
+                  const bf16* ob = reinterpret_cast<const bf16*>(&old);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) a8[i] = v[g4 * 8 + i] + __bfloat162float(ob[i]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) a8[i] = v[g4 * 8 + i];
+                }
+                uint4 o;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(a8[0], a8[1]), p1 = __floats2bfloat162_rn(a8[2], a8[3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(a8[4], a8[5]), p3 = __floats2bfloat162_rn(a8[6], a8[7]);
+                o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                dst[g4] = o;
+              }
+            } else {
+              float4* dst = reinterpret_cast<float4*>(crow);
+#pragma unroll
+              for (int g4 = 0; g4 < 8; ++g4) {
+                float4 o = make_float4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
+                if (e.flags & TXL_EPI_ACCUM) { float4 old = dst[g4]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                dst[g4] = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (col0 + i < p.N) {
+                float x = v[i];
+                if (e.flags & TXL_EPI_ACCUM) x += to_f32(crow[i]);
+                crow[i] = from_f32<TC>(x);
+              }
+            }
+          }
+        }
+        if (p.tma_store) {
+          fence_proxy_async_smem();
+          named_bar_sync(1 + grp, 128);
+          if (leader && blk_col0 < p.N) {               // TMA clips rows >= M and columns >= N
+            tma_store_2d(&tmC, cst, (int)blk_col0, tm * BM);
+            tma_store_commit();
           }
         }
       }
     }
+    if (p.tma_store && leader) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -274,14 +360,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, int STAGES, typename TC>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int grid, cudaStream_t st) {
   using C_ = Cfg<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
     TXL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
     attr_set = true;
   }
-  tc_gemm_kernel<BN, STAGES, TC><<<grid, THREADS, C_::SMEM, st>>>(tmA, tmB, p);
+  tc_gemm_kernel<BN, STAGES, TC><<<grid, THREADS, C_::SMEM, st>>>(tmA, tmB, tmC, p);
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }
@@ -322,8 +408,11 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
   p.kb_per_split = (int)cdiv64(p.nkb, p.ksplits);
   p.ksplits = (int)cdiv64(p.nkb, p.kb_per_split);   // no empty split
 
-  CUtensorMap tmA, tmB;
+  p.tma_store = (dtype_c == TXL_BF16 && !(epi->flags & TXL_EPI_ACCUM) && p.ksplits == 1) ? 1 : 0;
+  CUtensorMap tmA, tmB, tmC;
   int rc;
+  if (p.tma_store) { if ((rc = txl_make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, BM, 64))) return rc; }
+  else tmC = CUtensorMap{};
   if (!p.a_mn) rc = txl_make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
   else rc = txl_make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 64);
   if (rc) return rc;
@@ -335,9 +424,9 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
   const int grid = total < sms ? total : sms;
   cudaStream_t st = (cudaStream_t)stream;
   if (BN == 256) {
-    if (dtype_c == TXL_F32) rc = launch<256, 4, float>(tmA, tmB, p, grid, st); else rc = launch<256, 4, bf16>(tmA, tmB, p, grid, st);
+    if (dtype_c == TXL_F32) rc = launch<256, 4, float>(tmA, tmB, tmC, p, grid, st); else rc = launch<256, 4, bf16>(tmA, tmB, tmC, p, grid, st);
   } else {
-    if (dtype_c == TXL_F32) rc = launch<128, 6, float>(tmA, tmB, p, grid, st); else rc = launch<128, 6, bf16>(tmA, tmB, p, grid, st);
+    if (dtype_c == TXL_F32) rc = launch<128, 6, float>(tmA, tmB, tmC, p, grid, st); else rc = launch<128, 6, bf16>(tmA, tmB, tmC, p, grid, st);
   }
   if (rc) return rc;
   *handled = 1;
