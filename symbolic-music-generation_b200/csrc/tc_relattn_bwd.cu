@@ -5,8 +5,8 @@
 //   MODE_DKV: CTA = (b, h, J), loops I.   acc0 = dK  = sum_I dS^T.Qw     acc1 = dV  = sum_I P^T.dO      -> dk, dv
 //   MODE_DR : CTA = (h, diagonal J-2I), loops (I, b) — the R window is the same for all of them.
 //                                          acc0/acc1 = dRwin = sum dBD0^T.Qr                             -> dr (fp32 atomics, ~2 M per layer)
-// Every tile recomputes, on the tensor cores, S = Qw.K^T, BD0 = Qr.Rwin^T and dP = dO.V^T into TMEM; 256 "softmax" threads
-// (2 per query row, 32 keys each) apply HF's `_rel_shift` exactly as the forward kernel does (TMEM column offset + register
+// Every tile recomputes, on the tensor cores, S = Qw.K^T, BD0 = Qr.Rwin^T and dP = dO.V^T into TMEM; 512 "softmax" threads
+// (4 per query row, 16 keys each) apply HF's `_rel_shift` exactly as the forward kernel does (TMEM column offset + register
 // barrel shifter), rebuild P = exp2(score - lse) from the saved log-sum-exp, form dS = P (dP - delta) / sqrt(dh), and hand the
 // tensor cores bf16 tiles in shared memory: P and dS K-major (also read transposed, MN-major, for dV/dK), and dBD0 — dS
 // un-shifted back into window space by a per-row element offset on the shared-memory store (the inverse skew costs no ALU).
@@ -20,7 +20,9 @@
 namespace {
 constexpr int BQ = 128, BKV = 64, DH = 64, WIN = 192;
 constexpr int MODE_DQ = 0, MODE_DKV = 1, MODE_DR = 2;
-constexpr int N_SOFTMAX = 256, NTHREADS = 320;
+constexpr int KPT = 16;                       // keys per softmax thread: 4 threads share a query row
+constexpr int N_SOFTMAX = 128 * (BKV / KPT), NTHREADS = N_SOFTMAX + 64;
+constexpr int W_PROD = N_SOFTMAX / 32, W_MMA = W_PROD + 1;
 constexpr int TM_S = 0, TM_DP = 64, TM_BD = 128, TM_ACC0 = 320, TM_ACC1 = 384, TMEM_COLS = 512;
 constexpr int SZ_Q = 16384, SZ_KV = 8192, SZ_R = 24576, SZ_DBD = 49152;
 
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
     mbar_init(res_full, 1); mbar_init(f_full, 1); mbar_init(b_ready, N_SOFTMAX); mbar_init(b_done, 1); mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == W_MMA) tmem_alloc<TMEM_COLS>(tmem_slot);
   if (PL::DBD >= 0) {   // window-space tile: only positions [127-r+32hh, +32) of row r are ever written, the rest must read as 0
     for (int e = tid; e < SZ_DBD / 16; e += NTHREADS) reinterpret_cast<uint4*>(sm + PL::DBD)[e] = make_uint4(0, 0, 0, 0);
   }
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
     else { mk = &M.kc; mv = &M.vc; row = t.b * g.T + (j0 - g.mlen); }
   };
 
-  if (warp == 8) {
+  if (warp == W_PROD) {
     if (lane == 0) {
       // ======================= TMA producer
       {
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
         if (MODE != MODE_DR) tma_load_2d(st + PL::R, &M.r, &full[s], h * DH, g.T - BQ - t.I * BQ + t.J * BKV);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     if (lane == 0) {
       // ======================= MMA issuer
       const uint32_t id_s = umma_idesc_bf16(BQ, BKV, 0, 0), id_bd = umma_idesc_bf16(BQ, WIN, 0, 0);
@@ -217,16 +219,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
       const uint32_t id_nn = umma_idesc_bf16(BQ, DH, 1, 1);   // A MN-major (transposed tile), B MN-major
       const uint32_t base = smem_u32(sm);
       mbar_wait(res_full, 0);
-      for (int n = 0; n < it.count; ++n) {
-        const int s = n & 1; const uint32_t rph = (n >> 1) & 1, ph = n & 1;
-        const uint32_t st = base + PL::RING + s * PL::STAGE;
+      auto stage_base = [&](int n) -> uint32_t { return base + PL::RING + (n & 1) * PL::STAGE; };
+      auto front = [&](int n) {     // S, dP, BD0 of band tile n into TMEM
+        const uint32_t st = stage_base(n);
         const uint32_t qw = (MODE == MODE_DQ ? base : st) + PL::QW, qr = (MODE == MODE_DQ ? base : st) + PL::QR;
         const uint32_t dO = (MODE == MODE_DQ ? base : st) + PL::DO;
         const uint32_t kk_ = (MODE == MODE_DKV ? base : st) + PL::K, vv = (MODE == MODE_DKV ? base : st) + PL::V;
         const uint32_t rr = (MODE == MODE_DR ? base : st) + PL::R;
-        mbar_wait(&full[s], rph);
+        mbar_wait(&full[n & 1], (n >> 1) & 1);
         tc_fence_after();
-        // ---- front end: S, dP, BD0
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_S, umma_smem_desc(qw + k * 32, 16, 1024), umma_smem_desc(kk_ + k * 32, 16, 1024), id_s, k > 0);
 #pragma unroll
@@ -234,9 +235,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_BD, umma_smem_desc(qr + k * 32, 16, 1024), umma_smem_desc(rr + k * 32, 16, 1024), id_bd, k > 0);
         umma_commit(f_full);
-        // ---- back end, once the softmax threads have published the bf16 tiles of this band tile
+      };
+      front(0);
+      for (int n = 0; n < it.count; ++n) {
+        const int s = n & 1; const uint32_t ph = n & 1;
+        const uint32_t st = stage_base(n);
+        const uint32_t qw = (MODE == MODE_DQ ? base : st) + PL::QW, qr = (MODE == MODE_DQ ? base : st) + PL::QR;
+        const uint32_t dO = (MODE == MODE_DQ ? base : st) + PL::DO;
+        const uint32_t kk_ = (MODE == MODE_DKV ? base : st) + PL::K;
+        const uint32_t rr = (MODE == MODE_DR ? base : st) + PL::R;
+        // softmax threads have drained S/dP/BD0 of tile n and published its bf16 tiles
         mbar_wait(b_ready, ph);
         tc_fence_after();
+        // front end of the NEXT tile goes first: its softmax phase then overlaps this tile's back-end MMAs
+        if (n + 1 < it.count) front(n + 1);
         const uint32_t accum0 = n > 0;
         if (MODE == MODE_DQ) {
           const uint32_t ds = base + PL::DS, dbd = base + PL::DBD;
@@ -269,11 +281,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
       umma_commit(acc_full);
     }
   } else {
-    // ======================= softmax threads: row r = 32*(warp%4)+lane, keys [32*hh, 32*hh+32) of the tile, hh = warp/4
-    const int r = 32 * (warp & 3) + lane, hh = warp >> 2;
+    // ======================= softmax threads: row r = 32*(warp%4)+lane, keys [KPT*qd, KPT*qd+KPT) of the tile, qd = warp/4
+    const int r = 32 * (warp & 3) + lane, qd = warp >> 2;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const int sh = 31 - lane;
-    const int c0 = 127 - r + 32 * hh;     // first window column this thread writes in the dBD0 tile
+    const int c0 = 127 - r + KPT * qd;     // first window column this thread writes in the dBD0 tile
     Tile t = it.get(0, a);
     float lse2 = 0.f, dlt = 0.f;
     auto load_row = [&](const Tile& tt, float& l2, float& dl) {
@@ -287,8 +299,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
     load_row(t, lse2, dlt);
     for (int n = 0; n < it.count; ++n) {
       const uint32_t ph = n & 1;
-      Tile tn = t; float lse2n = 0.f, dltn = 0.f;
-      if (n + 1 < it.count) { tn = it.get(n + 1, a); if (MODE != MODE_DQ) load_row(tn, lse2n, dltn); else { lse2n = lse2; dltn = dlt; } }
+      Tile tn = t; float lse2n = lse2, dltn = dlt;
+      if (n + 1 < it.count) { tn = it.get(n + 1, a); if (MODE != MODE_DQ) load_row(tn, lse2n, dltn); }
       const int i0 = t.I * BQ, j0 = t.J * BKV, i = i0 + r;
       int lo_i = 1, hi_i = 0;
       if (i < g.T) { lo_i = band_lo(g, i); hi_i = min(band_hi(g, i), g.klen - 1); }
@@ -297,29 +309,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
 
       mbar_wait(f_full, ph);
       tc_fence_after();
-      float p[32], ds[32];
-      tmem_ld_32x32(tmem_base + lane_base + TM_S + 32 * hh, p);
+      float p[KPT], ds[KPT], w[48];
+      const uint32_t cb = TM_BD + 32 * (3 - (warp & 3)) + KPT * qd;
+      tmem_ld_32x16(tmem_base + lane_base + TM_S + KPT * qd, p);
+      tmem_ld_32x16(tmem_base + lane_base + TM_DP + KPT * qd, ds);
+      tmem_ld_32x16(tmem_base + lane_base + cb, w);
+      tmem_ld_32x16(tmem_base + lane_base + cb + 16, w + 16);
+      tmem_ld_32x16(tmem_base + lane_base + cb + 32, w + 32);
       tmem_ld_wait();
+      barrel_shift<16>(w, sh);
 #pragma unroll
-      for (int qq = 0; qq < 2; ++qq) {
-        const int qd = 2 * hh + qq;
-        float w[48];
-        const uint32_t cb = TM_BD + 32 * (3 - (warp & 3)) + 16 * qd;
-        tmem_ld_32x16(tmem_base + lane_base + cb, w);
-        tmem_ld_32x16(tmem_base + lane_base + cb + 16, w + 16);
-        tmem_ld_32x16(tmem_base + lane_base + cb + 32, w + 32);
-        tmem_ld_wait();
-        barrel_shift<16>(w, sh);
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) p[16 * qq + jj] += w[jj];
-      }
-      tmem_ld_32x32(tmem_base + lane_base + TM_DP + 32 * hh, ds);
-      tmem_ld_wait();
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int j = j0 + 32 * hh + jj;
+      for (int jj = 0; jj < KPT; ++jj) {
+        const int j = j0 + KPT * qd + jj;
         const bool valid = tile_full || (j >= lo_i && j <= hi_i);
-        const float pj = valid ? exp2f(fmaf(p[jj], a.scale_log2, -lse2)) : 0.f;
+        const float pj = valid ? exp2f(fmaf(p[jj] + w[jj], a.scale_log2, -lse2)) : 0.f;
         p[jj] = pj;
         ds[jj] = pj * (ds[jj] - dlt) * a.scale;
       }
@@ -327,30 +330,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
       if (n > 0) mbar_wait(b_done, (n - 1) & 1);
       if (PL::P >= 0) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < KPT / 8; ++c) {
           uint4 o; o.x = pack2(p[c * 8], p[c * 8 + 1]); o.y = pack2(p[c * 8 + 2], p[c * 8 + 3]); o.z = pack2(p[c * 8 + 4], p[c * 8 + 5]); o.w = pack2(p[c * 8 + 6], p[c * 8 + 7]);
-          *reinterpret_cast<uint4*>(sm + PL::P + r * 128 + (((4 * hh + c) ^ (r & 7)) << 4)) = o;
+          *reinterpret_cast<uint4*>(sm + PL::P + r * 128 + ((((KPT / 8) * qd + c) ^ (r & 7)) << 4)) = o;
         }
       }
       if (PL::DS >= 0) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < KPT / 8; ++c) {
           uint4 o; o.x = pack2(ds[c * 8], ds[c * 8 + 1]); o.y = pack2(ds[c * 8 + 2], ds[c * 8 + 3]); o.z = pack2(ds[c * 8 + 4], ds[c * 8 + 5]); o.w = pack2(ds[c * 8 + 6], ds[c * 8 + 7]);
-          *reinterpret_cast<uint4*>(sm + PL::DS + r * 128 + (((4 * hh + c) ^ (r & 7)) << 4)) = o;
+          *reinterpret_cast<uint4*>(sm + PL::DS + r * 128 + ((((KPT / 8) * qd + c) ^ (r & 7)) << 4)) = o;
         }
       }
       if (PL::DBD >= 0) {
-        // inverse _rel_shift: dBD0[r, c0 + jj] = dS[r, 32 hh + jj]  (bf16 pairs; element address = block, row, swizzled 16-byte chunk)
+        // inverse _rel_shift: dBD0[r, c0 + jj] = dS[r, KPT qd + jj]  (bf16 pairs; element address = block, row, swizzled 16-byte chunk)
         uint8_t* dbd = sm + PL::DBD;
         auto addr = [&](int c) -> uint8_t* { return dbd + (c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
         if ((c0 & 1) == 0) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) *reinterpret_cast<uint32_t*>(addr(c0 + 2 * k)) = pack2(ds[2 * k], ds[2 * k + 1]);
+          for (int k = 0; k < KPT / 2; ++k) *reinterpret_cast<uint32_t*>(addr(c0 + 2 * k)) = pack2(ds[2 * k], ds[2 * k + 1]);
         } else {
           *reinterpret_cast<bf16*>(addr(c0)) = __float2bfloat16_rn(ds[0]);
 #pragma unroll
-          for (int k = 0; k < 15; ++k) *reinterpret_cast<uint32_t*>(addr(c0 + 1 + 2 * k)) = pack2(ds[2 * k + 1], ds[2 * k + 2]);
-          *reinterpret_cast<bf16*>(addr(c0 + 31)) = __float2bfloat16_rn(ds[31]);
+          for (int k = 0; k < KPT / 2 - 1; ++k) *reinterpret_cast<uint32_t*>(addr(c0 + 1 + 2 * k)) = pack2(ds[2 * k + 1], ds[2 * k + 2]);
+          *reinterpret_cast<bf16*>(addr(c0 + KPT - 1)) = __float2bfloat16_rn(ds[KPT - 1]);
         }
       }
       fence_proxy_async_smem();
@@ -358,20 +361,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
       mbar_arrive(b_ready);
       t = tn; lse2 = lse2n; dlt = dltn;
     }
-    // ======================= drain the accumulators
+    // ======================= drain the accumulators (each thread: its row, KPT of the 64 columns)
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    float v0[32], v1[32];
-    tmem_ld_32x32(tmem_base + lane_base + TM_ACC0 + 32 * hh, v0);
-    tmem_ld_32x32(tmem_base + lane_base + TM_ACC1 + 32 * hh, v1);
+    float v0[KPT], v1[KPT];
+    tmem_ld_32x16(tmem_base + lane_base + TM_ACC0 + KPT * qd, v0);
+    tmem_ld_32x16(tmem_base + lane_base + TM_ACC1 + KPT * qd, v1);
     tmem_ld_wait();
     const Tile tl = it.get(0, a);
     if (MODE == MODE_DQ) {
       const int i = tl.I * BQ + r;
       if (i < g.T) {
-        uint4* dst = reinterpret_cast<uint4*>(a.dq + ((int64_t)tl.b * g.T + i) * a.ldq + h * DH + 32 * hh);
+        uint4* dst = reinterpret_cast<uint4*>(a.dq + ((int64_t)tl.b * g.T + i) * a.ldq + h * DH + KPT * qd);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < KPT / 8; ++c) {
           uint4 o;
           o.x = pack2(v0[c * 8] + v1[c * 8], v0[c * 8 + 1] + v1[c * 8 + 1]); o.y = pack2(v0[c * 8 + 2] + v1[c * 8 + 2], v0[c * 8 + 3] + v1[c * 8 + 3]);
           o.z = pack2(v0[c * 8 + 4] + v1[c * 8 + 4], v0[c * 8 + 5] + v1[c * 8 + 5]); o.w = pack2(v0[c * 8 + 6] + v1[c * 8 + 6], v0[c * 8 + 7] + v1[c * 8 + 7]);
@@ -379,39 +382,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) { v0[c] = 0.f; v1[c] = 0.f; }
+        for (int c = 0; c < KPT; ++c) { v0[c] = 0.f; v1[c] = 0.f; }
       }
-      // bias gradients: column sums over this warp's 32 rows, one atomic per column per warp
-      float s0 = 0.f, s1 = 0.f;
-      {
-        float tmp[32];
+      // bias gradients: sums over this warp's 32 rows, one atomic per column per warp
 #pragma unroll
-        for (int c = 0; c < 32; ++c) tmp[c] = v0[c];
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-          for (int c = 0; c < off; ++c) { bool up = lane & off; float send = up ? tmp[c] : tmp[c + off]; float keep = up ? tmp[c + off] : tmp[c]; tmp[c] = keep + __shfl_xor_sync(0xffffffffu, send, off); }
-        s0 = tmp[0];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) tmp[c] = v1[c];
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-          for (int c = 0; c < off; ++c) { bool up = lane & off; float send = up ? tmp[c] : tmp[c + off]; float keep = up ? tmp[c + off] : tmp[c]; tmp[c] = keep + __shfl_xor_sync(0xffffffffu, send, off); }
-        s1 = tmp[0];
+      for (int c = 0; c < KPT; ++c) {
+        const float s0 = warp_sum(v0[c]), s1 = warp_sum(v1[c]);
+        if (lane == c) { atomicAdd(&a.drwb[h * DH + KPT * qd + c], s0); atomicAdd(&a.drrb[h * DH + KPT * qd + c], s1); }
       }
-      atomicAdd(&a.drwb[h * DH + 32 * hh + lane], s0);
-      atomicAdd(&a.drrb[h * DH + 32 * hh + lane], s1);
     } else if (MODE == MODE_DKV) {
       if (r < BKV) {
         const int j = tl.J * BKV + r;
         bf16 *dk, *dv;
         if (j < g.mlen) { dk = a.dk_mem + ((int64_t)tl.b * g.mlen + j) * a.ldkv_mem; dv = a.dv_mem + ((int64_t)tl.b * g.mlen + j) * a.ldkv_mem; }
         else { dk = a.dk_cur + ((int64_t)tl.b * g.T + (j - g.mlen)) * a.ldkv_cur; dv = a.dv_cur + ((int64_t)tl.b * g.T + (j - g.mlen)) * a.ldkv_cur; }
-        uint4* pk = reinterpret_cast<uint4*>(dk + h * DH + 32 * hh);
-        uint4* pv = reinterpret_cast<uint4*>(dv + h * DH + 32 * hh);
+        uint4* pk = reinterpret_cast<uint4*>(dk + h * DH + KPT * qd);
+        uint4* pv = reinterpret_cast<uint4*>(dv + h * DH + KPT * qd);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < KPT / 8; ++c) {
           uint4 o; o.x = pack2(v0[c * 8], v0[c * 8 + 1]); o.y = pack2(v0[c * 8 + 2], v0[c * 8 + 3]); o.z = pack2(v0[c * 8 + 4], v0[c * 8 + 5]); o.w = pack2(v0[c * 8 + 6], v0[c * 8 + 7]);
           pk[c] = o;
           uint4 u; u.x = pack2(v1[c * 8], v1[c * 8 + 1]); u.y = pack2(v1[c * 8 + 2], v1[c * 8 + 3]); u.z = pack2(v1[c * 8 + 4], v1[c * 8 + 5]); u.w = pack2(v1[c * 8 + 6], v1[c * 8 + 7]);
@@ -422,21 +410,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
       const int x0 = g.T - BQ + BKV * it.delta;
       const int xa = x0 + r;                 // acc0: window row r
       if (xa >= 0 && xa < g.klen) {
-        float* d = a.dr + (int64_t)xa * HD + h * DH + 32 * hh;
+        float* d = a.dr + (int64_t)xa * HD + h * DH + KPT * qd;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) atomicAdd(d + c, v0[c]);
+        for (int c = 0; c < KPT; ++c) atomicAdd(d + c, v0[c]);
       }
       const int xb = x0 + 64 + r;            // acc1: lanes 64..127 hold window rows 128..191
       if (r >= 64 && xb >= 0 && xb < g.klen) {
-        float* d = a.dr + (int64_t)xb * HD + h * DH + 32 * hh;
+        float* d = a.dr + (int64_t)xb * HD + h * DH + KPT * qd;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) atomicAdd(d + c, v1[c]);
+        for (int c = 0; c < KPT; ++c) atomicAdd(d + c, v1[c]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == W_MMA) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // qw = q + r_w_bias, qr = q + r_r_bias (bf16, [B*T, HD]); delta[b,h,i] = sum_c dO.O

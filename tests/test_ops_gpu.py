@@ -83,10 +83,10 @@ def test_add_ln_fwd_bwd(ops, mode):
     tol = dict(rtol=1e-4, atol=1e-4) if mode == 'fp32' else dict(rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(y.float(), yr, **tol)
     dy = torch.randn(rows, d, device='cuda').to(dt)
-    yr.backward(dy.float())
-    dg, db = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
     half = (dy.float() * 0.25).to(dt)
     rest = (dy.float() - half.float()).to(dt)
+    yr.backward(rest.float() + half.float())
+    dg, db = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
     dx, dr = ops.add_ln_bwd(rest, z, gamma.detach(), mean, rstd, dg, db, dy2=half)      # two branches summed on read
     torch.testing.assert_close(dx.float(), zr.grad, **tol)
     torch.testing.assert_close(dr.float(), zr.grad, **tol)
