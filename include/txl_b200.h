@@ -167,6 +167,26 @@ int txl_sumsq(const float* g, int64_t n, float* out, void* stream);
 int txl_sample(const float* scores, int B, int V, int do_sample, float temperature, int top_k, float top_p,
                const float* u, int64_t* next, uint8_t* keep, float* warped, void* stream);
 
+/* ---- decode step (batched generation; [A.3-A.5] at T=1, [A.7], [A.8'])  -----------------------------------
+ * generate() keeps a private ring cache of PROJECTED keys/values kc, vc [B, H, mem_len, d_head] (HF re-projects all cached hidden
+ * states every step); API-level `mems` stay hidden states.  `pos` is a device int32 = tokens appended so far (slot = pos % mem_len).
+ * txl_decode_cache_init: kv_mem [B*mem_len, 2*H*dh] (k|v, from txl_gemm of the hidden-state mems) -> kc, vc.
+ * txl_decode_attn: qkv [B, 3*H*dh]; appends k,v at the ring slot (overwriting the oldest entry: for T=1, mlen==mem_len the live band IS
+ *   the ring after the write), then out[b,:] = softmax_s(((q+rwb).k_s + (q+rrb).r[mem_len - dist_s]) / sqrt(dh)) . v_s,
+ *   dist_s = (slot - s) mod mem_len;  r [mem_len+1, H*dh] = r_head_k for klen = mem_len+1.
+ * txl_skinny_gemm: C[M<=64, N] = A[M,K] W[N,K]^T (+bias)(ReLU), weight-streaming GEMM for the per-step Linears.
+ * txl_decode_uniform: u[b] = U(0,1) keyed on (seed, seq_offset + b, *pos) — reproducible under any sharding of sequences over GPUs.
+ * txl_decode_commit: HF sample()/greedy_search() bookkeeping on the device: finished rows emit pad, eos finishes a row, token stored at
+ *   out_ids[b, col0 + *pos] and fed back in tok[b]; then *pos += 1. */
+int txl_decode_cache_init(const void* kv_mem, int64_t ld, void* kc, void* vc, int B, int H, int mem_len, int dh, int dtype, void* stream);
+int txl_decode_attn(const void* qkv, void* kc, void* vc, const void* r, const float* rwb, const float* rrb, void* out, const int32_t* pos,
+                    int B, int H, int mem_len, int dh, int dtype, void* stream);
+int txl_skinny_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K,
+                    int relu, int dtype, void* stream);
+int txl_decode_uniform(float* u, int B, uint64_t seed, int64_t seq_offset, const int32_t* pos, void* stream);
+int txl_decode_commit(const int64_t* next, int64_t* tok, int64_t* unfinished, int64_t* out_ids, int64_t ld_out, int col0, int32_t* pos, int B,
+                      int64_t eos, int64_t pad, int use_eos, void* stream);
+
 /* ---- mems ring / layout helpers  [A.8' _update_mems] ----------------------------------------------
  * time-major (L?,rows,B,d) <-> batch-major copies used at the Python boundary */
 int txl_tm_to_bm(const void* src, void* dst, int rows, int B, int d, int dtype_src, int dtype_dst, void* stream);

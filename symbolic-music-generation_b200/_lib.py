@@ -64,6 +64,11 @@ SIGNATURES = {
     'txl_adamw_step': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
     'txl_sumsq': (_i, [_vp, _i64, _vp, _vp]),
     'txl_sample': (_i, [_vp, _i, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    'txl_decode_cache_init': (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'txl_decode_attn': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'txl_skinny_gemm': (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    'txl_decode_uniform': (_i, [_vp, _i, _u64, _i64, _vp, _vp]),
+    'txl_decode_commit': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _i, _i64, _i64, _i, _vp]),
     'txl_tm_to_bm': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'txl_bm_to_tm': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }

@@ -145,7 +145,8 @@ extern "C" int txl_sample(const float* scores, int B, int V, int do_sample, floa
   while (NP < V) NP <<= 1;
   TXL_CHECK_ARG(NP <= 16384, "sample: vocab %d too large for the shared-memory sampler", V);
   size_t smem = (size_t)NP * 12;
-  if (smem > 48 * 1024) TXL_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) { TXL_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
   sample_kernel<<<B, NT, smem, (cudaStream_t)stream>>>(scores, V, NP, do_sample, temperature, top_k, top_p, u, next, keep, warped);
   TXL_LAUNCH_CHECK();
   return TXL_OK;

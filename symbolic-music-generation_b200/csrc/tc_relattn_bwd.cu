@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + PL::BAR);
-  uint64_t *full = bars, *empty = bars + 2, *res_full = bars + 4, *f_full = bars + 5, *b_ready = bars + 6, *b_done = bars + 7, *acc_full = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t *full = bars, *empty = bars + 2, *res_full = bars + 4, *f_full = bars + 5, *b_ready = bars + 6, *b_done = bars + 7, *acc_full = bars + 8, *t_free = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const BandGeom g = make_band(a.band);
   const int HD = a.H * DH;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
 
   if (tid == 0) {
     mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
-    mbar_init(res_full, 1); mbar_init(f_full, 1); mbar_init(b_ready, N_SOFTMAX); mbar_init(b_done, 1); mbar_init(acc_full, 1);
+    mbar_init(res_full, 1); mbar_init(f_full, 1); mbar_init(b_ready, N_SOFTMAX); mbar_init(b_done, 1); mbar_init(acc_full, 1); mbar_init(t_free, N_SOFTMAX);
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -244,11 +244,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
         const uint32_t dO = (MODE == MODE_DQ ? base : st) + PL::DO;
         const uint32_t kk_ = (MODE == MODE_DKV ? base : st) + PL::K;
         const uint32_t rr = (MODE == MODE_DR ? base : st) + PL::R;
-        // softmax threads have drained S/dP/BD0 of tile n and published its bf16 tiles
+        // as soon as the softmax threads have pulled S/dP/BD0 of tile n into registers (long before they finish the arithmetic),
+        // the tensor core starts the front end of tile n+1: it then overlaps tile n's softmax phase
+        if (n + 1 < it.count) {
+          mbar_wait(t_free, ph);
+          tc_fence_after();
+          front(n + 1);
+        }
+        // softmax threads have published the bf16 tiles of tile n
         mbar_wait(b_ready, ph);
         tc_fence_after();
-        // front end of the NEXT tile goes first: its softmax phase then overlaps this tile's back-end MMAs
-        if (n + 1 < it.count) front(n + 1);
         const uint32_t accum0 = n > 0;
         if (MODE == MODE_DQ) {
           const uint32_t ds = base + PL::DS, dbd = base + PL::DBD;
@@ -317,6 +322,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
       tmem_ld_32x16(tmem_base + lane_base + cb + 16, w + 16);
       tmem_ld_32x16(tmem_base + lane_base + cb + 32, w + 32);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(t_free);                   // S / dP / BD0 of this tile now live in registers: TMEM may be overwritten
       barrel_shift<16>(w, sh);
 #pragma unroll
       for (int jj = 0; jj < KPT; ++jj) {

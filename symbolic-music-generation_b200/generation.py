@@ -11,7 +11,7 @@ from typing import Optional
 
 import torch
 
-from . import ops
+from . import decode, ops
 
 
 def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_tokens: Optional[int] = None, do_sample: Optional[bool] = None,
@@ -19,7 +19,7 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
              typical_p: Optional[float] = None, repetition_penalty: Optional[float] = None, renormalize_logits: Optional[bool] = None,
              num_beams: Optional[int] = None, num_beam_groups: Optional[int] = None, diversity_penalty=None, penalty_alpha=None,
              num_return_sequences: Optional[int] = None, eos_token_id='config', pad_token_id='config', generator=None,
-             return_step_scores: bool = False, use_decode_cache: bool = True, **unused):
+             return_step_scores: bool = False, use_decode_cache: bool = True, seed: int = 0, seq_offset: int = 0, use_cuda_graph: bool = True, **unused):
     cfg = model.config
     if input_ids is None:
         raise ValueError('generate needs input_ids (the reference always passes a tokenised prompt, eval.py:276)')
@@ -54,19 +54,35 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
     out_ids[:, :cur] = ids
     step_scores = []
     past = None
-    decoder = None
+    fast = (use_decode_cache and not return_step_scores and generator is None and decode.supported(model, B)
+            and max_length - cur >= 2)
     try:
         with torch.no_grad():
             while cur < max_length:
-                if decoder is not None:
-                    scores = decoder.step(out_ids[:, cur - 1])
-                else:
-                    inputs = model.prepare_inputs_for_generation(out_ids[:, :cur], past=past)
-                    out = model(**inputs, return_dict=True)
-                    scores = out.logits[:, -1, :].contiguous()
-                    past = out.mems
-                    if use_decode_cache and hasattr(model, '_make_decoder'):
-                        decoder = model._make_decoder(past)
+                inputs = model.prepare_inputs_for_generation(out_ids[:, :cur], past=past)
+                out = model(**inputs, return_dict=True)
+                scores = out.logits[:, -1, :].contiguous()
+                past = out.mems
+                if fast and (seed or not do_sample):
+                    u = None
+                    if do_sample:      # first draw uses the same keyed stream as the device loop (step index -1 -> pos 0 is the next one)
+                        u = torch.empty(B, dtype=torch.float32, device=dev)
+                        from ._lib import check as _chk, load as _ld, ptr as _ptr, stream_ptr as _sp
+                        neg = torch.full((1,), -1, dtype=torch.int32, device=dev)
+                        _chk(_ld().txl_decode_uniform(_ptr(u), B, int(seed), int(seq_offset), _ptr(neg), _sp()), 'decode_uniform')
+                    nxt, _, _ = ops.sample(scores, do_sample, temperature, top_k, top_p, u)
+                    if eos_token_id is not None:
+                        nxt = nxt * unfinished + pad_token_id * (1 - unfinished)
+                        unfinished = unfinished * (nxt != eos_token_id).long()
+                    out_ids[:, cur] = nxt
+                    cur += 1
+                    if cur < max_length:
+                        dec = decode.Decoder(model, past, out_ids, cur, do_sample=do_sample, temperature=temperature, top_k=top_k, top_p=top_p,
+                                             eos_token_id=eos_token_id, pad_token_id=pad_token_id, seed=seed, seq_offset=seq_offset,
+                                             use_graph=use_cuda_graph)
+                        dec.unfinished.copy_(unfinished)
+                        cur += dec.run(nxt, max_length - cur)
+                    break
                 u = torch.rand(B, device=dev, generator=generator) if do_sample else None
                 nxt, _, warped = ops.sample(scores, do_sample, temperature, top_k, top_p, u, want_warped=return_step_scores and do_sample)
                 if return_step_scores:

@@ -170,3 +170,36 @@ def test_generate_sampling_and_eos(pkg):
         z = (row == 0).nonzero()
         if len(z):
             assert (row[z[0, 0]:] == 0).all()
+
+
+def test_decode_cache_path_matches_generic_path_fp32(pkg):
+    """generate() through the projected-K/V ring cache + CUDA graph == generate() through forward(input_ids[:, -1:], mems) each step."""
+    _, model = make_pair(pkg, 'fp32', mem_len=48, n_layer=2)
+    ids, _ = _batch(422, 3, 6, pad=False)
+    slow = model.generate(input_ids=ids.cuda(), max_length=6 + 120, do_sample=False, eos_token_id=None, use_decode_cache=False)
+    fast = model.generate(input_ids=ids.cuda(), max_length=6 + 120, do_sample=False, eos_token_id=None)
+    nograph = model.generate(input_ids=ids.cuda(), max_length=6 + 120, do_sample=False, eos_token_id=None, use_cuda_graph=False)
+    assert torch.equal(slow, fast) and torch.equal(slow, nograph)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_decode_sampling_reproducible_and_shardable(pkg, mode):
+    """Keyed draws: same seed -> same tokens; sharding the sequences over calls (as over GPUs) with seq_offset gives the same tokens;
+    eos rows keep emitting pad; prompt is preserved."""
+    _, model = make_pair(pkg, mode, mem_len=32, n_layer=1)
+    ids, _ = _batch(422, 4, 5, pad=False)
+    kw = dict(max_length=70, do_sample=True, top_k=8, top_p=0.9, temperature=1.1, renormalize_logits=True, seed=1234)
+    a = model.generate(input_ids=ids.cuda(), **kw)
+    b = model.generate(input_ids=ids.cuda(), **kw)
+    assert a.shape[0] == 4 and torch.equal(a[:, :5].cpu(), ids) and torch.equal(a, b)
+    lo = model.generate(input_ids=ids[:2].cuda(), seq_offset=0, eos_token_id=None, **kw)
+    hi = model.generate(input_ids=ids[2:].cuda(), seq_offset=2, eos_token_id=None, **kw)
+    full = model.generate(input_ids=ids.cuda(), eos_token_id=None, **kw)
+    assert torch.equal(full, torch.cat([lo, hi], 0))
+    c = model.generate(input_ids=ids.cuda(), **dict(kw, seed=99))
+    assert not torch.equal(a, c) or a.shape != c.shape
+    gen = a[:, 5:].cpu()
+    for row in gen:
+        z = (row == 0).nonzero()
+        if len(z):
+            assert (row[z[0, 0]:] == 0).all()
