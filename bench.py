@@ -267,6 +267,8 @@ def run_ours(args):
         'roofline_step': {'bound': 'tensor', 'achieved': step_tf, 'peak': peaks['tf'], 'unit': 'TFLOP/s', 'frac': step_tf / peaks['tf'],
                           'note': f'whole step, algorithmic FLOP/token {fpt:.4e} (SURVEY §8d) / per-GPU tokens/s; peak = sustained bf16, {peaks["src"]}'},
     }
+    if not args.no_decode:
+        line['decode'] = decode_probe(torch, pkg, pdist, cfg, args, dev, rank, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_tokens_per_s(1, 1, budget_s=25.0)
         line['cpu_baseline'] = {'value': r['value'], 'unit': 'tokens/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
@@ -274,6 +276,48 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def decode_probe(torch, pkg, pdist, cfg_train, args, dev, rank, world):
+    """cfg4: batched autoregressive generation, `--decode-seqs` sequences in total sharded over the ranks (no collective), prompt 16
+    tokens, `--decode-new` new tokens, top-k 8 sampling, mems cache of 1024, eos disabled for timing.  Timed through generate()
+    (public API; CUDA events around the call, max over ranks); the prompt forward and cache build are inside the timed region."""
+    import torch.distributed as dist
+    lo, hi = pdist.shard_sequences(args.decode_seqs, rank, world)
+    Bl = hi - lo
+    cfg = pkg.MyTransfoXLConfig(compute_dtype=args.dtype, dropout=0.0, **dict(CFG2, mem_len=args.mem_len))
+    torch.manual_seed(77)
+    model = pkg.MyTransfoXLLMHeadModel(cfg).to(dev).eval()
+    g = torch.Generator().manual_seed(77)
+    prompt = torch.randint(1, cfg.vocab_size, (args.decode_seqs, 16), generator=g)[lo:hi].to(dev)
+    kw = dict(do_sample=True, top_k=8, temperature=1.0, renormalize_logits=True, eos_token_id=None, seed=77, seq_offset=lo)
+    model.generate(input_ids=prompt, max_length=16 + 8, **kw)          # warm-up (kernel attributes, allocator)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = model.generate(input_ids=prompt, max_length=16 + args.decode_new, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    assert out.shape == (Bl, 16 + args.decode_new)
+    peaks = measured_peaks()
+    L, M, d = cfg.n_layer, cfg.mem_len, cfg.d_model
+    n_params = sum(p.numel() for p in model.parameters())
+    step_bytes = Bl * L * M * d * 2 + n_params * 2 + L * M * d * 2        # SURVEY §8d: hidden-state mems + weights + R tables, bf16
+    ms_step = ms / args.decode_new
+    ach = step_bytes / (ms_step / 1e3) / 1e9
+    return {'metric': 'TXL decode tokens/s', 'value': args.decode_seqs * args.decode_new / (ms / 1e3), 'unit': 'tokens/s', 'ms_per_token_step': ms_step,
+            'config': {'workload': f'cfg4: {args.decode_seqs} sequences ({Bl} per GPU), prompt 16, {args.decode_new} new tokens, top_k 8, mem_len {M}, '
+                                   'projected-K/V ring cache, CUDA-graph step'},
+            'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': ach / peaks['hbm'], 'traffic': None,
+                         'algorithmic_bytes_per_step': step_bytes,
+                         'note': 'denominator bytes = hidden-state mems once + weights + R tables (SURVEY §8d); the K/V cache actually read is 2x the mems term'}}
 
 
 def dominant_kernel_probe(torch, ops, model, cfg, B, T, M, dev):
@@ -324,6 +368,9 @@ def main():
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--dropout', type=float, default=0.1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-decode', action='store_true')
+    ap.add_argument('--decode-seqs', type=int, default=64)
+    ap.add_argument('--decode-new', type=int, default=512)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

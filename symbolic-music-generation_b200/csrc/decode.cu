@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_attn_kernel(const T* __res
   float qwv[8], qrv[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { qwv[k] = qw[ch * 8 + k]; qrv[k] = qr[ch * 8 + k]; }
+#pragma unroll 4
   for (int s0 = warp * KPW; s0 < ML; s0 += (DEC_THREADS / 32) * KPW) {
     const int s = s0 + sub;
     float a = 0.f;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_attn_kernel(const T* __res
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 4
   for (int s0 = warp * KPW; s0 < ML; s0 += (DEC_THREADS / 32) * KPW) {
     const int s = s0 + sub;
     if (s < ML) {
@@ -131,43 +133,37 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_attn_kernel(const T* __res
   }
 }
 
-// C[M<=64, N] = A[M,K] . W[N,K]^T (+bias)(ReLU): one warp per output column, lanes split K in 16-byte pieces, the weight matrix is
-// streamed exactly once; the 64 per-row partial sums of a lane are reduced across the warp by a butterfly transpose (62 shuffles).
-constexpr int SK_MAXM = 64, SK_KC = 256, SK_WARPS = 8;
+// C[M<=64, N] = A[M,K] . W[N,K]^T (+bias)(ReLU) for the per-step Linears (M = sequences on this GPU).  Weight-streaming: the block's
+// 8 warps cover CPB output columns x KSPLIT slices of K, every weight element is read once with 16-byte loads, the activations come
+// straight from L1/L2 (all warps of a block, and all blocks, read the same 64 rows); the 64 per-row partial sums of a lane are
+// reduced across the warp by a butterfly transpose (62 shuffles) and across K slices through shared memory.
+constexpr int SK_MAXM = 64, SK_WARPS = 8;
 template <typename T>
 __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ W, int64_t ldw,
                                                                     const float* __restrict__ bias, T* __restrict__ C, int64_t ldc, int M, int N, int K,
-                                                                    int relu) {
-  extern __shared__ __align__(16) unsigned char sk_smem[];
-  T (*As)[SK_KC] = reinterpret_cast<T (*)[SK_KC]>(sk_smem);
+                                                                    int relu, int ksplit) {
+  __shared__ float part[SK_WARPS][SK_MAXM];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = blockIdx.x * SK_WARPS + warp;
+  const int cpb = SK_WARPS / ksplit;
+  const int col_in_blk = warp / ksplit, ks = warp % ksplit;
+  const int n = blockIdx.x * cpb + col_in_blk;
+  const int kper = ((K + ksplit - 1) / ksplit + 7) / 8 * 8;
+  const int kbeg = ks * kper, kend = min(K, kbeg + kper);
   float acc[SK_MAXM];
 #pragma unroll
   for (int m = 0; m < SK_MAXM; ++m) acc[m] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += SK_KC) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < SK_MAXM * (SK_KC / 8); e += SK_WARPS * 32) {
-      const int m = e / (SK_KC / 8), c8 = (e % (SK_KC / 8)) * 8;
-      float f[8];
-      if (m < M && k0 + c8 < K) load8(A + (int64_t)m * lda + k0 + c8, f);
-      else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) As[m][c8 + k] = from_f32<T>(f[k]);
-    }
-    __syncthreads();
-    if (n < N && k0 + lane * 8 < K) {
+  if (n < N) {
+    for (int k0 = kbeg + lane * 8; k0 < kend; k0 += 256) {
       float w[8];
-      load8(W + (int64_t)n * ldw + k0 + lane * 8, w);
+      load8(W + (int64_t)n * ldw + k0, w);
 #pragma unroll
       for (int m = 0; m < SK_MAXM; ++m) {
-        float a[8];
-        load8(&As[m][lane * 8], a);
+        if (m < M) {
+          float a[8];
+          load8(A + (int64_t)m * lda + k0, a);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[m] = fmaf(a[k], w[k], acc[m]);
+          for (int k = 0; k < 8; ++k) acc[m] = fmaf(a[k], w[k], acc[m]);
+        }
       }
     }
   }
@@ -186,13 +182,17 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const T* __r
       }
     }
   }
-  if (n < N) {
+  part[warp][lane] = acc[0];
+  part[warp][32 + lane] = acc[32];
+  __syncthreads();
+  if (ks == 0 && n < N) {
     const float bb = bias ? bias[n] : 0.f;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int m = 32 * half + lane;
       if (m < M) {
-        float x = acc[32 * half] + bb;
+        float x = bb;
+        for (int j = 0; j < ksplit; ++j) x += part[warp + j][m];
         if (relu) x = fmaxf(x, 0.f);
         C[(int64_t)m * ldc + n] = from_f32<T>(x);
       }
@@ -266,13 +266,11 @@ extern "C" int txl_skinny_gemm(const void* A, int64_t lda, const void* W, int64_
                                int relu, int dtype, void* stream) {
   TXL_CHECK_ARG(A && W && C && M > 0 && M <= SK_MAXM && N > 0 && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "skinny_gemm: needs M<=64, K,lda,ldw multiples of 8");
   TXL_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "skinny_gemm: 16-byte alignment");
-  dim3 grid((unsigned)cdiv64(N, SK_WARPS));
-  DEC_DISPATCH(dtype, {
-    const size_t smem = sizeof(T) * SK_MAXM * SK_KC;
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) { TXL_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-    skinny_gemm_kernel<T><<<grid, SK_WARPS * 32, smem, (cudaStream_t)stream>>>((const T*)A, lda, (const T*)W, ldw, bias, (T*)C, ldc, M, N, K, relu);
-  });
+  int ksplit = 1;
+  while (ksplit < SK_WARPS && K / (ksplit * 2) >= 256) ksplit *= 2;     // each warp gets >= 256 of K (one 16-byte piece per lane)
+  const int cpb = SK_WARPS / ksplit;
+  dim3 grid((unsigned)cdiv64(N, cpb));
+  DEC_DISPATCH(dtype, (skinny_gemm_kernel<T><<<grid, SK_WARPS * 32, 0, (cudaStream_t)stream>>>((const T*)A, lda, (const T*)W, ldw, bias, (T*)C, ldc, M, N, K, relu, ksplit)));
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }

@@ -4,7 +4,7 @@
 #include "common.cuh"
 
 namespace {
-constexpr int NT = 256;
+constexpr int NT = 1024;
 
 __device__ __forceinline__ bool before(float va, int ia, float vb, int ib) {  // total order: value desc, index asc
   return va > vb || (va == vb && ia < ib);
