@@ -81,6 +81,8 @@ int txl_posemb_table(void* out, int klen, int clamp_len, int d, int dtype, float
 #define TXL_EPI_ACCUM 2
 #define TXL_EPI_MASK_POS 4
 #define TXL_EPI_DROPOUT 8
+#define TXL_EPI_BIAS_ROW 16   /* bias is indexed by the output ROW m (used with TRANSPOSE: y^T = W x^T + b) */
+#define TXL_EPI_TRANSPOSE 32  /* store C transposed: C[n*ldc + m]  (decode: features are the GEMM's M so 128-row MMA tiles stay full) */
 typedef struct {
   const float* bias;     /* [N] or NULL */
   const void* aux;       /* [M,N] same dtype/ld as C, for MASK_POS */

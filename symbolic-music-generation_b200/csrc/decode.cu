@@ -133,44 +133,74 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_attn_kernel(const T* __res
   }
 }
 
-// C[M<=64, N] = A[M,K] . W[N,K]^T (+bias)(ReLU) for the per-step Linears (M = sequences on this GPU).  Weight-streaming: the block's
-// 8 warps cover CPB output columns x KSPLIT slices of K, every weight element is read once with 16-byte loads, the activations come
-// straight from L1/L2 (all warps of a block, and all blocks, read the same 64 rows); the 64 per-row partial sums of a lane are
-// reduced across the warp by a butterfly transpose (62 shuffles) and across K slices through shared memory.
-constexpr int SK_MAXM = 64, SK_WARPS = 8;
+// C[M<=64, N] = A[M,K] . W[N,K]^T (+bias)(ReLU) for the per-step Linears (M = sequences on this GPU).  Weight-streaming:
+// a block owns 16 output columns; the activations are staged once per block in shared memory (cp.async, double-buffered 256-wide K
+// chunks); warp (rh, cg) computes rows 32*rh.. for the 4 columns of group cg, lanes split K in 16-byte pieces, so every activation
+// fetched from shared memory is used for 4 columns and every weight element is read from HBM exactly once; the per-lane partial sums
+// are reduced across the warp by butterfly transposes.
+constexpr int SK_MAXM = 64, SK_KC = 256, SK_WARPS = 8, SK_CPW = 4, SK_COLS = (SK_WARPS / 2) * SK_CPW;   // 16 columns per block
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename T>
 __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ W, int64_t ldw,
                                                                     const float* __restrict__ bias, T* __restrict__ C, int64_t ldc, int M, int N, int K,
-                                                                    int relu, int ksplit) {
-  __shared__ float part[SK_WARPS][SK_MAXM];
+                                                                    int relu) {
+  extern __shared__ __align__(16) unsigned char sk_smem[];
+  T* As = reinterpret_cast<T*>(sk_smem);                       // [2][SK_MAXM][SK_KC]
+  constexpr int VPR = SK_KC * (int)sizeof(T) / 16;             // 16-byte vectors per staged row
+  constexpr int EPV = 16 / (int)sizeof(T);                     // elements per vector
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cpb = SK_WARPS / ksplit;
-  const int col_in_blk = warp / ksplit, ks = warp % ksplit;
-  const int n = blockIdx.x * cpb + col_in_blk;
-  const int kper = ((K + ksplit - 1) / ksplit + 7) / 8 * 8;
-  const int kbeg = ks * kper, kend = min(K, kbeg + kper);
-  float acc[SK_MAXM];
+  const int rh = warp & 1, cg = warp >> 1;
+  const int n0 = blockIdx.x * SK_COLS + cg * SK_CPW;
+  const int nchunks = (K + SK_KC - 1) / SK_KC;
+  auto stage = [&](int ck, int buf) {
+    T* dst = As + (size_t)buf * SK_MAXM * SK_KC;
+    for (int e = threadIdx.x; e < SK_MAXM * VPR; e += SK_WARPS * 32) {
+      const int m = e / VPR, v = e % VPR, k = ck * SK_KC + v * EPV;
+      if (m < M && k < K) cp_async16(dst + m * SK_KC + v * EPV, A + (int64_t)m * lda + k);
+    }
+    cp_async_commit();
+  };
+  float acc[SK_CPW][32];
 #pragma unroll
-  for (int m = 0; m < SK_MAXM; ++m) acc[m] = 0.f;
-  if (n < N) {
-    for (int k0 = kbeg + lane * 8; k0 < kend; k0 += 256) {
-      float w[8];
-      load8(W + (int64_t)n * ldw + k0, w);
+  for (int c = 0; c < SK_CPW; ++c)
 #pragma unroll
-      for (int m = 0; m < SK_MAXM; ++m) {
-        if (m < M) {
-          float a[8];
-          load8(A + (int64_t)m * lda + k0, a);
+    for (int m = 0; m < 32; ++m) acc[c][m] = 0.f;
+  stage(0, 0);
+  for (int ck = 0; ck < nchunks; ++ck) {
+    if (ck + 1 < nchunks) { stage(ck + 1, (ck + 1) & 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const int k = ck * SK_KC + lane * 8;
+    if (k < K) {
+      float w[SK_CPW][8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[m] = fmaf(a[k], w[k], acc[m]);
+      for (int c = 0; c < SK_CPW; ++c) {
+        if (n0 + c < N) load8(W + (int64_t)(n0 + c) * ldw + k, w[c]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[c][j] = 0.f;
         }
       }
-    }
-  }
-  // transpose-reduce: lane l ends with the totals of rows l and 32 + l
+      const T* abuf = As + (size_t)(ck & 1) * SK_MAXM * SK_KC + (size_t)(rh * 32) * SK_KC + lane * 8;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    float* v = acc + 32 * half;
+      for (int m = 0; m < 32; ++m) {
+        float a[8];
+        load8(abuf + m * SK_KC, a);
+#pragma unroll
+        for (int c = 0; c < SK_CPW; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c][m] = fmaf(a[j], w[c][j], acc[c][m]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int c = 0; c < SK_CPW; ++c) {
+    float* v = acc[c];
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
 #pragma unroll
@@ -181,21 +211,11 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_gemm_kernel(const T* __r
         v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
       }
     }
-  }
-  part[warp][lane] = acc[0];
-  part[warp][32 + lane] = acc[32];
-  __syncthreads();
-  if (ks == 0 && n < N) {
-    const float bb = bias ? bias[n] : 0.f;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int m = 32 * half + lane;
-      if (m < M) {
-        float x = bb;
-        for (int j = 0; j < ksplit; ++j) x += part[warp + j][m];
-        if (relu) x = fmaxf(x, 0.f);
-        C[(int64_t)m * ldc + n] = from_f32<T>(x);
-      }
+    const int n = n0 + c, m = rh * 32 + lane;
+    if (n < N && m < M) {
+      float x = v[0] + (bias ? bias[n] : 0.f);
+      if (relu) x = fmaxf(x, 0.f);
+      C[(int64_t)m * ldc + n] = from_f32<T>(x);
     }
   }
 }
@@ -266,11 +286,13 @@ extern "C" int txl_skinny_gemm(const void* A, int64_t lda, const void* W, int64_
                                int relu, int dtype, void* stream) {
   TXL_CHECK_ARG(A && W && C && M > 0 && M <= SK_MAXM && N > 0 && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "skinny_gemm: needs M<=64, K,lda,ldw multiples of 8");
   TXL_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "skinny_gemm: 16-byte alignment");
-  int ksplit = 1;
-  while (ksplit < SK_WARPS && K / (ksplit * 2) >= 256) ksplit *= 2;     // each warp gets >= 256 of K (one 16-byte piece per lane)
-  const int cpb = SK_WARPS / ksplit;
-  dim3 grid((unsigned)cdiv64(N, cpb));
-  DEC_DISPATCH(dtype, (skinny_gemm_kernel<T><<<grid, SK_WARPS * 32, 0, (cudaStream_t)stream>>>((const T*)A, lda, (const T*)W, ldw, bias, (T*)C, ldc, M, N, K, relu, ksplit)));
+  dim3 grid((unsigned)cdiv64(N, SK_COLS));
+  DEC_DISPATCH(dtype, {
+    const size_t smem = 2 * sizeof(T) * SK_MAXM * SK_KC;
+    static bool attr_set = false;
+    if (smem > 48 * 1024 && !attr_set) { TXL_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    skinny_gemm_kernel<T><<<grid, SK_WARPS * 32, smem, (cudaStream_t)stream>>>((const T*)A, lda, (const T*)W, ldw, bias, (T*)C, ldc, M, N, K, relu);
+  });
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }

@@ -70,13 +70,14 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
       int64_t gn = n0 + tx * TN + j;
       if (gn >= N) continue;
       float v = acc[i][j];
-      if (epi.bias) v += epi.bias[gn];
+      if (epi.bias) v += (epi.flags & TXL_EPI_BIAS_ROW) ? epi.bias[gm] : epi.bias[gn];
       if (epi.flags & TXL_EPI_RELU) v = fmaxf(v, 0.f);
       if (epi.flags & TXL_EPI_MASK_POS) v = to_f32(((const TC*)epi.aux)[gm * ldc + gn]) > 0.f ? v : 0.f;
       if (epi.flags & TXL_EPI_DROPOUT) v *= dropout_scale(epi.seed, epi.site, (uint64_t)(gm * N + gn), epi.drop_p, inv_keep);
       cs[j] += v;
-      if (epi.flags & TXL_EPI_ACCUM) v += to_f32(C[gm * ldc + gn]);
-      C[gm * ldc + gn] = from_f32<TC>(v);
+      const int64_t ci = (epi.flags & TXL_EPI_TRANSPOSE) ? gn * ldc + gm : gm * ldc + gn;
+      if (epi.flags & TXL_EPI_ACCUM) v += to_f32(C[ci]);
+      C[ci] = from_f32<TC>(v);
     }
   }
   if (epi.colsum) {
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
 extern "C" int txl_gemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                         int64_t ldc, int transA, int transB, int dtype_ab, int dtype_c, const TxlEpilogue* epi_in, void* stream) {
   TXL_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm: null pointer or empty shape (M=%ld N=%ld K=%ld)", (long)M, (long)N, (long)K);
-  TXL_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gemm: leading dimension too small");
+  TXL_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= ((epi_in && (epi_in->flags & TXL_EPI_TRANSPOSE)) ? M : N), "gemm: leading dimension too small");
   TxlEpilogue epi;
   if (epi_in) epi = *epi_in; else { epi.bias = nullptr; epi.aux = nullptr; epi.colsum = nullptr; epi.drop_p = 0.f; epi.seed = 0; epi.site = 0; epi.flags = 0; }
   if ((epi.flags & TXL_EPI_DROPOUT) && !(epi.drop_p > 0.f)) epi.flags &= ~TXL_EPI_DROPOUT;

@@ -252,7 +252,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               float x = v[i];
-              if (e.bias && col0 + i < p.N) x += e.bias[col0 + i];
+              if (e.bias && col0 + i < p.N) x += (e.flags & TXL_EPI_BIAS_ROW) ? (row_ok ? e.bias[row] : 0.f) : e.bias[col0 + i];
               if (e.flags & TXL_EPI_RELU) x = fmaxf(x, 0.f);
               v[i] = x;
             }
@@ -295,6 +295,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             continue;
           }
           if (!row_ok || !any_col) continue;
+          if (e.flags & TXL_EPI_TRANSPOSE) {          // lanes hold consecutive rows: each store instruction writes 32 contiguous elements
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) C[(col0 + i) * p.ldc + row] = from_f32<TC>(v[i]);
+            continue;
+          }
           TC* crow = C + row * p.ldc + col0;
           if (p.ksplits > 1) {
 #pragma unroll
@@ -408,7 +414,7 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
   p.kb_per_split = (int)cdiv64(p.nkb, p.ksplits);
   p.ksplits = (int)cdiv64(p.nkb, p.kb_per_split);   // no empty split
 
-  p.tma_store = (dtype_c == TXL_BF16 && !(epi->flags & TXL_EPI_ACCUM) && p.ksplits == 1) ? 1 : 0;
+  p.tma_store = (dtype_c == TXL_BF16 && !(epi->flags & (TXL_EPI_ACCUM | TXL_EPI_TRANSPOSE)) && p.ksplits == 1) ? 1 : 0;
   CUtensorMap tmA, tmB, tmC;
   int rc;
   if (p.tma_store) { if ((rc = txl_make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, BM, 64))) return rc; }

@@ -23,6 +23,10 @@ def supported(model, B):
 
 
 def _skinny(A, W, bias=None, relu=False, out=None):
+    """y[B, N] = x[B, K] W[N, K]^T (+bias)(ReLU).  bf16: the tcgen05 GEMM computes y^T = W x^T (output features fill the 128-row MMA tile,
+    the <=64 sequences are the MMA N) and stores it transposed; fp32 parity mode: the exact-FMA weight-streaming kernel."""
+    if A.dtype == torch.bfloat16 and A.shape[1] >= 16:
+        return ops.gemm(W, A, transB=True, bias=bias, relu=relu, out=out, bias_row=bias is not None, transpose_out=True)
     M, K = A.shape
     N = W.shape[0]
     if out is None:

@@ -67,7 +67,7 @@ def posemb_table(klen, clamp_len, d, dtype, device, drop_p=0.0, seed=0, site=0):
 
 # ----------------------------------------------------------------------------- GEMM
 def gemm(A, B, *, transA=False, transB=False, out=None, out_dtype=None, bias=None, relu=False, accumulate=False,
-         mask_pos_aux=None, colsum=None, drop_p=0.0, seed=0, site=0, M=None, N=None, K=None):
+         mask_pos_aux=None, colsum=None, drop_p=0.0, seed=0, site=0, M=None, N=None, K=None, bias_row=False, transpose_out=False):
     """C = epi(op(A) op(B)).  A, B are 2-D row-major tensors (possibly column-sliced views: stride(0) is the ld)."""
     assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1
     if M is None:
@@ -77,9 +77,9 @@ def gemm(A, B, *, transA=False, transB=False, out=None, out_dtype=None, bias=Non
     if N is None:
         N = B.shape[0] if transB else B.shape[1]
     if out is None:
-        out = torch.empty(M, N, dtype=out_dtype or A.dtype, device=A.device)
+        out = torch.empty((N, M) if transpose_out else (M, N), dtype=out_dtype or A.dtype, device=A.device)
     assert out.stride(1) == 1 and A.dtype == B.dtype
-    flags = (L.EPI_RELU if relu else 0) | (L.EPI_ACCUM if accumulate else 0)
+    flags = (L.EPI_RELU if relu else 0) | (L.EPI_ACCUM if accumulate else 0) | (L.EPI_BIAS_ROW if bias_row else 0) | (L.EPI_TRANSPOSE if transpose_out else 0)
     if mask_pos_aux is not None:
         flags |= L.EPI_MASK_POS
         assert mask_pos_aux.dtype == out.dtype and mask_pos_aux.stride(0) == out.stride(0)

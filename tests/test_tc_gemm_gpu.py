@@ -95,3 +95,19 @@ def test_tc_gemm_dropout_mask_matches_simt(ops):
     A32, B32 = A.float(), B.float()
     b = ops.gemm(A32, B32, transB=True, drop_p=0.5, seed=9, site=1)
     assert torch.equal(a != 0, b != 0)
+
+
+def test_tc_gemm_transposed_store_and_row_bias(ops):
+    """Decode-time Linears: y^T = W x^T with the sequences as the GEMM N; epilogue stores y (transposed back) and adds the per-feature bias."""
+    torch.manual_seed(4)
+    for B, N, K in ((64, 1536, 512), (8, 512, 2048), (37, 1190, 512)):
+        x = torch.randn(B, K, device='cuda').to(torch.bfloat16)
+        W = (0.05 * torch.randn(N, K, device='cuda')).to(torch.bfloat16)
+        bias = torch.randn(N, device='cuda')
+        ref = torch.relu(x.float() @ W.float().t() + bias)
+        Np = (N + 7) // 8 * 8
+        buf = torch.zeros(B, Np, device='cuda', dtype=torch.bfloat16)
+        y = ops.gemm(W, x, transB=True, bias=bias, relu=True, bias_row=True, transpose_out=True, out=buf[:, :N])
+        torch.testing.assert_close(y.float(), ref, rtol=2e-2, atol=2e-2)
+        y32 = ops.gemm(W.float(), x.float(), transB=True, bias=bias, relu=True, bias_row=True, transpose_out=True)      # SIMT path, same flags
+        torch.testing.assert_close(y32, torch.relu(x.float() @ W.float().t() + bias), rtol=1e-4, atol=1e-4)
