@@ -38,6 +38,16 @@ def flop_per_token(L, d, di, T, M, V, Kb):
     return (fwd_seq + bwd_seq) / T, fwd_seq / T
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs (B200_PROFILING.md recipe)."""
     Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
@@ -140,7 +150,7 @@ def run_reference(args):
         'e2e': {'value': r['value'], 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': 'reference dependency transformers==4.25.1 is not installable here; this is the oracle restatement (kind=port)',
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -273,7 +283,7 @@ def run_ours(args):
         r = cpu_reference_tokens_per_s(1, 1, budget_s=25.0)
         line['cpu_baseline'] = {'value': r['value'], 'unit': 'tokens/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -357,6 +367,11 @@ def dominant_kernel_probe(torch, ops, model, cfg, B, T, M, dev):
 
 
 def main():
+    # everything except the final JSON line goes to stderr (NCCL prints its version banner on stdout)
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=8)

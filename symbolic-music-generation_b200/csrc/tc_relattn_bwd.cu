@@ -31,7 +31,7 @@ template <int MODE> struct Plan;
 template <> struct Plan<MODE_DQ> {   // resident Qw Qr dO | ring {K V R} | dS dBD
   static constexpr int QW = 0, QR = 16384, DO = 32768, RING = 49152, STAGE = SZ_KV * 2 + SZ_R;
   static constexpr int K = 0, V = SZ_KV, R = 2 * SZ_KV;                     // offsets inside a stage
-  static constexpr int DS = RING + 2 * STAGE, DBD = DS + SZ_Q, P = -1, BAR = DBD + SZ_DBD;
+  static constexpr int DS = RING + 2 * STAGE, DBD = DS + SZ_Q, P = DBD + SZ_DBD, BAR = P + SZ_Q;   // P tile only for the tile store
   static constexpr int RES_BYTES = 3 * SZ_Q, STAGE_TX = STAGE;
 };
 template <> struct Plan<MODE_DKV> {  // resident K V | ring {Qw Qr dO R} | P dS pad
@@ -57,6 +57,7 @@ struct BwdArgs {
   int64_t ldq, ldkv_mem, ldkv_cur;
   float scale, scale_log2;
   int delta_min, n_delta;        // MODE_DR: diagonals J - 2I
+  int store_tiles, nt_max;       // MODE_DQ: also write the bf16 P and dS tiles of every band tile (consumed by the lite dK/dV and dR kernels)
 };
 
 struct Tile { int b, I, J; };
@@ -78,6 +79,9 @@ __device__ __forceinline__ void barrel_shift(float* w, int sh) {
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* m, const void* src, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(0), "r"(row) : "memory");
 }
 __device__ __forceinline__ int q_tile_first_kt(const BandGeom& g, int I) { return band_lo(g, I * BQ) / BKV; }
 __device__ __forceinline__ int q_tile_last_kt(const BandGeom& g, int I) {
@@ -118,7 +122,7 @@ struct TileIter {
   }
 };
 
-struct Maps { CUtensorMap qw, qr, dO, km, vm, kc, vc, r; };
+struct Maps { CUtensorMap qw, qr, dO, km, vm, kc, vc, r, pst, dst; };   // pst/dst: [tiles*128, 64] bf16 tile stores (P, dS)
 
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
 
   if (tid == 0) {
     mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
-    mbar_init(res_full, 1); mbar_init(f_full, 1); mbar_init(b_ready, N_SOFTMAX); mbar_init(b_done, 1); mbar_init(acc_full, 1); mbar_init(t_free, N_SOFTMAX);
+    mbar_init(res_full, 1); mbar_init(f_full, 1); mbar_init(b_ready, N_SOFTMAX); mbar_init(b_done, (MODE == MODE_DQ && a.store_tiles) ? 2 : 1); mbar_init(acc_full, 1); mbar_init(t_free, N_SOFTMAX);
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -254,6 +258,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
         // softmax threads have published the bf16 tiles of tile n
         mbar_wait(b_ready, ph);
         tc_fence_after();
+        if (MODE == MODE_DQ && a.store_tiles) {   // P and dS of this band tile -> global (TMA store straight from the swizzled smem tiles)
+          const int row = ((((it.b * a.H + h) * it.nI + it.I) * a.nt_max) + n) * BQ;
+          tma_store_tile(&M.pst, sm + PL::P, row);
+          tma_store_tile(&M.dst, sm + PL::DS, row);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         const uint32_t accum0 = n > 0;
         if (MODE == MODE_DQ) {
           const uint32_t ds = base + PL::DS, dbd = base + PL::DBD;
@@ -282,7 +292,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
         }
         umma_commit(b_done);
         umma_commit(&empty[s]);
+        if (MODE == MODE_DQ && a.store_tiles) {   // the work tiles may be overwritten only after the TMA stores have read them
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(b_done);
+        }
       }
+      if (MODE == MODE_DQ && a.store_tiles) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       umma_commit(acc_full);
     }
   } else {
@@ -335,7 +350,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
       }
       // previous tile's back-end MMAs must have finished reading the work tiles before they are overwritten
       if (n > 0) mbar_wait(b_done, (n - 1) & 1);
-      if (PL::P >= 0) {
+      if (PL::P >= 0 && (MODE != MODE_DQ || a.store_tiles)) {
 #pragma unroll
         for (int c = 0; c < KPT / 8; ++c) {
           uint4 o; o.x = pack2(p[c * 8], p[c * 8 + 1]); o.y = pack2(p[c * 8 + 2], p[c * 8 + 3]); o.z = pack2(p[c * 8 + 4], p[c * 8 + 5]); o.w = pack2(p[c * 8 + 6], p[c * 8 + 7]);
@@ -434,6 +449,226 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
   if (warp == W_MMA) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------ lite passes over the stored P / dS tiles
+// dK[J] = sum_I dS(I,J)^T . Qw(I),  dV[J] = sum_I P(I,J)^T . dO(I): pure TMA -> tcgen05 pipeline, no recomputation, no thread math.
+constexpr int LITE_STAGES = 3, LITE_STAGE = 4 * SZ_Q, LITE_BAR = LITE_STAGES * LITE_STAGE, LITE_SMEM = LITE_BAR + 128 + 1024;
+__global__ void __launch_bounds__(192, 1) relattn_bwd_dkv_lite_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + LITE_BAR);
+  uint64_t *full = bars, *empty = bars + LITE_STAGES, *acc_full = bars + 2 * LITE_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * LITE_STAGES + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BandGeom g = make_band(a.band);
+  const int J = blockIdx.x, h = blockIdx.y, b = blockIdx.z, nI = (g.T + BQ - 1) / BQ;
+  if (J * BKV < g.mlen && a.dk_mem == nullptr) return;
+  int Ilo = -1, count = 0;
+  for (int i = 0; i < nI; ++i)
+    if (q_tile_first_kt(g, i) <= J && J <= q_tile_last_kt(g, i)) { if (Ilo < 0) Ilo = i; ++count; }
+  auto out_ptrs = [&](int j, bf16*& dk, bf16*& dv) {
+    if (j < g.mlen) { dk = a.dk_mem + ((int64_t)b * g.mlen + j) * a.ldkv_mem; dv = a.dv_mem + ((int64_t)b * g.mlen + j) * a.ldkv_mem; }
+    else { dk = a.dk_cur + ((int64_t)b * g.T + (j - g.mlen)) * a.ldkv_cur; dv = a.dv_cur + ((int64_t)b * g.T + (j - g.mlen)) * a.ldkv_cur; }
+  };
+  if (count == 0) {
+    if (tid < BKV) { bf16 *dk, *dv; out_ptrs(J * BKV + tid, dk, dv); for (int c = 0; c < DH; ++c) { dk[h * DH + c] = __float2bfloat16(0.f); dv[h * DH + c] = __float2bfloat16(0.f); } }
+    return;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < LITE_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int n = 0; n < count; ++n) {
+        const int s = n % LITE_STAGES; const uint32_t rph = (n / LITE_STAGES) & 1;
+        const int I = Ilo + n;
+        mbar_wait(&empty[s], rph ^ 1);
+        uint8_t* st = sm + s * LITE_STAGE;
+        mbar_expect_tx(&full[s], LITE_STAGE);
+        const int trow = ((((b * a.H + h) * nI + I) * a.nt_max) + (J - q_tile_first_kt(g, I))) * BQ;
+        const int qrow = b * g.T + I * BQ;
+        tma_load_2d(st, &M.pst, &full[s], 0, trow);                    // P  (I,J)   [128 q x 64 keys]
+        tma_load_2d(st + SZ_Q, &M.dst, &full[s], 0, trow);             // dS (I,J)
+        tma_load_2d(st + 2 * SZ_Q, &M.qw, &full[s], h * DH, qrow);     // Qw (I)     [128 q x 64]
+        tma_load_2d(st + 3 * SZ_Q, &M.dO, &full[s], h * DH, qrow);     // dO (I)
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_nn = umma_idesc_bf16(BQ, DH, 1, 1);
+      for (int n = 0; n < count; ++n) {
+        const int s = n % LITE_STAGES; const uint32_t rph = (n / LITE_STAGES) & 1;
+        mbar_wait(&full[s], rph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(sm + s * LITE_STAGE);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)      // dK += dS^T . Qw   (second MN atom of the A operand = the Qw tile behind dS: rows 64..127 ignored)
+          umma_bf16(tmem_base, umma_smem_desc(st + SZ_Q + k * 2048, 16384, 1024), umma_smem_desc(st + 2 * SZ_Q + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)      // dV += P^T . dO
+          umma_bf16(tmem_base + 64, umma_smem_desc(st + k * 2048, 16384, 1024), umma_smem_desc(st + 3 * SZ_Q + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q4 = warp & 3, r = 32 * q4 + lane;     // warps 2..5 -> lane quadrants 2,3,0,1
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    if (r < BKV) {
+      bf16 *dk, *dv;
+      out_ptrs(J * BKV + r, dk, dv);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v0[32], v1[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q4) << 16) + 32 * half, v0);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q4) << 16) + 64 + 32 * half, v1);
+        tmem_ld_wait();
+        uint4* pk = reinterpret_cast<uint4*>(dk + h * DH + 32 * half);
+        uint4* pv = reinterpret_cast<uint4*>(dv + h * DH + 32 * half);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 o; o.x = pack2(v0[c * 8], v0[c * 8 + 1]); o.y = pack2(v0[c * 8 + 2], v0[c * 8 + 3]); o.z = pack2(v0[c * 8 + 4], v0[c * 8 + 5]); o.w = pack2(v0[c * 8 + 6], v0[c * 8 + 7]);
+          pk[c] = o;
+          uint4 u; u.x = pack2(v1[c * 8], v1[c * 8 + 1]); u.y = pack2(v1[c * 8 + 2], v1[c * 8 + 3]); u.z = pack2(v1[c * 8 + 4], v1[c * 8 + 5]); u.w = pack2(v1[c * 8 + 6], v1[c * 8 + 7]);
+          pv[c] = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
+// dRwin(diagonal) = sum_{I on the diagonal, b} dBD0^T . Qr, with dBD0 rebuilt from the stored dS tile by the inverse _rel_shift
+// (a per-row element offset on a shared-memory to shared-memory copy).
+constexpr int DRL_STAGES = 4, DRL_STAGE = 2 * SZ_Q, DRL_DBD = DRL_STAGES * DRL_STAGE, DRL_BAR = DRL_DBD + SZ_DBD, DRL_SMEM = DRL_BAR + 128 + 1024;
+constexpr int DRL_THREADS = N_SOFTMAX + 64;
+__global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + DRL_BAR);
+  uint64_t *full = bars, *empty = bars + DRL_STAGES, *b_ready = bars + 2 * DRL_STAGES, *b_done = b_ready + 1, *acc_full = b_ready + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_ready + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BandGeom g = make_band(a.band);
+  const int HD = a.H * DH, nI = (g.T + BQ - 1) / BQ;
+  const int delta = a.delta_min + (int)blockIdx.x, h = blockIdx.y;
+  int Ilo = -1, cntI = 0;
+  for (int i = 0; i < nI; ++i) {
+    int j = 2 * i + delta;
+    if (q_tile_first_kt(g, i) <= j && j <= q_tile_last_kt(g, i)) { if (Ilo < 0) Ilo = i; ++cntI; }
+  }
+  const int count = cntI * a.B;
+  if (count == 0) return;
+  if (tid == 0) {
+    for (int s = 0; s < DRL_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1 + N_SOFTMAX); }
+    mbar_init(b_ready, N_SOFTMAX); mbar_init(b_done, 1); mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc<128>(tmem_slot);
+  for (int e = tid; e < SZ_DBD / 16; e += DRL_THREADS) reinterpret_cast<uint4*>(sm + DRL_DBD)[e] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == W_PROD) {
+    if (lane == 0) {
+      for (int n = 0; n < count; ++n) {
+        const int s = n % DRL_STAGES; const uint32_t rph = (n / DRL_STAGES) & 1;
+        const int I = Ilo + n / a.B, b = n % a.B, J = 2 * I + delta;
+        mbar_wait(&empty[s], rph ^ 1);
+        uint8_t* st = sm + s * DRL_STAGE;
+        mbar_expect_tx(&full[s], DRL_STAGE);
+        const int trow = ((((b * a.H + h) * nI + I) * a.nt_max) + (J - q_tile_first_kt(g, I))) * BQ;
+        tma_load_2d(st, &M.dst, &full[s], 0, trow);                              // dS (I,J)
+        tma_load_2d(st + SZ_Q, &M.qr, &full[s], h * DH, b * g.T + I * BQ);       // Qr (I)
+      }
+    }
+  } else if (warp == W_MMA) {
+    if (lane == 0) {
+      const uint32_t id_nn = umma_idesc_bf16(BQ, DH, 1, 1);
+      const uint32_t dbd = smem_u32(sm + DRL_DBD);
+      for (int n = 0; n < count; ++n) {
+        const int s = n % DRL_STAGES;
+        const uint32_t qr = smem_u32(sm + s * DRL_STAGE + SZ_Q);
+        mbar_wait(b_ready, n & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base, umma_smem_desc(dbd + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + 64, umma_smem_desc(dbd + 16384 + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+        umma_commit(b_done);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int r = 32 * (warp & 3) + lane, qd = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    const int c0 = 127 - r + KPT * qd;
+    uint8_t* dbd = sm + DRL_DBD;
+    auto addr = [&](int c) -> uint8_t* { return dbd + (c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
+    for (int n = 0; n < count; ++n) {
+      const int s = n % DRL_STAGES; const uint32_t rph = (n / DRL_STAGES) & 1;
+      mbar_wait(&full[s], rph);
+      // this thread's 16 dS values (bf16) out of the swizzled K-major tile
+      const uint8_t* tile = sm + s * DRL_STAGE;
+      uint4 u0 = *reinterpret_cast<const uint4*>(tile + r * 128 + (((2 * qd) ^ (r & 7)) << 4));
+      uint4 u1 = *reinterpret_cast<const uint4*>(tile + r * 128 + (((2 * qd + 1) ^ (r & 7)) << 4));
+      mbar_arrive(&empty[s]);                        // dS tile consumed by this thread (Qr is released by the MMA commit)
+      uint32_t wv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      if (n > 0) mbar_wait(b_done, (n - 1) & 1);
+      if ((c0 & 1) == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) *reinterpret_cast<uint32_t*>(addr(c0 + 2 * k)) = wv[k];
+      } else {
+        *reinterpret_cast<uint16_t*>(addr(c0)) = (uint16_t)(wv[0] & 0xFFFFu);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) *reinterpret_cast<uint32_t*>(addr(c0 + 1 + 2 * k)) = (wv[k] >> 16) | (wv[k + 1] << 16);
+        *reinterpret_cast<uint16_t*>(addr(c0 + 15)) = (uint16_t)(wv[7] >> 16);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(b_ready);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float v0[KPT], v1[KPT];
+    tmem_ld_32x16(tmem_base + lane_base + KPT * qd, v0);
+    tmem_ld_32x16(tmem_base + lane_base + 64 + KPT * qd, v1);
+    tmem_ld_wait();
+    const int x0 = g.T - BQ + BKV * delta;
+    const int xa = x0 + r;
+    if (xa >= 0 && xa < g.klen) {
+      float* d = a.dr + (int64_t)xa * HD + h * DH + KPT * qd;
+#pragma unroll
+      for (int c = 0; c < KPT; ++c) atomicAdd(d + c, v0[c]);
+    }
+    const int xb = x0 + 64 + r;
+    if (r >= 64 && xb >= 0 && xb < g.klen) {
+      float* d = a.dr + (int64_t)xb * HD + h * DH + KPT * qd;
+#pragma unroll
+      for (int c = 0; c < KPT; ++c) atomicAdd(d + c, v1[c]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc<128>(tmem_base);
+}
+
 // qw = q + r_w_bias, qr = q + r_r_bias (bf16, [B*T, HD]); delta[b,h,i] = sum_c dO.O
 __global__ void relattn_bwd_prep_kernel(const bf16* __restrict__ q, int64_t ldq, const float* __restrict__ rwb, const float* __restrict__ rrb,
                                         const bf16* __restrict__ out, const bf16* __restrict__ dout, bf16* __restrict__ qw, bf16* __restrict__ qr,
@@ -468,9 +703,27 @@ int launch_mode(const Maps& M, const BwdArgs& a, dim3 grid, cudaStream_t st) {
 }
 }  // namespace
 
+static int bwd_nt_max(const TxlBand& band) {
+  const BandGeom g = make_band(band);
+  const int nI = (band.T + BQ - 1) / BQ;
+  int mx = 0;
+  for (int I = 0; I < nI; ++I) {
+    int j0 = band_lo(g, I * BQ) / BKV;
+    int ilast = I * BQ + BQ - 1 < band.T - 1 ? I * BQ + BQ - 1 : band.T - 1;
+    int hi = band_hi(g, ilast) < g.klen - 1 ? band_hi(g, ilast) : g.klen - 1;
+    int cnt = hi / BKV - j0 + 1;
+    if (cnt > mx) mx = cnt;
+  }
+  return mx;
+}
+static int64_t bwd_tile_rows(const TxlAttnDims* D) {
+  const int nI = (D->band.T + BQ - 1) / BQ;
+  return (int64_t)D->B * D->H * nI * bwd_nt_max(D->band) * BQ;
+}
 int64_t txl_relattn_bwd_tc_workspace(const TxlAttnDims* D) {
   const int64_t n = (int64_t)D->B * D->band.T * D->H * D->dh;
-  return 2 * n * 2 + (int64_t)D->B * D->H * D->band.T * 4 + 1024;
+  const int64_t base = 2 * n * 2 + (int64_t)D->B * D->H * D->band.T * 4 + 1024;
+  return base + 2 * bwd_tile_rows(D) * BKV * 2 + 2048;     // + bf16 P and dS tile stores
 }
 
 int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur, const void* r, const float* rwb,
@@ -524,9 +777,33 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
     if (j1 - 2 * I > dmax) dmax = j1 - 2 * I;
   }
   a.delta_min = dmin; a.n_delta = dmax - dmin + 1;
+  static int recompute = -1;     // TXL_ATTN_BWD_RECOMPUTE=1: three recompute passes instead of one recompute pass + two lite passes
+  if (recompute < 0) { const char* e = getenv("TXL_ATTN_BWD_RECOMPUTE"); recompute = (e && e[0] == '1') ? 1 : 0; }
+  const int64_t trows = bwd_tile_rows(D);
+  a.nt_max = bwd_nt_max(D->band);
+  a.store_tiles = (!recompute && trows * 1 < (1ll << 31)) ? 1 : 0;
+  if (a.store_tiles) {
+    uintptr_t pws = ((uintptr_t)(delta + (int64_t)D->B * D->H * T) + 1023) & ~(uintptr_t)1023;
+    bf16* pstore = (bf16*)pws; bf16* dstore = pstore + trows * BKV;
+    if ((rc = txl_make_tmap_2d(&M.pst, pstore, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
+    if ((rc = txl_make_tmap_2d(&M.dst, dstore, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
+  } else { M.pst = M.qw; M.dst = M.qw; }
   if ((rc = launch_mode<MODE_DQ>(M, a, dim3(nI, D->H, D->B), st))) return rc;
-  if ((rc = launch_mode<MODE_DKV>(M, a, dim3(klen / BKV, D->H, D->B), st))) return rc;
-  if ((rc = launch_mode<MODE_DR>(M, a, dim3(a.n_delta, D->H, 1), st))) return rc;
+  if (a.store_tiles) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TXL_CUDA(cudaFuncSetAttribute(relattn_bwd_dkv_lite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LITE_SMEM));
+      TXL_CUDA(cudaFuncSetAttribute(relattn_bwd_dr_lite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DRL_SMEM));
+      attr_set = true;
+    }
+    relattn_bwd_dkv_lite_kernel<<<dim3(klen / BKV, D->H, D->B), 192, LITE_SMEM, st>>>(M, a);
+    TXL_LAUNCH_CHECK();
+    relattn_bwd_dr_lite_kernel<<<dim3(a.n_delta, D->H, 1), DRL_THREADS, DRL_SMEM, st>>>(M, a);
+    TXL_LAUNCH_CHECK();
+  } else {
+    if ((rc = launch_mode<MODE_DKV>(M, a, dim3(klen / BKV, D->H, D->B), st))) return rc;
+    if ((rc = launch_mode<MODE_DR>(M, a, dim3(a.n_delta, D->H, 1), st))) return rc;
+  }
   *handled = 1;
   return TXL_OK;
 }
