@@ -249,12 +249,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   if (col0 + i < p.N) v[i] = to_f32(reinterpret_cast<const TC*>(e.aux)[row * p.ldc + col0 + i]) > 0.f ? v[i] : 0.f;
               }
             }
+            const bool col_bias = e.bias && !(e.flags & TXL_EPI_BIAS_ROW);
+            const float brow = (e.bias && (e.flags & TXL_EPI_BIAS_ROW) && row_ok) ? e.bias[row] : 0.f;
+            if (col_bias) {
+              if (full_cols) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = v[i];
-              if (e.bias && col0 + i < p.N) x += (e.flags & TXL_EPI_BIAS_ROW) ? (row_ok ? e.bias[row] : 0.f) : e.bias[col0 + i];
-              if (e.flags & TXL_EPI_RELU) x = fmaxf(x, 0.f);
-              v[i] = x;
+                for (int g4 = 0; g4 < 8; ++g4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(e.bias + col0 + g4 * 4);
+                  v[g4 * 4] += b4.x; v[g4 * 4 + 1] += b4.y; v[g4 * 4 + 2] += b4.z; v[g4 * 4 + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (col0 + i < p.N) v[i] += e.bias[col0 + i];
+              }
+            }
+            if (e.flags & TXL_EPI_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + brow, 0.f);
+            } else if (brow != 0.f) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += brow;
             }
             if (e.flags & TXL_EPI_DROPOUT) {
               const uint64_t base_idx = (uint64_t)row * (uint64_t)p.N + (uint64_t)col0;
