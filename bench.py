@@ -385,7 +385,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-decode', action='store_true')
     ap.add_argument('--decode-seqs', type=int, default=64)
-    ap.add_argument('--decode-new', type=int, default=512)
+    ap.add_argument('--decode-new', type=int, default=2048)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

@@ -162,7 +162,7 @@ template <typename T> __device__ __forceinline__ void st8(T* p, const float* f) 
 // rounds through the storage type so that forward statistics and backward see the same z
 template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f32(from_f32<T>(v)); }
 
-template <typename T>
+template <typename T, int STEPS>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ z, float* __restrict__ mean,
                                   float* __restrict__ rstd, int64_t rows, int d, float eps, float p, float inv_keep, uint64_t seed,
@@ -170,10 +170,10 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
   for (int64_t row = warp; row < rows; row += (int64_t)gridDim.x * wpb) {
-    float v[LN_MAX_STEPS][LN_VEC];
+    float v[STEPS][LN_VEC];
     float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < LN_MAX_STEPS; ++e) {
+    for (int e = 0; e < STEPS; ++e) {
       const int c = (e * 32 + lane) * LN_VEC;
       if (c < d) {
         float xv[LN_VEC], rv[LN_VEC];
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x
     const float mu = warp_sum(s) / d;
     float q = 0.f;
 #pragma unroll
-    for (int e = 0; e < LN_MAX_STEPS; ++e) {
+    for (int e = 0; e < STEPS; ++e) {
       const int c = (e * 32 + lane) * LN_VEC;
       if (c < d) {
 #pragma unroll
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x
     }
     const float rs = rsqrtf(warp_sum(q) / d + eps);
 #pragma unroll
-    for (int e = 0; e < LN_MAX_STEPS; ++e) {
+    for (int e = 0; e < STEPS; ++e) {
       const int c = (e * 32 + lane) * LN_VEC;
       if (c < d) {
         float gm[LN_VEC], bt[LN_VEC], o[LN_VEC];
@@ -220,14 +220,16 @@ extern "C" int txl_add_ln_fwd(const void* x, const void* r, const float* gamma, 
   TXL_CHECK_ARG(rows > 0 && d % LN_VEC == 0 && d <= 32 * LN_VEC * LN_MAX_STEPS, "add_ln_fwd: d=%d must be a multiple of 8, <= 1024", d);
   int grid = (int)imin64(cdiv64(rows, 8), (int64_t)txl_num_sms() * 8);
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  DISPATCH_DTYPE(dtype, (add_ln_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)r, gamma, beta, (T*)y, (T*)z, mean, rstd, rows, d, eps, drop_p, ik, seed, site)));
+#define LN_FWD_LAUNCH(S) add_ln_fwd_kernel<T, S><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)r, gamma, beta, (T*)y, (T*)z, mean, rstd, rows, d, eps, drop_p, ik, seed, site)
+  DISPATCH_DTYPE(dtype, { if (d <= 256) LN_FWD_LAUNCH(1); else if (d <= 512) LN_FWD_LAUNCH(2); else LN_FWD_LAUNCH(4); });
+#undef LN_FWD_LAUNCH
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }
 
 // dy_total = dy (+ dy2);  dz = LN'(dy_total)
-template <typename T>
-__global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, const T* __restrict__ z, const float* __restrict__ gamma,
+template <typename T, int STEPS>
+__global__ void __launch_bounds__(256, (STEPS <= 2 ? 2 : 1)) add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, const T* __restrict__ z, const float* __restrict__ gamma,
                                   const float* __restrict__ mean, const float* __restrict__ rstd, T* dx_out, int accumulate_dx,
                                   T* dr_out, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int d, float p,
                                   float inv_keep, uint64_t seed, uint32_t site) {
@@ -236,17 +238,17 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ d
   const int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
   for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
   __syncthreads();
-  float ag[LN_MAX_STEPS][LN_VEC], ab[LN_MAX_STEPS][LN_VEC];
+  float ag[STEPS][LN_VEC], ab[STEPS][LN_VEC];
 #pragma unroll
-  for (int e = 0; e < LN_MAX_STEPS; ++e)
+  for (int e = 0; e < STEPS; ++e)
 #pragma unroll
     for (int k = 0; k < LN_VEC; ++k) { ag[e][k] = 0.f; ab[e][k] = 0.f; }
   for (int64_t row = warp; row < rows; row += (int64_t)gridDim.x * wpb) {
     const float mu = mean[row], rs = rstd[row];
-    float g[LN_MAX_STEPS][LN_VEC], xh[LN_MAX_STEPS][LN_VEC];
+    float g[STEPS][LN_VEC], xh[STEPS][LN_VEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int e = 0; e < LN_MAX_STEPS; ++e) {
+    for (int e = 0; e < STEPS; ++e) {
       const int c = (e * 32 + lane) * LN_VEC;
       if (c < d) {
         float dyv[LN_VEC], zv[LN_VEC], gm[LN_VEC];
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ d
     }
     s1 = warp_sum(s1) / d; s2 = warp_sum(s2) / d;
 #pragma unroll
-    for (int e = 0; e < LN_MAX_STEPS; ++e) {
+    for (int e = 0; e < STEPS; ++e) {
       const int c = (e * 32 + lane) * LN_VEC;
       if (c < d) {
         float dz[LN_VEC];
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ d
     }
   }
 #pragma unroll
-  for (int e = 0; e < LN_MAX_STEPS; ++e) {
+  for (int e = 0; e < STEPS; ++e) {
     const int c = (e * 32 + lane) * LN_VEC;
     if (c < d) {
 #pragma unroll
@@ -306,10 +308,12 @@ extern "C" int txl_add_ln_bwd(const void* dy, const void* dy2, const void* z, co
                               int dtype, float drop_p, uint64_t seed, uint32_t site, void* stream) {
   TXL_CHECK_ARG(rows > 0 && d % LN_VEC == 0 && d <= 32 * LN_VEC * LN_MAX_STEPS, "add_ln_bwd: d=%d must be a multiple of 8, <= 1024", d);
   // dx_out may alias dy: each lane reads its elements of a row before any lane of the warp writes them
-  int grid = (int)imin64(cdiv64(rows, 8), (int64_t)txl_num_sms() * 4);
+  int grid = (int)imin64(cdiv64(rows, 8), (int64_t)txl_num_sms() * 2);
   float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   size_t smem = 2 * (size_t)d * sizeof(float);
-  DISPATCH_DTYPE(dtype, (add_ln_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)dy, (const T*)dy2, (const T*)z, gamma, mean, rstd, (T*)dx_out, accumulate_dx, (T*)dr_out, dgamma, dbeta, rows, d, drop_p, ik, seed, site)));
+#define LN_BWD_LAUNCH(S) add_ln_bwd_kernel<T, S><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)dy, (const T*)dy2, (const T*)z, gamma, mean, rstd, (T*)dx_out, accumulate_dx, (T*)dr_out, dgamma, dbeta, rows, d, drop_p, ik, seed, site)
+  DISPATCH_DTYPE(dtype, { if (d <= 256) LN_BWD_LAUNCH(1); else if (d <= 512) LN_BWD_LAUNCH(2); else LN_BWD_LAUNCH(4); });
+#undef LN_BWD_LAUNCH
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }

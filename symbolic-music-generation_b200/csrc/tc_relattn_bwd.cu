@@ -306,6 +306,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const int sh = 31 - lane;
     const int c0 = 127 - r + KPT * qd;     // first window column this thread writes in the dBD0 tile
+    // tile-invariant shared-memory offsets of this thread: its two 16-byte chunks of the K-major tiles, and its bf16 pairs in the dBD0 tile
+    uint32_t tile_off[KPT / 8], pair_off[KPT / 2], single_off[2];
+    {
+      auto dbd_off = [&](int c) -> uint32_t { return (uint32_t)((c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2); };
+#pragma unroll
+      for (int c = 0; c < KPT / 8; ++c) tile_off[c] = (uint32_t)(r * 128 + ((((KPT / 8) * qd + c) ^ (r & 7)) << 4));
+      const int ce = c0 + (c0 & 1);
+#pragma unroll
+      for (int k = 0; k < KPT / 2; ++k) pair_off[k] = dbd_off(ce + 2 * k);      // for odd c0 the last pair is unused
+      single_off[0] = dbd_off(c0); single_off[1] = dbd_off(c0 + KPT - 1);
+    }
     Tile t = it.get(0, a);
     float lse2 = 0.f, dlt = 0.f;
     auto load_row = [&](const Tile& tt, float& l2, float& dl) {
@@ -340,13 +351,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
       tc_fence_before();
       mbar_arrive(t_free);                   // S / dP / BD0 of this tile now live in registers: TMEM may be overwritten
       barrel_shift<16>(w, sh);
+      if (tile_full) {      // interior band tile (the common case): no mask arithmetic at all
 #pragma unroll
-      for (int jj = 0; jj < KPT; ++jj) {
-        const int j = j0 + KPT * qd + jj;
-        const bool valid = tile_full || (j >= lo_i && j <= hi_i);
-        const float pj = valid ? exp2f(fmaf(p[jj] + w[jj], a.scale_log2, -lse2)) : 0.f;
-        p[jj] = pj;
-        ds[jj] = pj * (ds[jj] - dlt) * a.scale;
+        for (int jj = 0; jj < KPT; ++jj) {
+          const float pj = exp2f(fmaf(p[jj] + w[jj], a.scale_log2, -lse2));
+          p[jj] = pj;
+          ds[jj] = pj * (ds[jj] - dlt) * a.scale;
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < KPT; ++jj) {
+          const int j = j0 + KPT * qd + jj;
+          const bool valid = j >= lo_i && j <= hi_i;
+          const float pj = valid ? exp2f(fmaf(p[jj] + w[jj], a.scale_log2, -lse2)) : 0.f;
+          p[jj] = pj;
+          ds[jj] = pj * (ds[jj] - dlt) * a.scale;
+        }
       }
       // previous tile's back-end MMAs must have finished reading the work tiles before they are overwritten
       if (n > 0) mbar_wait(b_done, (n - 1) & 1);
@@ -354,28 +374,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
 #pragma unroll
         for (int c = 0; c < KPT / 8; ++c) {
           uint4 o; o.x = pack2(p[c * 8], p[c * 8 + 1]); o.y = pack2(p[c * 8 + 2], p[c * 8 + 3]); o.z = pack2(p[c * 8 + 4], p[c * 8 + 5]); o.w = pack2(p[c * 8 + 6], p[c * 8 + 7]);
-          *reinterpret_cast<uint4*>(sm + PL::P + r * 128 + ((((KPT / 8) * qd + c) ^ (r & 7)) << 4)) = o;
+          *reinterpret_cast<uint4*>(sm + PL::P + tile_off[c]) = o;
         }
       }
       if (PL::DS >= 0) {
 #pragma unroll
         for (int c = 0; c < KPT / 8; ++c) {
           uint4 o; o.x = pack2(ds[c * 8], ds[c * 8 + 1]); o.y = pack2(ds[c * 8 + 2], ds[c * 8 + 3]); o.z = pack2(ds[c * 8 + 4], ds[c * 8 + 5]); o.w = pack2(ds[c * 8 + 6], ds[c * 8 + 7]);
-          *reinterpret_cast<uint4*>(sm + PL::DS + r * 128 + ((((KPT / 8) * qd + c) ^ (r & 7)) << 4)) = o;
+          *reinterpret_cast<uint4*>(sm + PL::DS + tile_off[c]) = o;
         }
       }
       if (PL::DBD >= 0) {
-        // inverse _rel_shift: dBD0[r, c0 + jj] = dS[r, KPT qd + jj]  (bf16 pairs; element address = block, row, swizzled 16-byte chunk)
+        // inverse _rel_shift: dBD0[r, c0 + jj] = dS[r, KPT qd + jj]; the (tile-invariant) shared-memory addresses were computed once
         uint8_t* dbd = sm + PL::DBD;
-        auto addr = [&](int c) -> uint8_t* { return dbd + (c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
         if ((c0 & 1) == 0) {
 #pragma unroll
-          for (int k = 0; k < KPT / 2; ++k) *reinterpret_cast<uint32_t*>(addr(c0 + 2 * k)) = pack2(ds[2 * k], ds[2 * k + 1]);
+          for (int k = 0; k < KPT / 2; ++k) *reinterpret_cast<uint32_t*>(dbd + pair_off[k]) = pack2(ds[2 * k], ds[2 * k + 1]);
         } else {
-          *reinterpret_cast<bf16*>(addr(c0)) = __float2bfloat16_rn(ds[0]);
+          *reinterpret_cast<bf16*>(dbd + single_off[0]) = __float2bfloat16_rn(ds[0]);
 #pragma unroll
-          for (int k = 0; k < KPT / 2 - 1; ++k) *reinterpret_cast<uint32_t*>(addr(c0 + 1 + 2 * k)) = pack2(ds[2 * k + 1], ds[2 * k + 2]);
-          *reinterpret_cast<bf16*>(addr(c0 + KPT - 1)) = __float2bfloat16_rn(ds[KPT - 1]);
+          for (int k = 0; k < KPT / 2 - 1; ++k) *reinterpret_cast<uint32_t*>(dbd + pair_off[k]) = pack2(ds[2 * k + 1], ds[2 * k + 2]);
+          *reinterpret_cast<bf16*>(dbd + single_off[1]) = __float2bfloat16_rn(ds[KPT - 1]);
         }
       }
       fence_proxy_async_smem();
@@ -551,15 +570,15 @@ __global__ void __launch_bounds__(192, 1) relattn_bwd_dkv_lite_kernel(const __gr
 
 // dRwin(diagonal) = sum_{I on the diagonal, b} dBD0^T . Qr, with dBD0 rebuilt from the stored dS tile by the inverse _rel_shift
 // (a per-row element offset on a shared-memory to shared-memory copy).
-constexpr int DRL_STAGES = 4, DRL_STAGE = 2 * SZ_Q, DRL_DBD = DRL_STAGES * DRL_STAGE, DRL_BAR = DRL_DBD + SZ_DBD, DRL_SMEM = DRL_BAR + 128 + 1024;
+constexpr int DRL_STAGES = 3, DRL_STAGE = 2 * SZ_Q, DRL_DBD = DRL_STAGES * DRL_STAGE, DRL_BAR = DRL_DBD + 2 * SZ_DBD, DRL_SMEM = DRL_BAR + 128 + 1024;
 constexpr int DRL_THREADS = N_SOFTMAX + 64;
 __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + DRL_BAR);
-  uint64_t *full = bars, *empty = bars + DRL_STAGES, *b_ready = bars + 2 * DRL_STAGES, *b_done = b_ready + 1, *acc_full = b_ready + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_ready + 3);
+  uint64_t *full = bars, *empty = bars + DRL_STAGES, *b_ready = bars + 2 * DRL_STAGES, *b_done = b_ready + 2, *acc_full = b_ready + 4;   // b_ready/b_done: one per dBD buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_ready + 5);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const BandGeom g = make_band(a.band);
   const int HD = a.H * DH, nI = (g.T + BQ - 1) / BQ;
@@ -573,11 +592,11 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(con
   if (count == 0) return;
   if (tid == 0) {
     for (int s = 0; s < DRL_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1 + N_SOFTMAX); }
-    mbar_init(b_ready, N_SOFTMAX); mbar_init(b_done, 1); mbar_init(acc_full, 1);
+    mbar_init(&b_ready[0], N_SOFTMAX); mbar_init(&b_ready[1], N_SOFTMAX); mbar_init(&b_done[0], 1); mbar_init(&b_done[1], 1); mbar_init(acc_full, 1);
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc<128>(tmem_slot);
-  for (int e = tid; e < SZ_DBD / 16; e += DRL_THREADS) reinterpret_cast<uint4*>(sm + DRL_DBD)[e] = make_uint4(0, 0, 0, 0);
+  for (int e = tid; e < 2 * SZ_DBD / 16; e += DRL_THREADS) reinterpret_cast<uint4*>(sm + DRL_DBD)[e] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -599,11 +618,11 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(con
   } else if (warp == W_MMA) {
     if (lane == 0) {
       const uint32_t id_nn = umma_idesc_bf16(BQ, DH, 1, 1);
-      const uint32_t dbd = smem_u32(sm + DRL_DBD);
       for (int n = 0; n < count; ++n) {
-        const int s = n % DRL_STAGES;
+        const int s = n % DRL_STAGES, buf = n & 1;
+        const uint32_t dbd = smem_u32(sm + DRL_DBD + buf * SZ_DBD);
         const uint32_t qr = smem_u32(sm + s * DRL_STAGE + SZ_Q);
-        mbar_wait(b_ready, n & 1);
+        mbar_wait(&b_ready[buf], (n >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -611,7 +630,7 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(con
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_bf16(tmem_base + 64, umma_smem_desc(dbd + 16384 + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
-        umma_commit(b_done);
+        umma_commit(&b_done[buf]);
         umma_commit(&empty[s]);
       }
       umma_commit(acc_full);
@@ -620,10 +639,10 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(con
     const int r = 32 * (warp & 3) + lane, qd = warp >> 2;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const int c0 = 127 - r + KPT * qd;
-    uint8_t* dbd = sm + DRL_DBD;
-    auto addr = [&](int c) -> uint8_t* { return dbd + (c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
     for (int n = 0; n < count; ++n) {
-      const int s = n % DRL_STAGES; const uint32_t rph = (n / DRL_STAGES) & 1;
+      const int s = n % DRL_STAGES, buf = n & 1; const uint32_t rph = (n / DRL_STAGES) & 1;
+      uint8_t* dbd = sm + DRL_DBD + buf * SZ_DBD;
+      auto addr = [&](int c) -> uint8_t* { return dbd + (c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
       mbar_wait(&full[s], rph);
       // this thread's 16 dS values (bf16) out of the swizzled K-major tile
       const uint8_t* tile = sm + s * DRL_STAGE;
@@ -631,7 +650,7 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(con
       uint4 u1 = *reinterpret_cast<const uint4*>(tile + r * 128 + (((2 * qd + 1) ^ (r & 7)) << 4));
       mbar_arrive(&empty[s]);                        // dS tile consumed by this thread (Qr is released by the MMA commit)
       uint32_t wv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-      if (n > 0) mbar_wait(b_done, (n - 1) & 1);
+      if (n > 1) mbar_wait(&b_done[buf], ((n - 2) >> 1) & 1);      // the MMAs that read this dBD buffer two tiles ago are done
       if ((c0 & 1) == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) *reinterpret_cast<uint32_t*>(addr(c0 + 2 * k)) = wv[k];
@@ -642,7 +661,7 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(con
         *reinterpret_cast<uint16_t*>(addr(c0 + 15)) = (uint16_t)(wv[7] >> 16);
       }
       fence_proxy_async_smem();
-      mbar_arrive(b_ready);
+      mbar_arrive(&b_ready[buf]);
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
