@@ -21,8 +21,8 @@ namespace {
 constexpr int BQ = 128, BKV = 64, DH = 64, WIN = 192;
 constexpr int MODE_DQ = 0, MODE_DKV = 1, MODE_DR = 2;
 constexpr int KPT = 16;                       // keys per softmax thread: 4 threads share a query row
-constexpr int N_SOFTMAX = 128 * (BKV / KPT), NTHREADS = N_SOFTMAX + 64;
-constexpr int W_PROD = N_SOFTMAX / 32, W_MMA = W_PROD + 1;
+constexpr int N_SOFTMAX = 128 * (BKV / KPT), NTHREADS = N_SOFTMAX + 96;
+constexpr int W_PROD = N_SOFTMAX / 32, W_MMA = W_PROD + 1, W_ST = W_PROD + 2;   // TMA-load, MMA-issue and tile-store warps
 constexpr int TM_S = 0, TM_DP = 64, TM_BD = 128, TM_ACC0 = 320, TM_ACC1 = 384, TMEM_COLS = 512;
 constexpr int SZ_Q = 16384, SZ_KV = 8192, SZ_R = 24576, SZ_DBD = 49152;
 
@@ -258,12 +258,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
         // softmax threads have published the bf16 tiles of tile n
         mbar_wait(b_ready, ph);
         tc_fence_after();
-        if (MODE == MODE_DQ && a.store_tiles) {   // P and dS of this band tile -> global (TMA store straight from the swizzled smem tiles)
-          const int row = ((((it.b * a.H + h) * it.nI + it.I) * a.nt_max) + n) * BQ;
-          tma_store_tile(&M.pst, sm + PL::P, row);
-          tma_store_tile(&M.dst, sm + PL::DS, row);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
         const uint32_t accum0 = n > 0;
         if (MODE == MODE_DQ) {
           const uint32_t ds = base + PL::DS, dbd = base + PL::DBD;
@@ -292,13 +286,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
         }
         umma_commit(b_done);
         umma_commit(&empty[s]);
-        if (MODE == MODE_DQ && a.store_tiles) {   // the work tiles may be overwritten only after the TMA stores have read them
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          mbar_arrive(b_done);
-        }
       }
-      if (MODE == MODE_DQ && a.store_tiles) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       umma_commit(acc_full);
+    }
+  } else if (warp == W_ST) {
+    // ======================= tile-store thread (MODE_DQ): bf16 P and dS of every band tile -> global, straight from the swizzled smem tiles
+    if (lane == 0 && MODE == MODE_DQ && a.store_tiles) {
+      for (int n = 0; n < it.count; ++n) {
+        mbar_wait(b_ready, n & 1);
+        const int row = ((((it.b * a.H + h) * it.nI + it.I) * a.nt_max) + n) * BQ;
+        tma_store_tile(&M.pst, sm + PL::P, row);
+        tma_store_tile(&M.dst, sm + PL::DS, row);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(b_done);          // second arrival: the work tiles may be overwritten only after the stores have read them
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else {
     // ======================= softmax threads: row r = 32*(warp%4)+lane, keys [KPT*qd, KPT*qd+KPT) of the tile, qd = warp/4
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(192, 1) relattn_bwd_dkv_lite_kernel(const __gr
 // dRwin(diagonal) = sum_{I on the diagonal, b} dBD0^T . Qr, with dBD0 rebuilt from the stored dS tile by the inverse _rel_shift
 // (a per-row element offset on a shared-memory to shared-memory copy).
 constexpr int DRL_STAGES = 3, DRL_STAGE = 2 * SZ_Q, DRL_DBD = DRL_STAGES * DRL_STAGE, DRL_BAR = DRL_DBD + 2 * SZ_DBD, DRL_SMEM = DRL_BAR + 128 + 1024;
-constexpr int DRL_THREADS = N_SOFTMAX + 64;
+constexpr int DRL_THREADS = N_SOFTMAX + 64;   // no store warp here
 __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
