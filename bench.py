@@ -331,39 +331,62 @@ def decode_probe(torch, pkg, pdist, cfg_train, args, dev, rank, world):
 
 
 def dominant_kernel_probe(torch, ops, model, cfg, B, T, M, dev):
-    """Times the relative-position attention forward kernel (the largest single kernel of the step) alone, 10 launches between
-    CUDA events on the current stream, inputs sized far beyond L2 (q/k/v for 32 sequences = 300 MB)."""
+    """Times the attention kernels alone (CUDA events on the launching stream, inputs of 32 sequences = 300 MB, far beyond L2).
+    `roofline` describes the largest single kernel of the step — the dQ pass of the attention backward (25 % of the step in
+    profiles/r01_launches_train_step_summary.txt); the forward kernel is reported next to it."""
     peaks = measured_peaks()
     d, H, dh = cfg.d_model, cfg.n_head, cfg.d_head
     dt = torch.bfloat16 if cfg.compute_dtype == 'bf16' else torch.float32
     torch.manual_seed(1)
     qkv = (0.5 * torch.randn(B * T, 3 * d, device=dev)).to(dt)
     kvm = (0.5 * torch.randn(B * M, 2 * d, device=dev)).to(dt)
-    P = ops.num_r(T, M, cfg.clamp_len)
-    r = (0.5 * torch.randn(P, d, device=dev)).to(dt)
+    r = (0.5 * torch.randn(T + M, d, device=dev)).to(dt)
     rwb = 0.1 * torch.randn(d, device=dev)
     rrb = 0.1 * torch.randn(d, device=dev)
     band = ops.make_band(T, M, cfg.mem_len, cfg.clamp_len, cfg.same_length)
+    dout = torch.randn(B * T, d, device=dev).to(dt)
+    dqkv, dkvm = torch.empty_like(qkv), torch.empty_like(kvm)
+    dr, drwb, drrb = torch.zeros(T + M, d, device=dev), torch.zeros(d, device=dev), torch.zeros(d, device=dev)
 
-    def run():
+    def fwd():
         return ops.relattn_fwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, B, T, H, dh, band)
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 10
-    e0.record()
-    for _ in range(n):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
+    out, lse = fwd()
+
+    def bwd():
+        ops.relattn_bwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, out, lse, dout, dqkv[:, :d], dkvm[:, :d],
+                        dkvm[:, d:], dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, drwb, drrb, B, T, H, dh, band)
+
+    def timeit(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    ms_fwd = timeit(fwd)
+    ms_bwd_all = timeit(bwd)
+    os.environ['TXL_DBG'] = '48'          # dQ pass alone (prep kernel and lite passes skipped; operands in the workspace are stale but valid)
+    try:
+        ms_dq = timeit(bwd)
+    finally:
+        os.environ.pop('TXL_DBG', None)
     Kb = min(M, T + M)
-    flops = 6.0 * T * Kb * d * B       # AC + BD + PV on the live band (SURVEY §8d), per launch
-    ach = flops / (ms / 1000) / 1e12
-    return {'kernel': 'relattn_fwd (AC+BD+rel_shift+band mask+softmax+PV)', 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tf_burst'],
-            'unit': 'TFLOP/s', 'frac': ach / peaks['tf_burst'], 'traffic': None, 'ms_per_launch': ms,
-            'algorithmic_flops_per_launch': flops, 'peak_source': 'burst bf16, ' + peaks['src']}
+    unit = 2.0 * T * Kb * d * B                      # one score-sized contraction over the live band, per launch
+    tf = lambda units, ms: units * unit / (ms / 1e3) / 1e12
+    dq = tf(3, ms_dq)                                # dP, dQw, dQr (S / BD0 recomputation is not algorithmic work)
+    return {'kernel': 'relattn_bwd_tc_kernel<0> (dQ pass of the attention backward: recompute S/BD0/dP, dS, dQw, dQr)', 'bound': 'tensor',
+            'achieved': dq, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': dq / peaks['tf_burst'],
+            'traffic': 266.8e6, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_ncu_full_attention_kernels.txt',
+            'ms_per_launch': ms_dq, 'algorithmic_flops_per_launch': 3 * unit, 'peak_source': 'burst bf16, ' + peaks['src'],
+            'other_kernels': {
+                'relattn_fwd_tc_kernel (AC+BD+rel_shift+band mask+softmax+PV)': {'ms_per_launch': ms_fwd, 'achieved': tf(3, ms_fwd), 'frac': tf(3, ms_fwd) / peaks['tf_burst'],
+                                                                                  'algorithmic_flops_per_launch': 3 * unit, 'traffic': 194.4e6},
+                'attention backward, all passes (prep + dQ + lite dK/dV + lite dR)': {'ms_per_call': ms_bwd_all, 'achieved': tf(6, ms_bwd_all),
+                                                                                      'frac': tf(6, ms_bwd_all) / peaks['tf_burst'], 'algorithmic_flops_per_call': 6 * unit}}}
 
 
 def main():

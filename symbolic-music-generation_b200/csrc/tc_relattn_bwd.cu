@@ -764,9 +764,11 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
       !al16(dv_cur) || !al16(ws) || (dk_mem && (!al16(dk_mem) || !al16(dv_mem))))
     return TXL_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  int dbg = 0;   // TXL_DBG (timing probes only): 16 = run the dQ pass alone, 32 = skip the prep kernel (operands from a previous call)
+  { const char* e = getenv("TXL_DBG"); dbg = e ? atoi(e) : 0; }
   const int64_t n = (int64_t)D->B * T * HD;
   bf16* qw = (bf16*)ws; bf16* qr = qw + n; float* delta = (float*)(qr + n);
-  {
+  if (!(dbg & 32)) {
     const int64_t warps = (int64_t)D->B * T * D->H;
     relattn_bwd_prep_kernel<<<(unsigned)cdiv64(warps, 8), 256, 0, st>>>((const bf16*)q, D->ldq, rwb, rrb, (const bf16*)out, (const bf16*)dout, qw, qr, delta, D->B, T, D->H);
     TXL_LAUNCH_CHECK();
@@ -811,6 +813,7 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
     if ((rc = txl_make_tmap_2d(&M.dst, dstore, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
   } else { M.pst = M.qw; M.dst = M.qw; }
   if ((rc = launch_mode<MODE_DQ>(M, a, dim3(nI, D->H, D->B), st))) return rc;
+  if (dbg & 16) { *handled = 1; return TXL_OK; }
   if (a.store_tiles) {
     static bool attr_set = false;
     if (!attr_set) {
