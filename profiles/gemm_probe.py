@@ -31,6 +31,10 @@ cases = {
     'fwd ff1   +bias+relu          -> [N,2048]': (lambda: ops.gemm(x, W1, transB=True, bias=b1, relu=True), 2 * N * d * di),
     'fwd ff2   h[N,2048] W2^T +bias -> [N,512]': (lambda: ops.gemm(xh, W2, transB=True, bias=b2), 2 * N * d * di),
     'dgrad ff2 df[N,512] W2 +mask+dropout+colsum -> [N,2048]': (lambda: ops.gemm(x, W2, mask_pos_aux=xh, colsum=cs, drop_p=0.1, seed=1, site=1), 2 * N * d * di),
+    'dgrad ff2 +mask+dropout (no colsum)': (lambda: ops.gemm(x, W2, mask_pos_aux=xh, drop_p=0.1, seed=1, site=1), 2 * N * d * di),
+    'dgrad ff2 +mask only': (lambda: ops.gemm(x, W2, mask_pos_aux=xh), 2 * N * d * di),
+    'dgrad ff2 plain': (lambda: ops.gemm(x, W2), 2 * N * d * di),
+    'colsum [N,2048]': (lambda: ops.colsum(xh, cs), 1),
     'dgrad ff1 dh[N,2048] W1 -> [N,512]': (lambda: ops.gemm(xh, W1), 2 * N * d * di),
     'dgrad qkv dqkv[N,1536] Wqkv -> [N,512]': (lambda: ops.gemm(x3, Wqkv), 2 * N * d * 3 * d),
     'wgrad qkv dqkv^T x -> [1536,512] fp32 +=': (lambda: ops.gemm(x3, x, transA=True, out=g3, accumulate=True), 2 * N * d * 3 * d),

@@ -203,3 +203,46 @@ def test_decode_sampling_reproducible_and_shardable(pkg, mode):
         z = (row == 0).nonzero()
         if len(z):
             assert (row[z[0, 0]:] == 0).all()
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 1e-2)])
+def test_cfg1_tiny_txl_forward_ce(pkg, mode, tol):
+    """BASELINE.json configs[0]: tiny Transformer-XL (4 layers, d_model 256, seq 512, mem_len 512) forward + CE loss on synthetic music tokens."""
+    ref, model = make_pair(pkg, mode, vocab_size=422, d_model=256, n_head=8, d_head=32, d_inner=1024, n_layer=4, mem_len=512, clamp_len=1024)
+    ids, labels = _batch(422, 2, 512)
+    ref.eval(); model.eval()
+    with torch.no_grad():
+        ro = ref(input_ids=ids, labels=labels.clone())
+        out = model(input_ids=ids.cuda(), labels=labels.cuda())
+    valid = ro.losses != 0
+    rel = ((out.losses.cpu() - ro.losses).abs() / ro.losses.abs().clamp(min=1e-3))[valid].max().item()
+    assert rel < tol, rel
+    assert abs(out.loss.item() - ro.loss.item()) / ro.loss.item() < tol
+    lrel = ((out.logits.float().cpu() - ro.logits).abs() / ro.logits.abs()).max().item()
+    assert lrel < tol, lrel
+
+
+def test_cfg2_shapes_one_layer_bf16_tensor_core_path(pkg):
+    """cfg2 geometry (d_model 512, 8 heads of 64, seq 1024, mem_len 1024, V 1190) on the tcgen05 kernels, one layer, carried non-zero mems:
+    per-token losses / log-probs within 1e-2 of the fp32 oracle, gradients close in direction and norm."""
+    ref, model = make_pair(pkg, 'bf16', vocab_size=1190, d_model=512, n_head=8, d_head=64, d_inner=2048, n_layer=1, mem_len=1024, clamp_len=1024)
+    ids, labels = _batch(1190, 2, 1024)
+    mems = [0.5 * torch.randn(1024, 2, 512)]
+    ref.train(); model.train()
+    ro = ref(input_ids=ids, mems=mems, labels=labels.clone())
+    ro.loss.backward()
+    out = model(input_ids=ids.cuda(), mems=[m.cuda() for m in mems], labels=labels.cuda())
+    out.loss.backward()
+    valid = ro.losses != 0
+    rel = ((out.losses.detach().cpu() - ro.losses.detach()).abs() / ro.losses.detach().abs().clamp(min=1e-3))[valid].max().item()
+    assert rel < 1e-2, rel
+    got = dict(model.named_parameters())
+    for name, p in ref.named_parameters():
+        g = got[name].grad.float().cpu()
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), p.grad.flatten(), dim=0).item()
+        assert cos > 0.99 and _fro(g, p.grad) < 0.12, (name, cos, _fro(g, p.grad))
+    model.eval(); ref.eval()
+    with torch.no_grad():
+        lg = model(input_ids=ids.cuda(), mems=[m.cuda() for m in mems]).logits.float().cpu()
+        lr = ref(input_ids=ids, mems=mems).logits
+    assert ((lg - lr).abs() / lr.abs()).max().item() < 1e-2

@@ -283,3 +283,33 @@ def test_adamw_matches_torch(ops):
         opt.step()
         ops.adamw_step(p, g, m, v, None, 3e-3, 0.9, 0.999, 1e-8, 0.1, step)
     torch.testing.assert_close(p, p_ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_relattn_tensor_core_vs_exact_fp32_kernels_full_band(ops):
+    """Size-independent cross-check at the cfg2 band geometry (T = mem_len = 1024, every diagonal and both band edges present): the
+    tcgen05 bf16 kernels against the exact-FMA fp32 kernels on the same (bf16-representable) inputs, forward and all gradients."""
+    torch.manual_seed(11)
+    B, H, dh, T, M = 1, 2, 64, 1024, 1024
+    d = H * dh
+    qkv = (0.5 * torch.randn(B * T, 3 * d, device='cuda')).bfloat16()
+    kvm = (0.5 * torch.randn(B * M, 2 * d, device='cuda')).bfloat16()
+    r = (0.5 * torch.randn(T + M, d, device='cuda')).bfloat16()
+    rwb, rrb = 0.3 * torch.randn(d, device='cuda'), 0.3 * torch.randn(d, device='cuda')
+    dout = torch.randn(B * T, d, device='cuda').bfloat16()
+    band = ops.make_band(T, M, M, 1024, 1)
+
+    def run(dt):
+        q_, k_, r_, do_ = qkv.to(dt), kvm.to(dt), r.to(dt), dout.to(dt)
+        out, lse = ops.relattn_fwd(q_[:, :d], k_[:, :d], k_[:, d:], q_[:, d:2 * d], q_[:, 2 * d:], r_, rwb, rrb, B, T, H, dh, band)
+        dq_, dk_ = torch.empty_like(q_), torch.empty_like(k_)
+        dr, dw, db = torch.zeros(T + M, d, device='cuda'), torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
+        ops.relattn_bwd(q_[:, :d], k_[:, :d], k_[:, d:], q_[:, d:2 * d], q_[:, 2 * d:], r_, rwb, rrb, out, lse, do_, dq_[:, :d], dk_[:, :d], dk_[:, d:],
+                        dq_[:, d:2 * d], dq_[:, 2 * d:], dr, dw, db, B, T, H, dh, band)
+        return [t.float() for t in (out, lse, dq_, dk_, dr, dw, db)]
+    tc, ex = run(torch.bfloat16), run(torch.float32)
+    names = ['out', 'lse', 'dqkv', 'dkv_mem', 'dr', 'drwb', 'drrb']
+    for n, a, b in zip(names, tc, ex):
+        err = ((a - b).norm() / b.norm()).item()
+        assert err < (2e-3 if n == 'lse' else 2e-2), (n, err)
+    # every probability row sums to one: exp(score - lse) over the live band == 1 is implied by lse agreement; check O is a convex combination
+    assert tc[0].abs().max() <= kvm[:, d:].float().abs().max() + 1e-2
