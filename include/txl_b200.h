@@ -142,9 +142,10 @@ int txl_relattn_bwd(const void* q, const void* k_mem, const void* v_mem, const v
  * argmax (optional int64 [N]) = argmax_v logit  (preprocess_logits_for_metrics, train.py:248-252). */
 int txl_logsoftmax_nll_fwd(const void* logits, int64_t ldl, const int64_t* labels, float* losses, float* lse,
                            float* logprobs, int64_t* argmax, int64_t N, int V, int dtype, void* stream);
-/* dlogits[n,v] = (softmax - onehot(label)) * grow[n]  (0 rows where label ignored); written in place over logits. */
-int txl_logsoftmax_nll_bwd(void* logits, int64_t ldl, const int64_t* labels, const float* lse, const float* grow,
-                           int64_t N, int V, int dtype, void* stream);
+/* dlogits[n,v] = (softmax - onehot(label)) * grow[n]  (0 rows where label ignored; pad columns v>=V zeroed).  dlogits may alias logits
+ * (same dtype/pitch) or be a separate buffer of another dtype (fp32 logits -> bf16 dlogits for the tensor-core dgrad/wgrad GEMMs). */
+int txl_logsoftmax_nll_bwd(const void* logits, int64_t ldl, int dtype, void* dlogits, int64_t ldd, int dtype_out, const int64_t* labels,
+                           const float* lse, const float* grow, int64_t N, int V, void* stream);
 /* loss = mean(losses[losses != 0]) and grow[n] = g_loss/cnt * (losses[n]!=0) + g_losses[n]  (transformer_xl.py:197-200) */
 int txl_masked_mean(const float* losses, int64_t N, float* loss_out, float* count_out, void* stream);
 

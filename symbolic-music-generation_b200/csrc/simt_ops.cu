@@ -396,28 +396,34 @@ extern "C" int txl_logsoftmax_nll_fwd(const void* logits, int64_t ldl, const int
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }
-template <typename T>
-__global__ void lsm_nll_bwd_kernel(T* __restrict__ logits, int64_t ldl, const int64_t* __restrict__ labels, const float* __restrict__ lse,
-                                   const float* __restrict__ grow, int64_t N, int V) {
+template <typename T, typename TO>
+__global__ void lsm_nll_bwd_kernel(const T* __restrict__ logits, int64_t ldl, TO* __restrict__ dlogits, int64_t ldd, const int64_t* __restrict__ labels,
+                                   const float* __restrict__ lse, const float* __restrict__ grow, int64_t N, int V) {
   int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
   for (int64_t row = warp; row < N; row += (int64_t)gridDim.x * wpb) {
-    T* l = logits + row * ldl;
+    const T* l = logits + row * ldl;
+    TO* o = dlogits + row * ldd;
     int64_t lab = labels[row];
     bool valid = lab >= 0 && lab < V;
     float g = valid ? grow[row] : 0.f, ls = lse[row];
-    for (int v = lane; v < ldl; v += 32) {
+    for (int v = lane; v < ldd; v += 32) {
       float out = 0.f;
       if (v < V && g != 0.f) out = (expf(to_f32(l[v]) - ls) - (v == lab ? 1.f : 0.f)) * g;
-      l[v] = from_f32<T>(out);
+      o[v] = from_f32<TO>(out);
     }
   }
 }
-extern "C" int txl_logsoftmax_nll_bwd(void* logits, int64_t ldl, const int64_t* labels, const float* lse, const float* grow,
-                                      int64_t N, int V, int dtype, void* stream) {
-  TXL_CHECK_ARG(N > 0 && V > 0 && ldl >= V, "lsm_nll_bwd: bad sizes");
+extern "C" int txl_logsoftmax_nll_bwd(const void* logits, int64_t ldl, int dtype, void* dlogits, int64_t ldd, int dtype_out, const int64_t* labels,
+                                      const float* lse, const float* grow, int64_t N, int V, void* stream) {
+  TXL_CHECK_ARG(N > 0 && V > 0 && ldl >= V && ldd >= V && logits && dlogits, "lsm_nll_bwd: bad sizes");
+  TXL_CHECK_ARG(logits != dlogits || (dtype == dtype_out && ldl == ldd), "lsm_nll_bwd: in-place needs identical dtype and pitch");
   int grid = (int)imin64(cdiv64(N, 8), (int64_t)txl_num_sms() * 8);
-  DISPATCH_DTYPE(dtype, (lsm_nll_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((T*)logits, ldl, labels, lse, grow, N, V)));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TXL_F32 && dtype_out == TXL_F32) lsm_nll_bwd_kernel<float, float><<<grid, 256, 0, st>>>((const float*)logits, ldl, (float*)dlogits, ldd, labels, lse, grow, N, V);
+  else if (dtype == TXL_F32 && dtype_out == TXL_BF16) lsm_nll_bwd_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)logits, ldl, (bf16*)dlogits, ldd, labels, lse, grow, N, V);
+  else if (dtype == TXL_BF16 && dtype_out == TXL_BF16) lsm_nll_bwd_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)logits, ldl, (bf16*)dlogits, ldd, labels, lse, grow, N, V);
+  else { txl_set_error("lsm_nll_bwd: unsupported dtype pair"); return TXL_EINVAL; }
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }

@@ -74,7 +74,7 @@ class Decoder:
         self.seed, self.seq_offset = int(seed), int(seq_offset)
         self.V = cfg.vocab_size
         self.Vp = (self.V + 7) // 8 * 8
-        self.logits = torch.zeros(B, self.Vp, dtype=dt, device=dev)
+        self.logits = torch.zeros(B, self.Vp, dtype=torch.float32 if dt == torch.bfloat16 else dt, device=dev)
         self.scores = None
         self.graph = None
         self.use_graph = use_graph

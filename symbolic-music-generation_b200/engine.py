@@ -116,7 +116,8 @@ def forward(cfg, W: List[LayerW], E, out_bias, ids, mems_bm, labels_shift, *, dr
         x = y2
     core = ops.dropout(x, drop_p, seed, SITE_FINAL) if drop_p > 0 else x
     # LM head: logits for every position; label shifting is done by the caller (labels_shift)
-    logits = torch.empty(N, g.Vp, dtype=dt, device=dev)
+    # logits stay fp32 (the log-softmax / NLL reads them once; bf16 logits would cost ~1.5e-2 absolute on every log-prob)
+    logits = torch.empty(N, g.Vp, dtype=torch.float32, device=dev)
     if g.Vp != g.V:
         logits[:, g.V:].zero_()
     ops.gemm(core, E, transB=True, bias=out_bias, out=logits, N=g.V)
@@ -139,7 +140,7 @@ def backward(cfg, W: List[LayerW], G: List[LayerW], E, gE, g_out_bias, sv: Saved
     dt = E.dtype
     p, seed = sv.drop_p, sv.seed
     # ---- LM head
-    dlogits = ops.logsoftmax_nll_bwd(sv.logits, g.V, sv.labels, sv.lse, grow)                       # in place, (N, Vp)
+    dlogits = ops.logsoftmax_nll_bwd(sv.logits, g.V, sv.labels, sv.lse, grow, out_dtype=dt)           # (N, Vp) in the compute dtype
     ops.colsum(dlogits[:, :g.V], g_out_bias)
     dl = dlogits[:, :g.V]
     ops.gemm(dl, sv.core, transA=True, out=gE, accumulate=True)                                       # dE += dlogits^T core

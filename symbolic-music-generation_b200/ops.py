@@ -167,10 +167,12 @@ def logsoftmax_nll_fwd(logits, V, labels=None, want_logprobs=False, want_argmax=
     return losses, lse, logprobs, argmax
 
 
-def logsoftmax_nll_bwd(logits, V, labels, lse, grow):
-    check(_lib().txl_logsoftmax_nll_bwd(ptr(logits), logits.stride(0), ptr(labels), ptr(lse), ptr(grow), logits.shape[0], V,
-                                        dtype_code(logits.dtype), stream_ptr()), 'logsoftmax_nll_bwd')
-    return logits
+def logsoftmax_nll_bwd(logits, V, labels, lse, grow, out_dtype=None):
+    """dlogits; in place when out_dtype is None or equals logits.dtype, else a new buffer of out_dtype with the same pitch."""
+    out = logits if out_dtype in (None, logits.dtype) else torch.empty(logits.shape[0], logits.stride(0), dtype=out_dtype, device=logits.device)
+    check(_lib().txl_logsoftmax_nll_bwd(ptr(logits), logits.stride(0), dtype_code(logits.dtype), ptr(out), out.stride(0), dtype_code(out.dtype),
+                                        ptr(labels), ptr(lse), ptr(grow), logits.shape[0], V, stream_ptr()), 'logsoftmax_nll_bwd')
+    return out
 
 
 def masked_mean(losses):

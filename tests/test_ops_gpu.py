@@ -134,7 +134,10 @@ def test_logsoftmax_nll(ops, mode):
     torch.testing.assert_close(loss, ref_loss[ref_loss != 0].mean())
     grow = torch.rand(N, device='cuda')
     l2 = logits.clone()
-    ops.logsoftmax_nll_bwd(l2, V, labels, lse, grow)
+    l2 = ops.logsoftmax_nll_bwd(l2, V, labels, lse, grow)
+    if mode == 'fp32':      # fp32 logits -> bf16 gradient buffer (what the bf16 training path does)
+        l3 = ops.logsoftmax_nll_bwd(logits.clone(), V, labels, lse, grow, out_dtype=torch.bfloat16)
+        torch.testing.assert_close(l3[:, :V].float(), l2[:, :V], rtol=1e-2, atol=1e-3)
     onehot = torch.zeros(N, V, device='cuda').scatter_(1, labels.clamp(min=0)[:, None], 1.0)
     ref = (ref_lp.exp() - onehot) * (grow * (labels >= 0))[:, None]
     torch.testing.assert_close(l2[:, :V].float(), ref, rtol=2e-2 if mode == 'bf16' else 1e-5, atol=1e-2 if mode == 'bf16' else 1e-6)
