@@ -190,6 +190,19 @@ int txl_decode_uniform(float* u, int B, uint64_t seed, int64_t seq_offset, const
 int txl_decode_commit(const int64_t* next, int64_t* tok, int64_t* unfinished, int64_t* out_ids, int64_t ld_out, int col0, int32_t* pos, int B,
                       int64_t eos, int64_t pad, int use_eos, void* stream);
 
+/* Fused decode step: embedding + all L layers (qkv, ring append + band attention, o_net, LN, FF1, FF2, LN) + LM-head GEMM as ONE persistent
+ * cooperative kernel (grid barriers between stages; every Linear split over 16-column x 256-K work items with fp32 partials summed by the
+ * consumer stage).  Per-layer pointers arrive as host arrays of L device pointers.  Call once with build_layer_table=1 (uploads the pointer
+ * table into `ws`, synchronises the stream), then once per token with build_layer_table=0 (a single launch; capturable in a CUDA graph).
+ * logits [B, Vp] fp32 = x E^T + out_bias (log-softmax / sampling / txl_decode_commit follow as separate calls).  B <= 64. */
+int64_t txl_decode_fused_workspace(int B, int d, int di, int V, int L, int dtype);
+int txl_decode_fused_step(const void* const* wqkv, const void* const* wo, const void* const* w1, const void* const* w2, const void* const* rtab,
+                          const float* const* b1, const float* const* b2, const float* const* rwb, const float* const* rrb,
+                          const float* const* ln1w, const float* const* ln1b, const float* const* ln2w, const float* const* ln2b,
+                          void* const* kc, void* const* vc, const void* E, const float* out_bias, const int64_t* tok, const int32_t* pos,
+                          float* logits, void* ws, int build_layer_table, int B, int H, int dh, int d, int di, int ML, int L, int V, int Vp,
+                          float eps, int dtype, void* stream);
+
 /* ---- mems ring / layout helpers  [A.8' _update_mems] ----------------------------------------------
  * time-major (L?,rows,B,d) <-> batch-major copies used at the Python boundary */
 int txl_tm_to_bm(const void* src, void* dst, int rows, int B, int d, int dtype_src, int dtype_dst, void* stream);

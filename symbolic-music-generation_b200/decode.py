@@ -40,7 +40,7 @@ class Decoder:
     """Device-resident generation state for `B` sequences.  Built from the mems the prompt forward returned."""
 
     def __init__(self, model, mems, out_ids, col0, *, do_sample, temperature, top_k, top_p, eos_token_id, pad_token_id, seed=0, seq_offset=0,
-                 use_graph=True):
+                 use_graph=True, use_fused=True):
         cfg = model.config
         self.model, self.cfg = model, cfg
         bm = mems._bm if hasattr(mems, '_bm') else model._mems_to_bm(mems, out_ids.shape[0])
@@ -79,11 +79,42 @@ class Decoder:
         self.graph = None
         self.use_graph = use_graph
         self.steps_done = 0
+        self.fused = None
+        if use_fused:
+            self._build_fused()
+
+    def _build_fused(self):
+        """Pointer tables + workspace of the persistent fused step kernel (csrc/decode_fused.cu)."""
+        m, cfg, lib = self.model, self.cfg, load()
+        L = cfg.n_layer
+
+        def arr(ts):
+            return (C.c_void_p * L)(*[t.data_ptr() for t in ts])
+        W = m._W
+        self._fused_keep = [[w.qkv for w in W], [w.o for w in W], [w.w1 for w in W], [w.w2 for w in W], self.r, [w.b1 for w in W], [w.b2 for w in W],
+                            [w.rwb for w in W], [w.rrb for w in W], [w.ln1_w for w in W], [w.ln1_b for w in W], [w.ln2_w for w in W], [w.ln2_b for w in W],
+                            self.kc, self.vc]
+        self._fused_arrays = [arr(ts) for ts in self._fused_keep]
+        nbytes = lib.txl_decode_fused_workspace(self.B, self.d, cfg.d_inner, self.V, L, dtype_code(self.dt))
+        self._fused_ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
+        self.logits32 = torch.zeros(self.B, self.Vp, dtype=torch.float32, device=self.dev)
+        self._fused_call(1)
+        self.fused = True
+
+    def _fused_call(self, build):
+        cfg = self.cfg
+        check(load().txl_decode_fused_step(*self._fused_arrays, ptr(self.model._E), ptr(self.model._out_bias), ptr(self.tok), ptr(self.pos),
+                                           ptr(self.logits32), ptr(self._fused_ws), int(build), self.B, cfg.n_head, cfg.d_head, self.d, cfg.d_inner,
+                                           self.ML, cfg.n_layer, self.V, self.Vp, float(cfg.layer_norm_epsilon), dtype_code(self.dt), stream_ptr()),
+              'decode_fused_step')
 
     # one decode step: every line is a kernel launch on the current stream
     def _step_kernels(self):
         m, cfg, lib = self.model, self.cfg, load()
         B, d, H, dh, ML = self.B, self.d, cfg.n_head, cfg.d_head, self.ML
+        if self.fused:
+            self._fused_call(0)
+            return self._finish_step(self.logits32)
         x = ops.embed_fwd(self.tok, m._E, math.sqrt(d))
         for li, w in enumerate(m._W):
             qkv = _skinny(x, w.qkv)
@@ -96,7 +127,11 @@ class Decoder:
             f = _skinny(hdn, w.w2, bias=w.b2)
             x, _, _, _ = ops.add_ln_fwd(y1, f, w.ln2_w, w.ln2_b, cfg.layer_norm_epsilon, save=False)
         _skinny(x, m._E, bias=m._out_bias, out=self.logits[:, :self.V])
-        _, _, logprobs, _ = ops.logsoftmax_nll_fwd(self.logits, self.V, None, want_logprobs=True)
+        return self._finish_step(self.logits)
+
+    def _finish_step(self, logits):
+        lib, B = load(), self.B
+        _, _, logprobs, _ = ops.logsoftmax_nll_fwd(logits, self.V, None, want_logprobs=True)
         self.scores = logprobs
         if self.do_sample:
             check(lib.txl_decode_uniform(ptr(self.u), B, self.seed, self.seq_offset, ptr(self.pos), stream_ptr()), 'decode_uniform')
