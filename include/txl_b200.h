@@ -196,6 +196,8 @@ int txl_decode_commit(const int64_t* next, int64_t* tok, int64_t* unfinished, in
  * table into `ws`, synchronises the stream), then once per token with build_layer_table=0 (a single launch; capturable in a CUDA graph).
  * logits [B, Vp] fp32 = x E^T + out_bias (log-softmax / sampling / txl_decode_commit follow as separate calls).  B <= 64. */
 int64_t txl_decode_fused_workspace(int B, int d, int di, int V, int L, int dtype);
+/* profiling hook: device buffer (>= 7 L + 4 uint64) receiving %globaltimer stamps after every stage of the fused step; NULL disables */
+int txl_decode_fused_set_timestamps(unsigned long long* dev_buf);
 int txl_decode_fused_step(const void* const* wqkv, const void* const* wo, const void* const* w1, const void* const* w2, const void* const* rtab,
                           const float* const* b1, const float* const* b2, const float* const* rwb, const float* const* rrb,
                           const float* const* ln1w, const float* const* ln1b, const float* const* ln2w, const float* const* ln2b,

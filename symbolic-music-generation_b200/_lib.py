@@ -70,6 +70,7 @@ SIGNATURES = {
     'txl_decode_uniform': (_i, [_vp, _i, _u64, _i64, _vp, _vp]),
     'txl_decode_commit': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _i, _i64, _i64, _i, _vp]),
     'txl_decode_fused_workspace': (_i64, [_i, _i, _i, _i, _i, _i]),
+    'txl_decode_fused_set_timestamps': (_i, [_vp]),
     'txl_decode_fused_step': (_i, [_vp] * 15 + [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     'txl_tm_to_bm': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'txl_bm_to_tm': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -35,7 +35,7 @@ __global__ void cache_init_kernel(const T* __restrict__ kv, int64_t ld, T* __res
   }
 }
 
-constexpr int DEC_THREADS = 256;
+constexpr int DEC_THREADS = 512;
 template <typename T, int DH>
 __global__ void __launch_bounds__(DEC_THREADS) decode_attn_kernel(const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc, const T* __restrict__ r,
                                                                   const float* __restrict__ rwb, const float* __restrict__ rrb, T* __restrict__ out,

@@ -34,6 +34,7 @@ struct FusedArgs {
   const float* out_bias;
   int B, H, dh, d, di, ML, L, V, Vp;
   float eps, emb_scale;
+  unsigned long long* tstamp;   // optional [1 + 7 L + 2] globaltimer stamps taken by block 0 after every stage (profiling only)
 };
 
 template <typename T> __device__ __forceinline__ void ldv8(const T* p, float* f) {
@@ -77,9 +78,36 @@ __device__ void gemm_stage(const ASrc<T>& A, const T* __restrict__ W, float* __r
     const int cgi = item % ncg, ks = item / ncg;
     const int k0 = ks * FD_KC;
     __syncthreads();
-    for (int e = threadIdx.x; e < FD_MAXB * FD_KC; e += FD_THREADS) {
-      const int b = e / FD_KC, k = k0 + e % FD_KC;
-      As[e] = (b < B && k < K) ? from_f32<T>(a_elem(A, B, K, b, k)) : from_f32<T>(0.f);
+    // stage A[:, k0 : k0+256] into shared memory, 8 elements per thread per step, all loads of a step issued before use
+    constexpr int VPR = FD_KC / 8;                       // 8-element vectors per row
+#pragma unroll 4
+    for (int e = threadIdx.x; e < FD_MAXB * VPR; e += FD_THREADS) {
+      const int b = e / VPR, k = k0 + (e % VPR) * 8;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      if (b < B && k < K) {
+        if (A.t) {
+          ldv8(A.t + (int64_t)b * K + k, f);
+        } else {
+          for (int sidx = 0; sidx < A.nks; ++sidx) {
+            const float4 p0 = *reinterpret_cast<const float4*>(A.part + ((int64_t)sidx * B + b) * K + k);
+            const float4 p1 = *reinterpret_cast<const float4*>(A.part + ((int64_t)sidx * B + b) * K + k + 4);
+            f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
+          }
+          if (A.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += A.bias[k + j];
+          }
+          if (A.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+        }
+      }
+      T* dst = As + (size_t)b * FD_KC + (e % VPR) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = from_f32<T>(f[j]);
     }
     __syncthreads();
     const int n0 = cgi * FD_COLS + cgp * 4;
@@ -129,36 +157,52 @@ __device__ void gemm_stage(const ASrc<T>& A, const T* __restrict__ W, float* __r
   }
 }
 
-// y[b,:] = LN(resid[b,:] + sum_s part[s][b,:] (+bias)) * gamma + beta, one warp per row
+// y[b,:] = LN(resid[b,:] + sum_s part[s][b,:] (+bias)) * gamma + beta, one warp per row, the row held in registers (d <= 1024)
 template <typename T>
 __device__ void ln_stage(const T* __restrict__ resid, const float* __restrict__ part, int nks, const float* __restrict__ bias, const float* __restrict__ gamma,
                          const float* __restrict__ beta, T* __restrict__ y, int B, int d, float eps) {
-  const int lane = threadIdx.x & 31, gw = blockIdx.x * (FD_THREADS / 32) + (threadIdx.x >> 5), nw = gridDim.x * (FD_THREADS / 32);
+  // rows are spread over CTAs first (row b -> CTA b, warp 0): a CTA-local burst of 8 rows would leave 140 CTAs spinning on the barrier
+  const int lane = threadIdx.x & 31, gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nw = gridDim.x * (FD_THREADS / 32);
+  constexpr int MAXV = 4;                                  // 8-element vectors per lane
   for (int b = gw; b < B; b += nw) {
+    float v[MAXV][8];
     float s = 0.f;
-    for (int c = lane; c < d; c += 32) {
-      float v = to_f32(resid[(int64_t)b * d + c]);
-      for (int j = 0; j < nks; ++j) v += part[((int64_t)j * B + b) * d + c];
-      if (bias) v += bias[c];
-      v = to_f32(from_f32<T>(v));
-      s += v;
+#pragma unroll
+    for (int e = 0; e < MAXV; ++e) {
+      const int c = (e * 32 + lane) * 8;
+      if (c < d) {
+        ldv8(resid + (int64_t)b * d + c, v[e]);
+        for (int j = 0; j < nks; ++j) {
+          const float4 p0 = *reinterpret_cast<const float4*>(part + ((int64_t)j * B + b) * d + c);
+          const float4 p1 = *reinterpret_cast<const float4*>(part + ((int64_t)j * B + b) * d + c + 4);
+          v[e][0] += p0.x; v[e][1] += p0.y; v[e][2] += p0.z; v[e][3] += p0.w; v[e][4] += p1.x; v[e][5] += p1.y; v[e][6] += p1.z; v[e][7] += p1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (bias) v[e][k] += bias[c + k];
+          v[e][k] = to_f32(from_f32<T>(v[e][k]));
+          s += v[e][k];
+        }
+      }
     }
     const float mu = warp_sum(s) / d;
     float q = 0.f;
-    for (int c = lane; c < d; c += 32) {
-      float v = to_f32(resid[(int64_t)b * d + c]);
-      for (int j = 0; j < nks; ++j) v += part[((int64_t)j * B + b) * d + c];
-      if (bias) v += bias[c];
-      v = to_f32(from_f32<T>(v)) - mu;
-      q += v * v;
+#pragma unroll
+    for (int e = 0; e < MAXV; ++e) {
+      const int c = (e * 32 + lane) * 8;
+      if (c < d) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float t = v[e][k] - mu; q += t * t; }
+      }
     }
     const float rs = rsqrtf(warp_sum(q) / d + eps);
-    for (int c = lane; c < d; c += 32) {
-      float v = to_f32(resid[(int64_t)b * d + c]);
-      for (int j = 0; j < nks; ++j) v += part[((int64_t)j * B + b) * d + c];
-      if (bias) v += bias[c];
-      v = to_f32(from_f32<T>(v));
-      y[(int64_t)b * d + c] = from_f32<T>((v - mu) * rs * gamma[c] + beta[c]);
+#pragma unroll
+    for (int e = 0; e < MAXV; ++e) {
+      const int c = (e * 32 + lane) * 8;
+      if (c < d) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[(int64_t)b * d + c + k] = from_f32<T>((v[e][k] - mu) * rs * gamma[c + k] + beta[c + k]);
+      }
     }
   }
 }
@@ -269,6 +313,12 @@ __global__ void __launch_bounds__(FD_THREADS, 1) decode_fused_kernel(const Fused
   float* fsm = reinterpret_cast<float*>(fd_smem);
   const int B = a.B, d = a.d, di = a.di;
   const int ks_d = (d + FD_KC - 1) / FD_KC, ks_di = (di + FD_KC - 1) / FD_KC;
+  int ts_i = 0;
+  auto stamp = [&]() {
+    if (a.tstamp && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.tstamp[ts_i] = t; }
+    ++ts_i;
+  };
+  stamp();
   // ---- embedding
   for (int e = blockIdx.x * FD_THREADS + threadIdx.x; e < B * d; e += gridDim.x * FD_THREADS) {
     const int b = e / d, c = e % d;
@@ -281,28 +331,37 @@ __global__ void __launch_bounds__(FD_THREADS, 1) decode_fused_kernel(const Fused
     ASrc<T> sx{a.x, nullptr, 0, nullptr, 0};
     gemm_stage<T>(sx, Lw.wqkv, a.part, B, 3 * d, d, As);                       // qkv partials [ks_d][B][3d]
     grid.sync();
+    stamp();
     attn_stage<T, DH>(a, Lw, a.part, ks_d, fsm);                               // -> vec
     grid.sync();
+    stamp();
     ASrc<T> sv{a.vec, nullptr, 0, nullptr, 0};
     gemm_stage<T>(sv, Lw.wo, a.part, B, d, d, As);                             // ao partials [ks_d][B][d]
     grid.sync();
+    stamp();
     ln_stage<T>(a.x, a.part, ks_d, nullptr, Lw.ln1w, Lw.ln1b, a.y1, B, d, a.eps);
     grid.sync();
+    stamp();
     ASrc<T> sy{a.y1, nullptr, 0, nullptr, 0};
     gemm_stage<T>(sy, Lw.w1, a.part, B, di, d, As);                            // h partials [ks_d][B][di]
     grid.sync();
+    stamp();
     // FF2 reads h = relu(sum partials + b1) while staging; its own partials go behind the h partials
     float* fpart = a.part + (size_t)ks_d * B * di;
     ASrc<T> sh{nullptr, a.part, ks_d, Lw.b1, 1};
     gemm_stage<T>(sh, Lw.w2, fpart, B, d, di, As);                             // f partials [ks_di][B][d]
     grid.sync();
+    stamp();
     ln_stage<T>(a.y1, fpart, ks_di, Lw.b2, Lw.ln2w, Lw.ln2b, a.x, B, d, a.eps);
     grid.sync();
+    stamp();
   }
   // ---- LM head: logits partials, summed (+bias) into a.logits by a final pass
   ASrc<T> sx{a.x, nullptr, 0, nullptr, 0};
   gemm_stage<T>(sx, a.E, a.part, B, a.V, d, As);
   grid.sync();
+  stamp();
+  if (a.tstamp) { grid.sync(); stamp(); }     // calibration: an empty stage = the cost of one grid barrier
   for (int e = blockIdx.x * FD_THREADS + threadIdx.x; e < B * a.V; e += gridDim.x * FD_THREADS) {
     const int b = e / a.V, v = e % a.V;
     float s = a.out_bias[v];
@@ -334,6 +393,10 @@ int launch_fused(const FusedArgs<T>& a, cudaStream_t st) {
 }
 }  // namespace
 
+static unsigned long long* g_fd_tstamp = nullptr;
+/* profiling hook: device buffer of >= 7 L + 4 uint64 that receives %globaltimer stamps after every stage (NULL disables) */
+extern "C" int txl_decode_fused_set_timestamps(unsigned long long* dev_buf) { g_fd_tstamp = dev_buf; return TXL_OK; }
+
 // C-ABI: pointers arrive in flat arrays (one entry per layer) so that no struct layout crosses the language boundary.
 extern "C" int64_t txl_decode_fused_workspace(int B, int d, int di, int V, int L, int dtype) {
   const int64_t ks_d = (d + FD_KC - 1) / FD_KC, ks_di = (di + FD_KC - 1) / FD_KC;
@@ -341,9 +404,10 @@ extern "C" int64_t txl_decode_fused_workspace(int B, int d, int di, int V, int L
   const int64_t alt1 = ks_d * B * 3ll * d, alt2 = ks_d * B * (int64_t)V;
   if (alt1 > part) part = alt1;
   if (alt2 > part) part = alt2;
+  part = (part + 63) / 64 * 64;
   const int64_t layer_bytes = (dtype == TXL_F32 ? sizeof(FusedLayer<float>) : sizeof(FusedLayer<bf16>)) * (int64_t)L;
   const int64_t esz = dtype == TXL_F32 ? 4 : 2;
-  return part * 4 + 3 * (int64_t)B * d * esz + layer_bytes + 4096;
+  return part * 4 + 3 * (((int64_t)B * d * esz + 255) / 256 * 256) + layer_bytes + 4096;
 }
 
 extern "C" int txl_decode_fused_step(const void* const* wqkv, const void* const* wo, const void* const* w1, const void* const* w2, const void* const* rtab,
@@ -352,7 +416,7 @@ extern "C" int txl_decode_fused_step(const void* const* wqkv, const void* const*
                                      void* const* kc, void* const* vc, const void* E, const float* out_bias, const int64_t* tok, const int32_t* pos,
                                      float* logits, void* ws, int build_layer_table, int B, int H, int dh, int d, int di, int ML, int L, int V, int Vp,
                                      float eps, int dtype, void* stream) {
-  TXL_CHECK_ARG(B > 0 && B <= FD_MAXB && L > 0 && d % 8 == 0 && di % 8 == 0 && H * dh == d, "decode_fused: needs B<=64, d and d_inner multiples of 8");
+  TXL_CHECK_ARG(B > 0 && B <= FD_MAXB && L > 0 && d % 8 == 0 && di % 8 == 0 && H * dh == d && d <= 1024, "decode_fused: needs B<=64, d<=1024, d and d_inner multiples of 8");
   TXL_CHECK_ARG(dh == 32 || dh == 64 || dh == 128, "decode_fused: d_head %d not in {32,64,128}", dh);
   TXL_CHECK_ARG(E && out_bias && tok && pos && logits && ws, "decode_fused: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -361,13 +425,15 @@ extern "C" int txl_decode_fused_step(const void* const* wqkv, const void* const*
   const int64_t alt1 = ks_d * B * 3ll * d, alt2 = ks_d * B * (int64_t)V;
   if (alt1 > part) part = alt1;
   if (alt2 > part) part = alt2;
+  part = (part + 63) / 64 * 64;          // keeps the activation buffers behind the partials 256-byte aligned
 #define FD_RUN(TT)                                                                                                         \
   {                                                                                                                        \
     char* p = (char*)ws;                                                                                                   \
     float* partp = (float*)p; p += part * 4;                                                                               \
-    TT* x = (TT*)p; p += (int64_t)B * d * sizeof(TT);                                                                      \
-    TT* y1 = (TT*)p; p += (int64_t)B * d * sizeof(TT);                                                                     \
-    TT* vec = (TT*)p; p += (int64_t)B * d * sizeof(TT);                                                                    \
+    const int64_t act = ((int64_t)B * d * sizeof(TT) + 255) / 256 * 256;                                                   \
+    TT* x = (TT*)p; p += act;                                                                                              \
+    TT* y1 = (TT*)p; p += act;                                                                                             \
+    TT* vec = (TT*)p; p += act;                                                                                            \
     p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);                                                                   \
     FusedLayer<TT>* table = (FusedLayer<TT>*)p;                                                                            \
     if (build_layer_table) {                                                                                               \
@@ -386,7 +452,7 @@ extern "C" int txl_decode_fused_step(const void* const* wqkv, const void* const*
     FusedArgs<TT> a;                                                                                                       \
     a.layers = table; a.E = (const TT*)E; a.tok = tok; a.pos = pos; a.x = x; a.y1 = y1; a.vec = vec; a.part = partp; a.logits = logits;   \
     a.out_bias = out_bias; a.B = B; a.H = H; a.dh = dh; a.d = d; a.di = di; a.ML = ML; a.L = L; a.V = V; a.Vp = Vp; a.eps = eps;         \
-    a.emb_scale = sqrtf((float)d);                                                                                         \
+    a.emb_scale = sqrtf((float)d); a.tstamp = g_fd_tstamp;                                                                 \
     return launch_fused<TT>(a, st);                                                                                        \
   }
   if (dtype == TXL_F32) FD_RUN(float) else if (dtype == TXL_BF16) FD_RUN(bf16) else { txl_set_error("decode_fused: bad dtype"); return TXL_EINVAL; }

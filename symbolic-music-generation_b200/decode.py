@@ -40,7 +40,7 @@ class Decoder:
     """Device-resident generation state for `B` sequences.  Built from the mems the prompt forward returned."""
 
     def __init__(self, model, mems, out_ids, col0, *, do_sample, temperature, top_k, top_p, eos_token_id, pad_token_id, seed=0, seq_offset=0,
-                 use_graph=True, use_fused=True):
+                 use_graph=True, use_fused=False):
         cfg = model.config
         self.model, self.cfg = model, cfg
         bm = mems._bm if hasattr(mems, '_bm') else model._mems_to_bm(mems, out_ids.shape[0])

@@ -19,7 +19,7 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
              typical_p: Optional[float] = None, repetition_penalty: Optional[float] = None, renormalize_logits: Optional[bool] = None,
              num_beams: Optional[int] = None, num_beam_groups: Optional[int] = None, diversity_penalty=None, penalty_alpha=None,
              num_return_sequences: Optional[int] = None, eos_token_id='config', pad_token_id='config', generator=None,
-             return_step_scores: bool = False, use_decode_cache: bool = True, seed: int = 0, seq_offset: int = 0, use_cuda_graph: bool = True, use_fused_step: bool = True, **unused):
+             return_step_scores: bool = False, use_decode_cache: bool = True, seed: int = 0, seq_offset: int = 0, use_cuda_graph: bool = True, use_fused_step: bool = False, **unused):
     cfg = model.config
     if input_ids is None:
         raise ValueError('generate needs input_ids (the reference always passes a tokenised prompt, eval.py:276)')
