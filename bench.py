@@ -380,7 +380,7 @@ def dominant_kernel_probe(torch, ops, model, cfg, B, T, M, dev):
     dq = tf(3, ms_dq)                                # dP, dQw, dQr (S / BD0 recomputation is not algorithmic work)
     return {'kernel': 'relattn_bwd_tc_kernel<0> (dQ pass of the attention backward: recompute S/BD0/dP, dS, dQw, dQr)', 'bound': 'tensor',
             'achieved': dq, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': dq / peaks['tf_burst'],
-            'traffic': 266.8e6, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_ncu_full_attention_kernels.txt',
+            'traffic': 1459.2e6, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one launch (258 MB read + 1201 MB bf16 P/dS tile writes), profiles/r01_ncu_full_summary.txt',
             'ms_per_launch': ms_dq, 'algorithmic_flops_per_launch': 3 * unit, 'peak_source': 'burst bf16, ' + peaks['src'],
             'other_kernels': {
                 'relattn_fwd_tc_kernel (AC+BD+rel_shift+band mask+softmax+PV)': {'ms_per_launch': ms_fwd, 'achieved': tf(3, ms_fwd), 'frac': tf(3, ms_fwd) / peaks['tf_burst'],
