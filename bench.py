@@ -330,6 +330,11 @@ def decode_probe(torch, pkg, pdist, cfg_train, args, dev, rank, world):
                          'note': 'denominator bytes = hidden-state mems once + weights + R tables (SURVEY §8d); the K/V cache actually read is 2x the mems term'}}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dQ pass (ncu --set full, cfg2 shape, 32 sequences)
+DQ_TRAFFIC = None
+DQ_TRAFFIC_SRC = 'not captured yet for relattn_bwd_dq_saved_kernel'
+
+
 def dominant_kernel_probe(torch, ops, model, cfg, B, T, M, dev):
     """Times the attention kernels alone (CUDA events on the launching stream, inputs of 32 sequences = 300 MB, far beyond L2).
     `roofline` describes the largest single kernel of the step — the dQ pass of the attention backward (25 % of the step in
@@ -348,13 +353,13 @@ def dominant_kernel_probe(torch, ops, model, cfg, B, T, M, dev):
     dqkv, dkvm = torch.empty_like(qkv), torch.empty_like(kvm)
     dr, drwb, drrb = torch.zeros(T + M, d, device=dev), torch.zeros(d, device=dev), torch.zeros(d, device=dev)
 
-    def fwd():
-        return ops.relattn_fwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, B, T, H, dh, band)
-    out, lse = fwd()
+    def fwd():      # as the training step calls it: the forward also leaves its soft-max numerators (bf16 P~ tiles) for the backward
+        return ops.relattn_fwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, B, T, H, dh, band, save=True)
+    out, lse, saved = fwd()
 
     def bwd():
         ops.relattn_bwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, out, lse, dout, dqkv[:, :d], dkvm[:, :d],
-                        dkvm[:, d:], dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, drwb, drrb, B, T, H, dh, band)
+                        dkvm[:, d:], dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, drwb, drrb, B, T, H, dh, band, saved=saved)
 
     def timeit(fn, n=10):
         for _ in range(3):
@@ -377,10 +382,10 @@ def dominant_kernel_probe(torch, ops, model, cfg, B, T, M, dev):
     Kb = min(M, T + M)
     unit = 2.0 * T * Kb * d * B                      # one score-sized contraction over the live band, per launch
     tf = lambda units, ms: units * unit / (ms / 1e3) / 1e12
-    dq = tf(3, ms_dq)                                # dP, dQw, dQr (S / BD0 recomputation is not algorithmic work)
-    return {'kernel': 'relattn_bwd_tc_kernel<0> (dQ pass of the attention backward: recompute S/BD0/dP, dS, dQw, dQr)', 'bound': 'tensor',
-            'achieved': dq, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': dq / peaks['tf_burst'],
-            'traffic': 1459.2e6, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one launch (258 MB read + 1201 MB bf16 P/dS tile writes), profiles/r01_ncu_full_summary.txt',
+    dq = tf(3, ms_dq)                                # dP, dQw, dQr
+    return {'kernel': 'relattn_bwd_dq_saved_kernel (dQ pass of the attention backward: P from the saved P~ tiles, dP, dS, dQw, dQr; writes bf16 P/dS tiles)',
+            'bound': 'tensor', 'achieved': dq, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': dq / peaks['tf_burst'],
+            'traffic': DQ_TRAFFIC, 'traffic_source': DQ_TRAFFIC_SRC,
             'ms_per_launch': ms_dq, 'algorithmic_flops_per_launch': 3 * unit, 'peak_source': 'burst bf16, ' + peaks['src'],
             'other_kernels': {
                 'relattn_fwd_tc_kernel (AC+BD+rel_shift+band mask+softmax+PV)': {'ms_per_launch': ms_fwd, 'achieved': tf(3, ms_fwd), 'frac': tf(3, ms_fwd) / peaks['tf_burst'],

@@ -124,17 +124,23 @@ typedef struct {
   int64_t ldq, ldkv_mem, ldkv_cur;
   int dtype;
 } TxlAttnDims;
+/* saved (optional, may be NULL): txl_relattn_saved_bytes(dims) bytes of forward state the tensor-core backward reuses instead of
+ * recomputing the scores — the bf16 soft-max numerators of every live band tile and the running row maxima behind them (what
+ * autograd keeps as `attn_prob` in HF, at half the size).  txl_relattn_saved_bytes returns 0 when no kernel would use it
+ * (fp32 mode, odd shapes): pass NULL then.  Passing a buffer the selected forward kernel cannot fill is an error, never ignored. */
+int64_t txl_relattn_saved_bytes(const TxlAttnDims* dims);
 int txl_relattn_fwd(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur,
-                    const void* r, const float* rwb, const float* rrb, void* out, float* lse,
+                    const void* r, const float* rwb, const float* rrb, void* out, float* lse, void* saved,
                     const TxlAttnDims* dims, void* stream);
 /* Backward.  dq/dk_cur/dv_cur are written with the same strides as their forward tensors (they may be
  * slices of one [B,T,3d] buffer); dk_mem/dv_mem may be NULL (mems detached and all-zero => no wgrad term).
- * dr [klen,H*dh], drwb/drrb [H*dh] are fp32 and ACCUMULATED into.  ws: workspace of txl_relattn_bwd_workspace bytes. */
+ * dr [klen,H*dh], drwb/drrb [H*dh] are fp32 and ACCUMULATED into.  ws: workspace of txl_relattn_bwd_workspace bytes.
+ * saved: NULL, or the buffer the forward call with the same inputs and dims filled (read-only here). */
 int64_t txl_relattn_bwd_workspace(const TxlAttnDims* dims);
 int txl_relattn_bwd(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur,
                     const void* r, const float* rwb, const float* rrb, const void* out, const float* lse,
                     const void* dout, void* dq, void* dk_mem, void* dv_mem, void* dk_cur, void* dv_cur,
-                    float* dr, float* drwb, float* drrb, void* ws, const TxlAttnDims* dims, void* stream);
+                    float* dr, float* drwb, float* drrb, void* ws, const void* saved, const TxlAttnDims* dims, void* stream);
 
 /* ---- LM head: log-softmax + NLL  [A.6 ProjectedAdaptiveLogSoftmax n_clusters=0; transformer_xl.py:185,193]
  * logits [N, ldl] (dtype) are the raw h.E^T+b produced by txl_gemm; labels int64 [N] (-100 = ignore).

@@ -22,10 +22,13 @@ band = ops.make_band(T, M, M, 1024, 1)
 dout = torch.randn(B * T, d, device='cuda').to(dt)
 dqkv, dkvm = torch.empty_like(qkv), torch.empty_like(kvm)
 dr, drwb, drrb = torch.zeros(T + M, d, device='cuda'), torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
+SAVE = os.environ.get('PROBE_SAVE', '1') == '1'      # forward leaves its P~ tiles for the backward (the training path) vs. full recompute
 for it in range(3):
-    out, lse = ops.relattn_fwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, B, T, H, dh, band)
+    out, lse, saved = ops.relattn_fwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, B, T, H, dh, band, save=True)
+    if not SAVE:
+        saved = None
     ops.relattn_bwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, out, lse, dout, dqkv[:, :d], dkvm[:, :d], dkvm[:, d:],
-                    dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, drwb, drrb, B, T, H, dh, band)
+                    dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, drwb, drrb, B, T, H, dh, band, saved=saved)
 torch.cuda.synchronize()
 if os.environ.get('PROBE_TIME'):
     def tm(fn, n=5):
@@ -37,7 +40,8 @@ if os.environ.get('PROBE_TIME'):
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n * 1e3
     f = lambda: ops.relattn_fwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, B, T, H, dh, band)
+    fs = lambda: ops.relattn_fwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, B, T, H, dh, band, save=True)
     b = lambda: ops.relattn_bwd(qkv[:, :d], kvm[:, :d], kvm[:, d:], qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, out, lse, dout, dqkv[:, :d], dkvm[:, :d], dkvm[:, d:],
-                                dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, drwb, drrb, B, T, H, dh, band)
-    print(f"TXL_DBG={os.environ.get('TXL_DBG', '0')}  fwd {tm(f):8.1f} us   bwd(all passes) {tm(b):8.1f} us")
+                                dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, drwb, drrb, B, T, H, dh, band, saved=saved)
+    print(f"TXL_DBG={os.environ.get('TXL_DBG', '0')} saved={saved is not None}  fwd {tm(f):8.1f} us  fwd+save {tm(fs):8.1f} us   bwd(all passes) {tm(b):8.1f} us")
 print('probe done')

@@ -52,9 +52,10 @@ SIGNATURES = {
     'txl_add_ln_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _i, _f, _u64, _u32, _vp]),
     'txl_colsum': (_i, [_vp, _i64, _i64, _i64, _i, _vp, _vp]),
     'txl_dropout': (_i, [_vp, _vp, _i64, _i, _f, _u64, _u32, _vp]),
-    'txl_relattn_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(TxlAttnDims), _vp]),
+    'txl_relattn_saved_bytes': (_i64, [C.POINTER(TxlAttnDims)]),
+    'txl_relattn_fwd': (_i, [_vp] * 11 + [C.POINTER(TxlAttnDims), _vp]),
     'txl_relattn_bwd_workspace': (_i64, [C.POINTER(TxlAttnDims)]),
-    'txl_relattn_bwd': (_i, [_vp] * 20 + [C.POINTER(TxlAttnDims), _vp]),
+    'txl_relattn_bwd': (_i, [_vp] * 21 + [C.POINTER(TxlAttnDims), _vp]),
     'txl_logsoftmax_nll_fwd': (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     'txl_logsoftmax_nll_bwd': (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp]),
     'txl_masked_mean': (_i, [_vp, _i64, _vp, _vp, _vp]),

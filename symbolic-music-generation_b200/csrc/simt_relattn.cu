@@ -4,12 +4,13 @@
 #include "common.cuh"
 
 int txl_relattn_fwd_tc(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur, const void* r,
-                       const float* rwb, const float* rrb, void* out, float* lse, const TxlAttnDims* dims, void* stream, int* handled);
+                       const float* rwb, const float* rrb, void* out, float* lse, void* saved, const TxlAttnDims* dims, void* stream, int* handled);
+int64_t txl_relattn_saved_bytes_tc(const TxlAttnDims* D);
 
 int64_t txl_relattn_bwd_tc_workspace(const TxlAttnDims* D);
 int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur, const void* r, const float* rwb,
                        const float* rrb, const void* out, const float* lse, const void* dout, void* dq, void* dk_mem, void* dv_mem, void* dk_cur,
-                       void* dv_cur, float* dr, float* drwb, float* drrb, void* ws, const TxlAttnDims* D, void* stream, int* handled);
+                       void* dv_cur, float* dr, float* drwb, float* drrb, void* ws, const void* saved, const TxlAttnDims* D, void* stream, int* handled);
 
 namespace {
 constexpr int BQ = 32;   // query rows per CTA
@@ -338,17 +339,18 @@ int check_dims(const TxlAttnDims* D) {
   }
 
 extern "C" int txl_relattn_fwd(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur,
-                               const void* r, const float* rwb, const float* rrb, void* out, float* lse, const TxlAttnDims* D,
-                               void* stream) {
+                               const void* r, const float* rwb, const float* rrb, void* out, float* lse, void* saved,
+                               const TxlAttnDims* D, void* stream) {
   int rc = check_dims(D);
   if (rc) return rc;
   TXL_CHECK_ARG(q && k_cur && v_cur && r && rwb && rrb && out && lse && (D->band.mlen == 0 || (k_mem && v_mem)), "relattn_fwd: null pointer");
   if (D->dtype == TXL_BF16) {
     int handled = 0;
-    rc = txl_relattn_fwd_tc(q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb, out, lse, D, stream, &handled);
+    rc = txl_relattn_fwd_tc(q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb, out, lse, saved, D, stream, &handled);
     if (rc) return rc;
     if (handled) return TXL_OK;
   }
+  if (saved) { txl_set_error("relattn_fwd: `saved` given but the tensor-core path cannot run this call (see txl_relattn_saved_bytes)"); return TXL_EINVAL; }
   AttnPtrs P{q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb};
   dim3 grid((D->band.T + BQ - 1) / BQ, D->H, D->B);
   cudaStream_t st = (cudaStream_t)stream;
@@ -361,6 +363,11 @@ extern "C" int txl_relattn_fwd(const void* q, const void* k_mem, const void* v_m
   return TXL_OK;
 }
 
+extern "C" int64_t txl_relattn_saved_bytes(const TxlAttnDims* D) {
+  if (!D || check_dims(D)) return 0;
+  return txl_relattn_saved_bytes_tc(D);
+}
+
 extern "C" int64_t txl_relattn_bwd_workspace(const TxlAttnDims* D) {
   if (!D) return 0;
   int64_t simt = 2ll * D->B * (D->band.mlen + D->band.T) * D->H * D->dh * (int64_t)sizeof(float);
@@ -371,7 +378,7 @@ extern "C" int64_t txl_relattn_bwd_workspace(const TxlAttnDims* D) {
 extern "C" int txl_relattn_bwd(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur,
                                const void* r, const float* rwb, const float* rrb, const void* out, const float* lse,
                                const void* dout, void* dq, void* dk_mem, void* dv_mem, void* dk_cur, void* dv_cur, float* dr,
-                               float* drwb, float* drrb, void* ws, const TxlAttnDims* D, void* stream) {
+                               float* drwb, float* drrb, void* ws, const void* saved, const TxlAttnDims* D, void* stream) {
   int rc = check_dims(D);
   if (rc) return rc;
   TXL_CHECK_ARG(q && k_cur && v_cur && r && rwb && rrb && out && lse && dout && dq && dk_cur && dv_cur && dr && drwb && drrb && ws,
@@ -379,10 +386,11 @@ extern "C" int txl_relattn_bwd(const void* q, const void* k_mem, const void* v_m
   TXL_CHECK_ARG((dk_mem == nullptr) == (dv_mem == nullptr), "relattn_bwd: dk_mem/dv_mem must both be given or both NULL");
   if (D->dtype == TXL_BF16) {
     int handled = 0;
-    rc = txl_relattn_bwd_tc(q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb, out, lse, dout, dq, dk_mem, dv_mem, dk_cur, dv_cur, dr, drwb, drrb, ws, D, stream, &handled);
+    rc = txl_relattn_bwd_tc(q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb, out, lse, dout, dq, dk_mem, dv_mem, dk_cur, dv_cur, dr, drwb, drrb, ws, saved, D, stream, &handled);
     if (rc) return rc;
     if (handled) return TXL_OK;
   }
+  if (saved) { txl_set_error("relattn_bwd: `saved` given but the tensor-core path cannot run this call"); return TXL_EINVAL; }
   AttnPtrs P{q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb};
   cudaStream_t st = (cudaStream_t)stream;
   const int klen = D->band.mlen + D->band.T, HD = D->H * D->dh;

@@ -29,6 +29,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is still open)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -74,6 +86,32 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// The same, called by ALL 32 lanes of a converged warp: the instruction is predicated on elect.sync, which lets ptxas keep the
+// descriptors in uniform registers and emit one predicated UTCHMMA.  Issued from divergent `if (lane == 0)` code the compiler
+// wraps every MMA in an ELECT / BRA.U.ANY loop instead: 117 cycles per issue vs 48 (= the smem operand floor of an M128 N64 K16
+// MMA), measured with profiles/umma_probe.cu.  elect.sync picks the same leader for the same member mask every time, so the
+// MMAs and the tcgen05.commit that tracks them come from one thread.
+__device__ __forceinline__ void umma_bf16_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one_warp() {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok)::"memory");
+  return ok != 0;
 }
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -129,3 +167,8 @@ int txl_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 // 3-D bf16 tensor [d2, rows, cols] with pitches (ld2, ld) in elements; box = 1 x box_rows x box_cols.
 int txl_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld2, uint64_t ld,
                      uint32_t box_rows, uint32_t box_cols);
+
+// forward state saved for the tensor-core attention backward (tc_relattn_bwd.cu): bf16 P~ tiles [tile_rows, 64] then fp32 maxima [tile_rows]
+int64_t txl_relattn_saved_bytes_tc(const TxlAttnDims* D);
+int64_t txl_relattn_tile_rows(const TxlAttnDims* D);
+int txl_relattn_nt_max(const TxlBand* band);

@@ -32,6 +32,8 @@ struct FwdArgs {
   TxlBand band;
   int64_t ldq;
   float scale_log2;
+  float* m_tiles;      // saved-for-backward (optional): running max used by every (row, key tile), [B, H, nI, nt_max, 128] fp32
+  int nt_max;          //   ... the bf16 P~ = exp2(score - m) tiles themselves go out through tmP, [B, H, nI, nt_max][128 x 64]
 };
 
 // w[j] <- w[j + sh] for j < OUT, 0 <= sh < 32; W = OUT + 31 valid inputs.  Select ops only, static register indices.
@@ -58,7 +60,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __global__ void __launch_bounds__(NTHREADS, 2)
 relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKm, const __grid_constant__ CUtensorMap tmVm,
                       const __grid_constant__ CUtensorMap tmKc, const __grid_constant__ CUtensorMap tmVc,
-                      const __grid_constant__ CUtensorMap tmR, const FwdArgs a) {
+                      const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmP, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -74,6 +76,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKm, const __grid_con
   const int jt0 = band_lo(g, i0) / BKV;
   const int jt1 = min(band_hi(g, ilast), g.klen - 1) / BKV;
   const int ntiles = jt1 - jt0 + 1;
+  const int tile0 = ((b * a.H + h) * (int)gridDim.x + (int)blockIdx.x) * a.nt_max;   // first saved tile of this CTA
 
   if (tid == 0) {
     mbar_init(kr_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1);
@@ -112,25 +115,31 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKm, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
-      // ======================= TMA producer + MMA issuer (one thread)
+    // ======================= TMA producer + MMA issuer: the whole warp runs the loop converged, one elected lane issues
+    {
       const uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);
       const uint32_t idesc_bd = umma_idesc_bf16(BQ, WIN, 0, 0);
       const uint32_t idesc_pv = umma_idesc_bf16(BQ, DH, 0, 1);
       const uint32_t qw_addr = smem_u32(sm + OFF_QW), qr_addr = smem_u32(sm + OFF_QR), p_addr = smem_u32(sm + OFF_P);
       const uint32_t k_addr = smem_u32(sm + OFF_K), v_addr = smem_u32(sm + OFF_V), r_addr = smem_u32(sm + OFF_R);
       auto load_kr = [&](int n) {
-        const int j0 = (jt0 + n) * BKV;
-        mbar_expect_tx(kr_full, BKV * DH * 2 + WIN * DH * 2);
-        if (j0 < g.mlen) tma_load_2d(sm + OFF_K, &tmKm, kr_full, h * DH, b * g.mlen + j0);
-        else tma_load_2d(sm + OFF_K, &tmKc, kr_full, h * DH, b * g.T + (j0 - g.mlen));
-        tma_load_2d(sm + OFF_R, &tmR, kr_full, h * DH, g.T - BQ - i0 + j0);     // x0 = T-128-i0+j0 (rows past klen: zero fill)
+        if (lane == 0) {
+          const int j0 = (jt0 + n) * BKV;
+          mbar_expect_tx(kr_full, BKV * DH * 2 + WIN * DH * 2);
+          if (j0 < g.mlen) tma_load_2d(sm + OFF_K, &tmKm, kr_full, h * DH, b * g.mlen + j0);
+          else tma_load_2d(sm + OFF_K, &tmKc, kr_full, h * DH, b * g.T + (j0 - g.mlen));
+          tma_load_2d(sm + OFF_R, &tmR, kr_full, h * DH, g.T - BQ - i0 + j0);     // x0 = T-128-i0+j0 (rows past klen: zero fill)
+        }
+        __syncwarp();
       };
       auto load_v = [&](int n) {
-        const int j0 = (jt0 + n) * BKV;
-        mbar_expect_tx(v_full, BKV * DH * 2);
-        if (j0 < g.mlen) tma_load_2d(sm + OFF_V, &tmVm, v_full, h * DH, b * g.mlen + j0);
-        else tma_load_2d(sm + OFF_V, &tmVc, v_full, h * DH, b * g.T + (j0 - g.mlen));
+        if (lane == 0) {
+          const int j0 = (jt0 + n) * BKV;
+          mbar_expect_tx(v_full, BKV * DH * 2);
+          if (j0 < g.mlen) tma_load_2d(sm + OFF_V, &tmVm, v_full, h * DH, b * g.mlen + j0);
+          else tma_load_2d(sm + OFF_V, &tmVc, v_full, h * DH, b * g.T + (j0 - g.mlen));
+        }
+        __syncwarp();
       };
       load_kr(0);
       load_v(0);
@@ -141,23 +150,36 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKm, const __grid_con
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16(tmem_base, umma_smem_desc(qw_addr + kk * 32, 16, 1024), umma_smem_desc(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_bf16_warp(tmem_base, umma_smem_desc(qw_addr + kk * 32, 16, 1024), umma_smem_desc(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16(tmem_base + 64, umma_smem_desc(qr_addr + kk * 32, 16, 1024), umma_smem_desc(r_addr + kk * 32, 16, 1024), idesc_bd, kk > 0);
-        umma_commit(s_full);
+          umma_bf16_warp(tmem_base + 64, umma_smem_desc(qr_addr + kk * 32, 16, 1024), umma_smem_desc(r_addr + kk * 32, 16, 1024), idesc_bd, kk > 0);
+        umma_commit_warp(s_full);
         mbar_wait(s_full, ph);                        // K and R smem are free again: prefetch the next tile behind the softmax
         if (n + 1 < ntiles) load_kr(n + 1);
         mbar_wait(p_full, ph);
+        if (a.m_tiles) {      // save the bf16 P~ tile for the backward pass, straight from the swizzled MMA operand
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmP)), "r"(p_addr), "r"(0), "r"((tile0 + n) * BQ) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          __syncwarp();
+        }
         mbar_wait(v_full, ph);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk)
-          umma_bf16(tmem_base, umma_smem_desc(p_addr + kk * 32, 16, 1024), umma_smem_desc(v_addr + kk * 2048, 8192, 1024), idesc_pv, kk > 0);
-        umma_commit(o_full);
+          umma_bf16_warp(tmem_base, umma_smem_desc(p_addr + kk * 32, 16, 1024), umma_smem_desc(v_addr + kk * 2048, 8192, 1024), idesc_pv, kk > 0);
+        umma_commit_warp(o_full);
         mbar_wait(o_full, ph);
         if (n + 1 < ntiles) load_v(n + 1);
+        if (a.m_tiles) {                              // P smem is rewritten only after the next s_full
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
       }
+      if (a.m_tiles && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __syncwarp();
     }
   } else {
     // ======================= softmax threads: thread r owns query row i0 + r (= TMEM lane r)
@@ -219,6 +241,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKm, const __grid_con
       }
       l_run = l_run * corr + sum;
       m_run = m_new;
+      if (a.m_tiles) a.m_tiles[(int64_t)(tile0 + n) * BQ + r] = m_safe;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
@@ -253,7 +276,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKm, const __grid_con
 }  // namespace
 
 int txl_relattn_fwd_tc(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur, const void* r,
-                       const float* rwb, const float* rrb, void* out, float* lse, const TxlAttnDims* D, void* stream, int* handled) {
+                       const float* rwb, const float* rrb, void* out, float* lse, void* saved, const TxlAttnDims* D, void* stream, int* handled) {
   *handled = 0;
   static int disabled = -1;
   if (disabled < 0) { const char* e = getenv("TXL_DISABLE_TC_ATTN"); const char* e2 = getenv("TXL_DISABLE_TC"); disabled = ((e && e[0] == '1') || (e2 && e2[0] == '1')) ? 1 : 0; }
@@ -273,8 +296,17 @@ int txl_relattn_fwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
     if ((rc = txl_make_tmap_2d(&tmVm, v_mem, (uint64_t)D->B * mlen, (uint64_t)HD, (uint64_t)D->ldkv_mem, BKV, DH))) return rc;
   } else { tmKm = tmKc; tmVm = tmVc; }
   if ((rc = txl_make_tmap_2d(&tmR, r, (uint64_t)klen, (uint64_t)HD, (uint64_t)HD, WIN, DH))) return rc;
-
+  CUtensorMap tmP = tmR;
   FwdArgs a;
+  a.m_tiles = nullptr; a.nt_max = 0;
+  if (saved) {
+    if (!al16(saved) || txl_relattn_saved_bytes_tc(D) == 0) return TXL_OK;
+    const int64_t trows = txl_relattn_tile_rows(D);
+    a.nt_max = txl_relattn_nt_max(&D->band);
+    a.m_tiles = reinterpret_cast<float*>(reinterpret_cast<bf16*>(saved) + trows * BKV);
+    if ((rc = txl_make_tmap_2d(&tmP, saved, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
+  }
+
   a.q = (const bf16*)q; a.rwb = rwb; a.rrb = rrb; a.out = (bf16*)out; a.lse = lse; a.B = D->B; a.H = D->H; a.band = D->band; a.ldq = D->ldq;
   a.scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
   static bool attr_set = false;
@@ -283,7 +315,7 @@ int txl_relattn_fwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
     attr_set = true;
   }
   dim3 grid((T + BQ - 1) / BQ, D->H, D->B);
-  relattn_fwd_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmKm, tmVm, tmKc, tmVc, tmR, a);
+  relattn_fwd_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmKm, tmVm, tmKc, tmVc, tmR, tmP, a);
   TXL_LAUNCH_CHECK();
   *handled = 1;
   return TXL_OK;

@@ -58,6 +58,8 @@ struct BwdArgs {
   float scale, scale_log2;
   int delta_min, n_delta;        // MODE_DR: diagonals J - 2I
   int store_tiles, nt_max;       // MODE_DQ: also write the bf16 P and dS tiles of every band tile (consumed by the lite dK/dV and dR kernels)
+  const float* m_tiles;          // saved by the forward kernel: the running max behind every (row, key tile) of its P~ tiles
+  int abl;                       // TXL_ABL timing ablations (results invalid when non-zero)
 };
 
 struct Tile { int b, I, J; };
@@ -122,7 +124,7 @@ struct TileIter {
   }
 };
 
-struct Maps { CUtensorMap qw, qr, dO, km, vm, kc, vc, r, pst, dst; };   // pst/dst: [tiles*128, 64] bf16 tile stores (P, dS)
+struct Maps { CUtensorMap qw, qr, dO, km, vm, kc, vc, r, pst, dst, psv, r64; };   // pst/dst: [tiles*128, 64] bf16 tile stores (P, dS); psv: P~ saved by the forward; r64: R in 64-row boxes
 
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
       }
     }
   } else if (warp == W_MMA) {
-    if (lane == 0) {
+    {   // whole warp, converged: one elected lane issues (umma_bf16_warp)
       // ======================= MMA issuer
       const uint32_t id_s = umma_idesc_bf16(BQ, BKV, 0, 0), id_bd = umma_idesc_bf16(BQ, WIN, 0, 0);
       const uint32_t id_kn = umma_idesc_bf16(BQ, DH, 0, 1);   // A K-major, B MN-major
@@ -233,12 +235,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
         mbar_wait(&full[n & 1], (n >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_S, umma_smem_desc(qw + k * 32, 16, 1024), umma_smem_desc(kk_ + k * 32, 16, 1024), id_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16_warp(tmem_base + TM_S, umma_smem_desc(qw + k * 32, 16, 1024), umma_smem_desc(kk_ + k * 32, 16, 1024), id_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_DP, umma_smem_desc(dO + k * 32, 16, 1024), umma_smem_desc(vv + k * 32, 16, 1024), id_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16_warp(tmem_base + TM_DP, umma_smem_desc(dO + k * 32, 16, 1024), umma_smem_desc(vv + k * 32, 16, 1024), id_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + TM_BD, umma_smem_desc(qr + k * 32, 16, 1024), umma_smem_desc(rr + k * 32, 16, 1024), id_bd, k > 0);
-        umma_commit(f_full);
+        for (int k = 0; k < 4; ++k) umma_bf16_warp(tmem_base + TM_BD, umma_smem_desc(qr + k * 32, 16, 1024), umma_smem_desc(rr + k * 32, 16, 1024), id_bd, k > 0);
+        umma_commit_warp(f_full);
       };
       front(0);
       for (int n = 0; n < it.count; ++n) {
@@ -263,31 +265,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
           const uint32_t ds = base + PL::DS, dbd = base + PL::DBD;
 #pragma unroll
           for (int k = 0; k < 4; ++k)      // dQw += dS . K
-            umma_bf16(tmem_base + TM_ACC0, umma_smem_desc(ds + k * 32, 16, 1024), umma_smem_desc(kk_ + k * 2048, 8192, 1024), id_kn, accum0 | (k > 0));
+            umma_bf16_warp(tmem_base + TM_ACC0, umma_smem_desc(ds + k * 32, 16, 1024), umma_smem_desc(kk_ + k * 2048, 8192, 1024), id_kn, accum0 | (k > 0));
 #pragma unroll
           for (int k = 0; k < 12; ++k)     // dQr += dBD0 . Rwin
-            umma_bf16(tmem_base + TM_ACC1, umma_smem_desc(dbd + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), umma_smem_desc(rr + k * 2048, 8192, 1024), id_kn, accum0 | (k > 0));
+            umma_bf16_warp(tmem_base + TM_ACC1, umma_smem_desc(dbd + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), umma_smem_desc(rr + k * 2048, 8192, 1024), id_kn, accum0 | (k > 0));
         } else if (MODE == MODE_DKV) {
           const uint32_t ds = base + PL::DS, pp = base + PL::P;
 #pragma unroll
           for (int k = 0; k < 8; ++k)      // dK += dS^T . Qw   (rows 64..127 of the accumulator are a second, ignored MN atom)
-            umma_bf16(tmem_base + TM_ACC0, umma_smem_desc(ds + k * 2048, 16384, 1024), umma_smem_desc(qw + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
+            umma_bf16_warp(tmem_base + TM_ACC0, umma_smem_desc(ds + k * 2048, 16384, 1024), umma_smem_desc(qw + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
 #pragma unroll
           for (int k = 0; k < 8; ++k)      // dV += P^T . dO
-            umma_bf16(tmem_base + TM_ACC1, umma_smem_desc(pp + k * 2048, 16384, 1024), umma_smem_desc(dO + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
+            umma_bf16_warp(tmem_base + TM_ACC1, umma_smem_desc(pp + k * 2048, 16384, 1024), umma_smem_desc(dO + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
         } else {
           const uint32_t dbd = base + PL::DBD;
 #pragma unroll
           for (int k = 0; k < 8; ++k)      // dRwin[0..127]   += dBD0[:, 0..127]^T . Qr
-            umma_bf16(tmem_base + TM_ACC0, umma_smem_desc(dbd + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
+            umma_bf16_warp(tmem_base + TM_ACC0, umma_smem_desc(dbd + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
 #pragma unroll
           for (int k = 0; k < 8; ++k)      // dRwin[64..191]  += dBD0[:, 64..191]^T . Qr   (lanes 64..127 hold window rows 128..191)
-            umma_bf16(tmem_base + TM_ACC1, umma_smem_desc(dbd + 16384 + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
+            umma_bf16_warp(tmem_base + TM_ACC1, umma_smem_desc(dbd + 16384 + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, accum0 | (k > 0));
         }
-        umma_commit(b_done);
-        umma_commit(&empty[s]);
+        umma_commit_warp(b_done);
+        umma_commit_warp(&empty[s]);
       }
-      umma_commit(acc_full);
+      umma_commit_warp(acc_full);
     }
   } else if (warp == W_ST) {
     // ======================= tile-store thread (MODE_DQ): bf16 P and dS of every band tile -> global, straight from the swizzled smem tiles
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __gri
 
 // ------------------------------------------------------------------ lite passes over the stored P / dS tiles
 // dK[J] = sum_I dS(I,J)^T . Qw(I),  dV[J] = sum_I P(I,J)^T . dO(I): pure TMA -> tcgen05 pipeline, no recomputation, no thread math.
-constexpr int LITE_STAGES = 3, LITE_STAGE = 4 * SZ_Q, LITE_BAR = LITE_STAGES * LITE_STAGE, LITE_SMEM = LITE_BAR + 128 + 1024;
+constexpr int LITE_STAGES = 3, LITE_STAGE = 4 * SZ_Q, LITE_BAR = LITE_STAGES * LITE_STAGE, LITE_SMEM = LITE_BAR + 256 + 1024;
 __global__ void __launch_bounds__(192, 1) relattn_bwd_dkv_lite_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__(192, 1) relattn_bwd_dkv_lite_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, converged: one elected lane issues (umma_bf16_warp)
       const uint32_t id_nn = umma_idesc_bf16(BQ, DH, 1, 1);
       for (int n = 0; n < count; ++n) {
         const int s = n % LITE_STAGES; const uint32_t rph = (n / LITE_STAGES) & 1;
@@ -533,13 +535,13 @@ __global__ void __launch_bounds__(192, 1) relattn_bwd_dkv_lite_kernel(const __gr
         const uint32_t st = smem_u32(sm + s * LITE_STAGE);
 #pragma unroll
         for (int k = 0; k < 8; ++k)      // dK += dS^T . Qw   (second MN atom of the A operand = the Qw tile behind dS: rows 64..127 ignored)
-          umma_bf16(tmem_base, umma_smem_desc(st + SZ_Q + k * 2048, 16384, 1024), umma_smem_desc(st + 2 * SZ_Q + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+          umma_bf16_warp(tmem_base, umma_smem_desc(st + SZ_Q + k * 2048, 16384, 1024), umma_smem_desc(st + 2 * SZ_Q + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
 #pragma unroll
         for (int k = 0; k < 8; ++k)      // dV += P^T . dO
-          umma_bf16(tmem_base + 64, umma_smem_desc(st + k * 2048, 16384, 1024), umma_smem_desc(st + 3 * SZ_Q + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
-        umma_commit(&empty[s]);
+          umma_bf16_warp(tmem_base + 64, umma_smem_desc(st + k * 2048, 16384, 1024), umma_smem_desc(st + 3 * SZ_Q + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+        umma_commit_warp(&empty[s]);
       }
-      umma_commit(acc_full);
+      umma_commit_warp(acc_full);
     }
   } else {
     const int q4 = warp & 3, r = 32 * q4 + lane;     // warps 2..5 -> lane quadrants 2,3,0,1
@@ -619,7 +621,7 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(con
       }
     }
   } else if (warp == W_MMA) {
-    if (lane == 0) {
+    {   // whole warp, converged: one elected lane issues (umma_bf16_warp)
       const uint32_t id_nn = umma_idesc_bf16(BQ, DH, 1, 1);
       for (int n = 0; n < count; ++n) {
         const int s = n % DRL_STAGES, buf = n & 1;
@@ -629,14 +631,14 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(con
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base, umma_smem_desc(dbd + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+          umma_bf16_warp(tmem_base, umma_smem_desc(dbd + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base + 64, umma_smem_desc(dbd + 16384 + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
-        umma_commit(&b_done[buf]);
-        umma_commit(&empty[s]);
+          umma_bf16_warp(tmem_base + 64, umma_smem_desc(dbd + 16384 + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+        umma_commit_warp(&b_done[buf]);
+        umma_commit_warp(&empty[s]);
       }
-      umma_commit(acc_full);
+      umma_commit_warp(acc_full);
     }
   } else {
     const int r = 32 * (warp & 3) + lane, qd = warp >> 2;
@@ -691,6 +693,265 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(con
   if (warp == W_MMA) tmem_dealloc<128>(tmem_base);
 }
 
+// ------------------------------------------------------------------ dQ pass over the P~ tiles the forward kernel saved
+// The forward pass leaves, per band tile, the bf16 numerators P~ = exp2(score - m) it fed to P.V and the running max m it used.
+// With the final log-sum-exp, P = P~ * exp2(m - lse): no S / BD0 recomputation, no _rel_shift, no mask arithmetic, no exp per
+// element.  Per tile only dP = dO.V^T is formed on the tensor cores (double-buffered in TMEM); the 512 softmax threads turn
+// (P~, dP) into the bf16 P / dS / dBD0 work tiles, and dQw += dS.K, dQr += dBD0.Rwin accumulate in TMEM as before.
+// (Tried and slower, see profiles/README.md: P~ through per-thread global loads with double-buffered work tiles; P / dS tile stores
+// straight from registers; the lite dK/dV kernel rebuilding P.dO from P~ by scaling dO rows.)
+// Operand traffic is what bounds this pass (a 2-stage ring put the ~2300-cycle TMA round trip on the critical path: measured
+// period = TMA latency + back-end MMA issue), so: K/V/P~ stream through a 3-stage ring, and consecutive R windows — which
+// overlap by 128 of their 192 rows — live in a 4-slot ring of 64-row chunks, one new 8 KB chunk per tile instead of 24 KB.
+struct PlanS {   // resident dO | R ring 4 x 64 rows | ring {K V P~} x 3 | dS dBD P
+  static constexpr int NST = 3;
+  static constexpr int DO = 0, RRING = SZ_Q, RING = RRING + 4 * SZ_KV, STAGE = 2 * SZ_KV + SZ_Q;
+  static constexpr int K = 0, V = SZ_KV, PT = 2 * SZ_KV;                                     // offsets inside a stage
+  static constexpr int DS = RING + NST * STAGE, DBD = DS + SZ_Q, P = DBD + SZ_DBD, BAR = P + SZ_Q;
+  static constexpr int SMEM = BAR + 256 + 1024;
+};
+static_assert(PlanS::SMEM <= 232448, "dQ pass shared-memory plan exceeds 227 KB");
+constexpr int TS_DP = 0, TS_ACC0 = 128, TS_ACC1 = 192, TS_COLS = 256;
+__device__ long long g_ts[3][32][8];     // TXL_ABL & 256: per-tile timestamps of one CTA — softmax thread 0, MMA warp, TMA producer
+#define TS(role, n, k) do { if ((a.abl & 256) && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && (n) < 32) g_ts[role][n][k] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_dq_saved_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
+  using PL = PlanS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + PL::BAR);
+  uint64_t *full = bars, *empty = bars + 3, *rfull = bars + 6, *rfree = bars + 10, *f_full = bars + 14, *t_free = bars + 16;
+  uint64_t *res_full = bars + 18, *acc_full = bars + 19, *b_ready = bars + 20, *b_done = bars + 21;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BandGeom g = make_band(a.band);
+  const int I = blockIdx.x, h = blockIdx.y, b = blockIdx.z, nI = gridDim.x;
+  const int J0 = q_tile_first_kt(g, I), count = q_tile_last_kt(g, I) - J0 + 1;
+  const int tile0 = ((b * a.H + h) * nI + I) * a.nt_max;
+  const int xbase = g.T - BQ - I * BQ + J0 * BKV;          // R row of window column 0 of band tile 0; chunk c = rows [xbase + 64 c, +64)
+
+  if (tid == 0) {
+    for (int s = 0; s < PL::NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rfree[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&f_full[s], 1); mbar_init(&t_free[s], N_SOFTMAX / 32); }
+    mbar_init(res_full, 1); mbar_init(acc_full, 1);
+    mbar_init(b_ready, N_SOFTMAX / 32); mbar_init(b_done, 2);    // b_done: back-end MMAs finished + the tile store has read the work tiles
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc<TS_COLS>(tmem_slot);
+  for (int e = tid; e < SZ_DBD / 16; e += NTHREADS) reinterpret_cast<uint4*>(sm + PL::DBD)[e] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == W_PROD) {
+    if (lane == 0) {
+      auto load_chunk = [&](int c) {
+        const int sl = c & 3;
+        if (c >= 4) mbar_wait(&rfree[sl], ((c >> 2) - 1) & 1);      // the window that last used this slot (tile c-4) is done
+        mbar_expect_tx(&rfull[sl], SZ_KV);
+        tma_load_2d(sm + PL::RRING + sl * SZ_KV, &M.r64, &rfull[sl], h * DH, xbase + BKV * c);   // rows outside [0, klen): zero fill
+      };
+      auto load_stage = [&](int n) {
+        const int s = n % PL::NST;
+        const int j0 = (J0 + n) * BKV;
+        if (n >= PL::NST) mbar_wait(&empty[s], ((n / PL::NST) - 1) & 1);   // back end of tile n-3 has read this stage
+        TS(2, n, 0);
+        uint8_t* st = sm + PL::RING + s * PL::STAGE;
+        mbar_expect_tx(&full[s], PL::STAGE);
+        if (j0 < g.mlen) { tma_load_2d(st + PL::K, &M.km, &full[s], h * DH, b * g.mlen + j0); tma_load_2d(st + PL::V, &M.vm, &full[s], h * DH, b * g.mlen + j0); }
+        else { tma_load_2d(st + PL::K, &M.kc, &full[s], h * DH, b * g.T + (j0 - g.mlen)); tma_load_2d(st + PL::V, &M.vc, &full[s], h * DH, b * g.T + (j0 - g.mlen)); }
+        tma_load_2d(st + PL::PT, &M.psv, &full[s], 0, (tile0 + n) * BQ);
+      };
+      mbar_expect_tx(res_full, SZ_Q);
+      tma_load_2d(sm + PL::DO, &M.dO, res_full, h * DH, b * g.T + I * BQ);
+      // band tile n reads window chunks n, n+1, n+2: chunks 0 .. count+1 in all.  Loads are issued in the order their slots free up:
+      // the back end of tile m releases stage m mod 3 (-> tile m+3) and window chunk m (-> chunk m+4)
+      const int nchunks = count + 2;
+      for (int c = 0; c < 4 && c < nchunks; ++c) load_chunk(c);
+      for (int n = 0; n < PL::NST && n < count; ++n) load_stage(n);
+      for (int m = 0; m < count; ++m) {
+        if (m + PL::NST < count) load_stage(m + PL::NST);
+        if (m + 4 < nchunks) load_chunk(m + 4);
+      }
+    }
+  } else if (warp == W_MMA) {
+    {   // whole warp, converged: one elected lane issues (umma_bf16_warp)
+      const uint32_t id_s = umma_idesc_bf16(BQ, BKV, 0, 0), id_kn = umma_idesc_bf16(BQ, DH, 0, 1);
+      const uint32_t base = smem_u32(sm);
+      mbar_wait(res_full, 0);
+      auto front = [&](int n) {     // dP of band tile n into its TMEM buffer
+        const int s = n % PL::NST, tb = n & 1;
+        const uint32_t vv = base + PL::RING + s * PL::STAGE + PL::V, dO = base + PL::DO;
+        mbar_wait(&full[s], (n / PL::NST) & 1);
+        TS(1, n, 0);
+        if (n >= 2) mbar_wait(&t_free[tb], ((n - 2) >> 1) & 1);
+        TS(1, n, 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_warp(tmem_base + TS_DP + 64 * tb, umma_smem_desc(dO + k * 32, 16, 1024), umma_smem_desc(vv + k * 32, 16, 1024), id_s, k > 0);
+        umma_commit_warp(&f_full[tb]);
+      };
+      front(0);
+      int fronts = 1;
+      for (int n = 0; n < count; ++n) {
+        const int s = n % PL::NST;
+        const uint32_t st = base + PL::RING + s * PL::STAGE;
+        // front end of tile n+1 ahead of tile n's back end only if its operands have already landed: never park behind a TMA
+        // round trip while a finished set of work tiles waits for its MMAs
+        if (fronts == n + 1 && n + 1 < count) {
+          const int s1 = (n + 1) % PL::NST;
+          if (__shfl_sync(0xffffffffu, mbar_test_wait(&full[s1], ((n + 1) / PL::NST) & 1), 0)) { front(n + 1); ++fronts; }
+        }
+        mbar_wait(b_ready, n & 1);
+        if (n == 0) { mbar_wait(&rfull[0], 0); mbar_wait(&rfull[1], 0); mbar_wait(&rfull[2], 0); }
+        else mbar_wait(&rfull[(n + 2) & 3], ((n + 2) >> 2) & 1);
+        TS(1, n, 2);
+        tc_fence_after();
+        const uint32_t accum0 = n > 0;
+        const uint32_t ds = base + PL::DS, dbd = base + PL::DBD, kk_ = st + PL::K, rr = base + PL::RRING;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)      // dQw += dS . K
+          umma_bf16_warp(tmem_base + TS_ACC0, umma_smem_desc(ds + k * 32, 16, 1024), umma_smem_desc(kk_ + k * 2048, 8192, 1024), id_kn, accum0 | (k > 0));
+#pragma unroll
+        for (int k = 0; k < 12; ++k)     // dQr += dBD0 . Rwin, window chunk k/4 lives in ring slot (n + k/4) mod 4
+          umma_bf16_warp(tmem_base + TS_ACC1, umma_smem_desc(dbd + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                         umma_smem_desc(rr + ((n + (k >> 2)) & 3) * SZ_KV + (k & 3) * 2048, 8192, 1024), id_kn, accum0 | (k > 0));
+        umma_commit_warp(b_done);
+        umma_commit_warp(&empty[s]);
+        umma_commit_warp(&rfree[n & 3]);          // chunk n was the first chunk of this window: no later tile reads it
+        TS(1, n, 3);
+        if (fronts == n + 1 && n + 1 < count) { front(n + 1); ++fronts; }
+      }
+      umma_commit_warp(acc_full);
+    }
+  } else if (warp == W_ST) {
+    if (lane == 0) {     // bf16 P and dS of every band tile -> global (consumed by the lite dK/dV and dR kernels)
+      for (int n = 0; n < count; ++n) {
+        mbar_wait(b_ready, n & 1);
+        tma_store_tile(&M.pst, sm + PL::P, (tile0 + n) * BQ);
+        tma_store_tile(&M.dst, sm + PL::DS, (tile0 + n) * BQ);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(b_done);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    const int r = 32 * (warp & 3) + lane, qd = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    const int c0 = 127 - r + KPT * qd;
+    uint32_t tile_off[KPT / 8], pair_off[KPT / 2], single_off[2];
+    {
+      auto dbd_off = [&](int c) -> uint32_t { return (uint32_t)((c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2); };
+#pragma unroll
+      for (int c = 0; c < KPT / 8; ++c) tile_off[c] = (uint32_t)(r * 128 + ((((KPT / 8) * qd + c) ^ (r & 7)) << 4));
+      const int ce = c0 + (c0 & 1);
+#pragma unroll
+      for (int k = 0; k < KPT / 2; ++k) pair_off[k] = dbd_off(ce + 2 * k);
+      single_off[0] = dbd_off(c0); single_off[1] = dbd_off(c0 + KPT - 1);
+    }
+    const int i = I * BQ + r;
+    float lse2 = 0.f, dlt = 0.f;
+    if (i < g.T) {
+      const int64_t o = ((int64_t)b * a.H + h) * g.T + i;
+      lse2 = a.lse[o] * 1.4426950408889634f; dlt = a.delta[o];
+    }
+    const float* mt = a.m_tiles + (int64_t)tile0 * BQ + r;
+    float m_next = mt[0];
+    for (int n = 0; n < count; ++n) {
+      const int s = n % PL::NST, tb = n & 1; const uint32_t sph = (n / PL::NST) & 1, tph = (n >> 1) & 1;
+      const float f = exp2f(m_next - lse2);
+      if (n + 1 < count) m_next = mt[(n + 1) * BQ];
+      if (tid == 0) TS(0, n, 0);
+      mbar_wait(&full[s], sph);
+      if (tid == 0) TS(0, n, 1);
+      const uint8_t* pt = sm + PL::RING + s * PL::STAGE + PL::PT;
+      uint32_t pw[KPT / 2];
+#pragma unroll
+      for (int c = 0; c < KPT / 8; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(pt + tile_off[c]);
+        pw[4 * c] = u.x; pw[4 * c + 1] = u.y; pw[4 * c + 2] = u.z; pw[4 * c + 3] = u.w;
+      }
+      mbar_wait(&f_full[tb], tph);
+      if (tid == 0) TS(0, n, 2);
+      tc_fence_after();
+      float p[KPT], ds[KPT];
+      tmem_ld_32x16(tmem_base + lane_base + TS_DP + 64 * tb + KPT * qd, ds);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_free[tb]);
+      if (tid == 0) TS(0, n, 3);
+#pragma unroll
+      for (int k = 0; k < KPT / 2; ++k) {
+        p[2 * k] = __uint_as_float(pw[k] << 16) * f;
+        p[2 * k + 1] = __uint_as_float(pw[k] & 0xFFFF0000u) * f;
+      }
+      const float fs = a.scale;
+#pragma unroll
+      for (int jj = 0; jj < KPT; ++jj) ds[jj] = p[jj] * (ds[jj] - dlt) * fs;
+      if (tid == 0) TS(0, n, 4);
+      if (n > 0) mbar_wait(b_done, (n - 1) & 1);      // back end + tile store of tile n-1 have read the work tiles
+      if (tid == 0) TS(0, n, 5);
+      {
+        uint8_t* dbd = sm + PL::DBD;
+        if ((c0 & 1) == 0) {
+#pragma unroll
+          for (int k = 0; k < KPT / 2; ++k) *reinterpret_cast<uint32_t*>(dbd + pair_off[k]) = pack2(ds[2 * k], ds[2 * k + 1]);
+        } else {
+          *reinterpret_cast<bf16*>(dbd + single_off[0]) = __float2bfloat16_rn(ds[0]);
+#pragma unroll
+          for (int k = 0; k < KPT / 2 - 1; ++k) *reinterpret_cast<uint32_t*>(dbd + pair_off[k]) = pack2(ds[2 * k + 1], ds[2 * k + 2]);
+          *reinterpret_cast<bf16*>(dbd + single_off[1]) = __float2bfloat16_rn(ds[KPT - 1]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < KPT / 8; ++c) {
+        uint4 o; o.x = pack2(p[c * 8], p[c * 8 + 1]); o.y = pack2(p[c * 8 + 2], p[c * 8 + 3]); o.z = pack2(p[c * 8 + 4], p[c * 8 + 5]); o.w = pack2(p[c * 8 + 6], p[c * 8 + 7]);
+        uint4 d; d.x = pack2(ds[c * 8], ds[c * 8 + 1]); d.y = pack2(ds[c * 8 + 2], ds[c * 8 + 3]); d.z = pack2(ds[c * 8 + 4], ds[c * 8 + 5]); d.w = pack2(ds[c * 8 + 6], ds[c * 8 + 7]);
+        *reinterpret_cast<uint4*>(sm + PL::P + tile_off[c]) = o;
+        *reinterpret_cast<uint4*>(sm + PL::DS + tile_off[c]) = d;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_ready);
+      if (tid == 0) TS(0, n, 6);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float v0[KPT], v1[KPT];
+    tmem_ld_32x16(tmem_base + lane_base + TS_ACC0 + KPT * qd, v0);
+    tmem_ld_32x16(tmem_base + lane_base + TS_ACC1 + KPT * qd, v1);
+    tmem_ld_wait();
+    if (i < g.T) {
+      uint4* dst = reinterpret_cast<uint4*>(a.dq + ((int64_t)b * g.T + i) * a.ldq + h * DH + KPT * qd);
+#pragma unroll
+      for (int c = 0; c < KPT / 8; ++c) {
+        uint4 o;
+        o.x = pack2(v0[c * 8] + v1[c * 8], v0[c * 8 + 1] + v1[c * 8 + 1]); o.y = pack2(v0[c * 8 + 2] + v1[c * 8 + 2], v0[c * 8 + 3] + v1[c * 8 + 3]);
+        o.z = pack2(v0[c * 8 + 4] + v1[c * 8 + 4], v0[c * 8 + 5] + v1[c * 8 + 5]); o.w = pack2(v0[c * 8 + 6] + v1[c * 8 + 6], v0[c * 8 + 7] + v1[c * 8 + 7]);
+        dst[c] = o;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < KPT; ++c) { v0[c] = 0.f; v1[c] = 0.f; }
+    }
+#pragma unroll
+    for (int c = 0; c < KPT; ++c) {
+      const float s0 = warp_sum(v0[c]), s1 = warp_sum(v1[c]);
+      if (lane == c) { atomicAdd(&a.drwb[h * DH + KPT * qd + c], s0); atomicAdd(&a.drrb[h * DH + KPT * qd + c], s1); }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc<TS_COLS>(tmem_base);
+}
+
 // qw = q + r_w_bias, qr = q + r_r_bias (bf16, [B*T, HD]); delta[b,h,i] = sum_c dO.O
 __global__ void relattn_bwd_prep_kernel(const bf16* __restrict__ q, int64_t ldq, const float* __restrict__ rwb, const float* __restrict__ rrb,
                                         const bf16* __restrict__ out, const bf16* __restrict__ dout, bf16* __restrict__ qw, bf16* __restrict__ qr,
@@ -725,7 +986,9 @@ int launch_mode(const Maps& M, const BwdArgs& a, dim3 grid, cudaStream_t st) {
 }
 }  // namespace
 
-static int bwd_nt_max(const TxlBand& band) {
+int bwd_nt_max_impl(const TxlBand& band);
+static int bwd_nt_max(const TxlBand& band) { return bwd_nt_max_impl(band); }
+int bwd_nt_max_impl(const TxlBand& band) {
   const BandGeom g = make_band(band);
   const int nI = (band.T + BQ - 1) / BQ;
   int mx = 0;
@@ -742,6 +1005,25 @@ static int64_t bwd_tile_rows(const TxlAttnDims* D) {
   const int nI = (D->band.T + BQ - 1) / BQ;
   return (int64_t)D->B * D->H * nI * bwd_nt_max(D->band) * BQ;
 }
+int64_t txl_relattn_tile_rows(const TxlAttnDims* D) { return bwd_tile_rows(D); }
+int txl_relattn_nt_max(const TxlBand* band) { return bwd_nt_max(*band); }
+static bool tc_disabled(const char* name) {
+  const char* e = getenv(name); const char* e2 = getenv("TXL_DISABLE_TC");
+  return (e && e[0] == '1') || (e2 && e2[0] == '1');
+}
+// bytes of forward state (bf16 P~ tiles + fp32 row maxima) the tensor-core backward can reuse; 0 when that path does not apply
+int64_t txl_relattn_saved_bytes_tc(const TxlAttnDims* D) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("TXL_ATTN_BWD_RECOMPUTE"); off = (tc_disabled("TXL_DISABLE_TC_ATTN") || tc_disabled("TXL_DISABLE_TC_ATTN_BWD") || (e && e[0] == '1')) ? 1 : 0; }
+  if (off || D->dtype != TXL_BF16) return 0;
+  const int T = D->band.T, mlen = D->band.mlen;
+  if (D->dh != DH || (T % BKV) || (mlen % BKV) || T + mlen < WIN || mlen <= 0) return 0;
+  if (!(D->band.same_length && mlen == D->band.mem_len)) return 0;
+  if ((D->ldq % 8) || (D->ldkv_cur % 8) || (D->ldkv_mem % 8)) return 0;
+  const int64_t trows = bwd_tile_rows(D);
+  if (trows >= (1ll << 31)) return 0;
+  return trows * BKV * 2 + trows * 4;
+}
 int64_t txl_relattn_bwd_tc_workspace(const TxlAttnDims* D) {
   const int64_t n = (int64_t)D->B * D->band.T * D->H * D->dh;
   const int64_t base = 2 * n * 2 + (int64_t)D->B * D->H * D->band.T * 4 + 1024;
@@ -750,7 +1032,7 @@ int64_t txl_relattn_bwd_tc_workspace(const TxlAttnDims* D) {
 
 int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur, const void* r, const float* rwb,
                        const float* rrb, const void* out, const float* lse, const void* dout, void* dq, void* dk_mem, void* dv_mem, void* dk_cur,
-                       void* dv_cur, float* dr, float* drwb, float* drrb, void* ws, const TxlAttnDims* D, void* stream, int* handled) {
+                       void* dv_cur, float* dr, float* drwb, float* drrb, void* ws, const void* saved, const TxlAttnDims* D, void* stream, int* handled) {
   *handled = 0;
   static int disabled = -1;
   if (disabled < 0) { const char* e = getenv("TXL_DISABLE_TC_ATTN_BWD"); const char* e2 = getenv("TXL_DISABLE_TC"); disabled = ((e && e[0] == '1') || (e2 && e2[0] == '1')) ? 1 : 0; }
@@ -812,7 +1094,33 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
     if ((rc = txl_make_tmap_2d(&M.pst, pstore, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
     if ((rc = txl_make_tmap_2d(&M.dst, dstore, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
   } else { M.pst = M.qw; M.dst = M.qw; }
-  if ((rc = launch_mode<MODE_DQ>(M, a, dim3(nI, D->H, D->B), st))) return rc;
+  a.m_tiles = nullptr; M.psv = M.qw; M.r64 = M.r;
+  { const char* e = getenv("TXL_ABL"); a.abl = e ? atoi(e) : 0; }
+  if (saved && a.store_tiles && txl_relattn_saved_bytes_tc(D) > 0 && al16(saved)) {
+    a.m_tiles = reinterpret_cast<const float*>(reinterpret_cast<const bf16*>(saved) + trows * BKV);
+    if ((rc = txl_make_tmap_2d(&M.psv, saved, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
+    if ((rc = txl_make_tmap_2d(&M.r64, r, (uint64_t)klen, (uint64_t)HD, (uint64_t)HD, BKV, DH))) return rc;
+    static bool attr_s = false;
+    if (!attr_s) { TXL_CUDA(cudaFuncSetAttribute(relattn_bwd_dq_saved_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PlanS::SMEM)); attr_s = true; }
+    relattn_bwd_dq_saved_kernel<<<dim3(nI, D->H, D->B), NTHREADS, PlanS::SMEM, st>>>(M, a);
+    TXL_LAUNCH_CHECK();
+    if (a.abl & 256) {
+      static int printed = 0;
+      if (!printed++) {
+        cudaDeviceSynchronize();
+        static long long ts[3][32][8];
+        cudaMemcpyFromSymbol(ts, g_ts, sizeof(ts));
+        const long long t0 = ts[2][0][0];
+        for (int n = 0; n < 19; ++n) {
+          fprintf(stderr, "tile %2d  prod: empty %6lld | mma: full %6lld tfree %6lld bready %6lld issued %6lld | smx: top %6lld full %6lld ffull %6lld ld %6lld math %6lld bdone %6lld arrive %6lld\n", n,
+                  ts[2][n][0] - t0, ts[1][n][0] - t0, ts[1][n][1] - t0, ts[1][n][2] - t0, ts[1][n][3] - t0, ts[0][n][0] - t0, ts[0][n][1] - t0, ts[0][n][2] - t0,
+                  ts[0][n][3] - t0, ts[0][n][4] - t0, ts[0][n][5] - t0, ts[0][n][6] - t0);
+        }
+      }
+    }
+  } else {
+    if ((rc = launch_mode<MODE_DQ>(M, a, dim3(nI, D->H, D->B), st))) return rc;
+  }
   if (dbg & 16) { *handled = 1; return TXL_OK; }
   if (a.store_tiles) {
     static bool attr_set = false;

@@ -104,14 +104,15 @@ def forward(cfg, W: List[LayerW], E, out_bias, ids, mems_bm, labels_shift, *, dr
         r = ops.gemm(pos, w.r, transB=True)                                    # (P, d)
         k_mem = kvm[:, :d] if kvm is not None else None
         v_mem = kvm[:, d:] if kvm is not None else None
-        vec, lse = ops.relattn_fwd(qkv[:, :d], k_mem, v_mem, qkv[:, d:2 * d], qkv[:, 2 * d:], r, w.rwb, w.rrb, B, T, H, dh, g.band)
+        att = ops.relattn_fwd(qkv[:, :d], k_mem, v_mem, qkv[:, d:2 * d], qkv[:, 2 * d:], r, w.rwb, w.rrb, B, T, H, dh, g.band, save=bool(save))
+        vec, lse, att_saved = att if save else (att[0], att[1], None)
         ao = ops.gemm(vec, w.o, transB=True)
         y1, z1, mean1, rstd1 = ops.add_ln_fwd(x, ao, w.ln1_w, w.ln1_b, cfg.layer_norm_epsilon, drop_p, seed, site + S_ATTN_OUT, save)
         h = ops.gemm(y1, w.w1, transB=True, bias=w.b1, relu=True, drop_p=drop_p, seed=seed, site=site + S_FF_INNER)
         f = ops.gemm(h, w.w2, transB=True, bias=w.b2)
         y2, z2, mean2, rstd2 = ops.add_ln_fwd(y1, f, w.ln2_w, w.ln2_b, cfg.layer_norm_epsilon, drop_p, seed, site + S_FF_OUT, save)
         if save:
-            sv.layers.append(dict(x=x, qkv=qkv, kvm=kvm if mems_real else None, kvm_fwd=kvm, r=r, vec=vec, lse=lse, z1=z1, mean1=mean1,
+            sv.layers.append(dict(x=x, qkv=qkv, kvm=kvm if mems_real else None, kvm_fwd=kvm, r=r, vec=vec, lse=lse, att_saved=att_saved, z1=z1, mean1=mean1,
                                   rstd1=rstd1, y1=y1, h=h, z2=z2, mean2=mean2, rstd2=rstd2))
         x = y2
     core = ops.dropout(x, drop_p, seed, SITE_FINAL) if drop_p > 0 else x
@@ -172,7 +173,7 @@ def backward(cfg, W: List[LayerW], G: List[LayerW], E, gE, g_out_bias, sv: Saved
         v_mem = kvm[:, d:] if kvm is not None else None
         ops.relattn_bwd(qkv[:, :d], k_mem, v_mem, qkv[:, d:2 * d], qkv[:, 2 * d:], s['r'], w.rwb, w.rrb, s['vec'], s['lse'], dvec,
                         dqkv[:, :d], dkvm[:, :d] if dkvm is not None else None, dkvm[:, d:] if dkvm is not None else None,
-                        dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, gw.rwb, gw.rrb, B, T, H, dh, g.band)
+                        dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, gw.rwb, gw.rrb, B, T, H, dh, g.band, saved=s['att_saved'])
         # r_net:  r = pos Wr^T
         dr_c = dr if dt == torch.float32 else ops.cast_f32_to_bf16(dr, torch.empty_like(dr, dtype=dt))
         ops.gemm(dr_c, sv.pos, transA=True, out=gw.r, accumulate=True)

@@ -132,18 +132,23 @@ def _attn_dims(q, k_mem, k_cur, B, T, H, dh, band):
     return TxlAttnDims(B, H, dh, band, q.stride(0), k_mem.stride(0) if k_mem is not None else 0, k_cur.stride(0), dtype_code(q.dtype))
 
 
-def relattn_fwd(q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb, B, T, H, dh, band: TxlBand):
-    """q/k_cur/v_cur: [B*T, >=H*dh] views; k_mem/v_mem: [B*mlen, >=H*dh] views or None; r: [P, H*dh]."""
+def relattn_fwd(q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb, B, T, H, dh, band: TxlBand, save=False):
+    """q/k_cur/v_cur: [B*T, >=H*dh] views; k_mem/v_mem: [B*mlen, >=H*dh] views or None; r: [P, H*dh].
+    save=True also returns the forward state `relattn_bwd(saved=...)` reuses (None when no kernel would use it)."""
     out = torch.empty(B * T, H * dh, dtype=q.dtype, device=q.device)
     lse = torch.empty(B, H, T, dtype=torch.float32, device=q.device)
     dims = _attn_dims(q, k_mem, k_cur, B, T, H, dh, band)
+    saved = None
+    if save:
+        nbytes = _lib().txl_relattn_saved_bytes(C.byref(dims))
+        saved = torch.empty(nbytes, dtype=torch.uint8, device=q.device) if nbytes > 0 else None
     check(_lib().txl_relattn_fwd(ptr(q), ptr(k_mem), ptr(v_mem), ptr(k_cur), ptr(v_cur), ptr(r), ptr(rwb), ptr(rrb), ptr(out), ptr(lse),
-                                 C.byref(dims), stream_ptr()), 'relattn_fwd')
-    return out, lse
+                                 ptr(saved), C.byref(dims), stream_ptr()), 'relattn_fwd')
+    return (out, lse, saved) if save else (out, lse)
 
 
 def relattn_bwd(q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb, out, lse, dout, dq, dk_mem, dv_mem, dk_cur, dv_cur, dr, drwb, drrb,
-                B, T, H, dh, band: TxlBand):
+                B, T, H, dh, band: TxlBand, saved=None):
     dims = _attn_dims(q, k_mem, k_cur, B, T, H, dh, band)
     assert dq.stride(0) == q.stride(0) and dk_cur.stride(0) == k_cur.stride(0)
     assert dk_mem is None or dk_mem.stride(0) == k_mem.stride(0)
@@ -151,7 +156,7 @@ def relattn_bwd(q, k_mem, v_mem, k_cur, v_cur, r, rwb, rrb, out, lse, dout, dq, 
     ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
     check(_lib().txl_relattn_bwd(ptr(q), ptr(k_mem), ptr(v_mem), ptr(k_cur), ptr(v_cur), ptr(r), ptr(rwb), ptr(rrb), ptr(out), ptr(lse),
                                  ptr(dout), ptr(dq), ptr(dk_mem), ptr(dv_mem), ptr(dk_cur), ptr(dv_cur), ptr(dr), ptr(drwb), ptr(drrb),
-                                 ptr(ws), C.byref(dims), stream_ptr()), 'relattn_bwd')
+                                 ptr(ws), ptr(saved), C.byref(dims), stream_ptr()), 'relattn_bwd')
 
 
 # ----------------------------------------------------------------------------- LM head

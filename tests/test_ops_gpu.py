@@ -170,7 +170,10 @@ def _ref_attention(q, k, v, r, rwb, rrb, T, M, ML, C, same):
                                                    (2, 2, 64, 128, 128, 128, 1024, 1), (1, 1, 64, 256, 256, 256, 64, 1), (2, 1, 64, 192, 64, 64, 1024, 1),
                                                    (1, 2, 64, 64, 192, 192, 1024, 1), (1, 2, 64, 128, 128, 128, 1024, 0), (1, 1, 64, 256, 0, 256, 1024, 1),
                                                    (1, 2, 64, 320, 128, 128, 16, 1), (1, 1, 64, 512, 512, 512, 1024, 1)])
-def test_relattn_fwd_bwd(ops, mode, B, H, dh, T, M, ML, C, same):
+@pytest.mark.parametrize('save', [False, True])
+def test_relattn_fwd_bwd(ops, mode, B, H, dh, T, M, ML, C, same, save):
+    """save=True: the forward call also leaves its soft-max numerators for the backward (tensor-core shapes with a dense band);
+    where no kernel uses them the wrapper returns None and the call is the recompute path again."""
     torch.manual_seed(5)
     dt = DT[mode]
     d = H * dh
@@ -183,7 +186,13 @@ def test_relattn_fwd_bwd(ops, mode, B, H, dh, T, M, ML, C, same):
     band = ops.make_band(T, M, ML, C, same)
     km = kvm[:, :d] if M > 0 else None
     vm = kvm[:, d:] if M > 0 else None
-    out, lse = ops.relattn_fwd(qkv[:, :d], km, vm, qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, B, T, H, dh, band)
+    out, lse, saved = ops.relattn_fwd(qkv[:, :d], km, vm, qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, B, T, H, dh, band, save=True)
+    if save and saved is None:
+        pytest.skip('no saved forward state for this shape / mode: identical to save=False')
+    if not save:
+        saved = None
+    elif mode == 'bf16' and dh == 64 and same and M == ML and M % 64 == 0 and T % 64 == 0 and M > 0 and T + M >= 192:
+        assert saved is not None
     # reference on CPU fp32 from the same (rounded) inputs
     f = lambda t: t.float().cpu()
     q = f(qkv[:, :d]).view(B, T, H, dh).requires_grad_()
@@ -209,7 +218,7 @@ def test_relattn_fwd_bwd(ops, mode, B, H, dh, T, M, ML, C, same):
     drwb, drrb = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
     ops.relattn_bwd(qkv[:, :d], km, vm, qkv[:, d:2 * d], qkv[:, 2 * d:], r, rwb, rrb, out, lse, dout, dqkv[:, :d],
                     dkvm[:, :d] if M > 0 else None, dkvm[:, d:] if M > 0 else None, dqkv[:, d:2 * d], dqkv[:, 2 * d:], dr, drwb, drrb,
-                    B, T, H, dh, band)
+                    B, T, H, dh, band, saved=saved)
     btol = dict(rtol=1e-3, atol=1e-4) if mode == 'fp32' else dict(rtol=5e-2, atol=5e-2)
     torch.testing.assert_close(f(dqkv[:, :d]).view(B, T, H, dh), q.grad, **btol)
     torch.testing.assert_close(f(dqkv[:, d:2 * d]).view(B, T, H, dh), kc.grad, **btol)
@@ -301,18 +310,21 @@ def test_relattn_tensor_core_vs_exact_fp32_kernels_full_band(ops):
     dout = torch.randn(B * T, d, device='cuda').bfloat16()
     band = ops.make_band(T, M, M, 1024, 1)
 
-    def run(dt):
+    def run(dt, save=False):
         q_, k_, r_, do_ = qkv.to(dt), kvm.to(dt), r.to(dt), dout.to(dt)
-        out, lse = ops.relattn_fwd(q_[:, :d], k_[:, :d], k_[:, d:], q_[:, d:2 * d], q_[:, 2 * d:], r_, rwb, rrb, B, T, H, dh, band)
+        out, lse, saved = ops.relattn_fwd(q_[:, :d], k_[:, :d], k_[:, d:], q_[:, d:2 * d], q_[:, 2 * d:], r_, rwb, rrb, B, T, H, dh, band, save=True)
+        assert (saved is not None) == (dt == torch.bfloat16)
+        saved = saved if save else None
         dq_, dk_ = torch.empty_like(q_), torch.empty_like(k_)
         dr, dw, db = torch.zeros(T + M, d, device='cuda'), torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
         ops.relattn_bwd(q_[:, :d], k_[:, :d], k_[:, d:], q_[:, d:2 * d], q_[:, 2 * d:], r_, rwb, rrb, out, lse, do_, dq_[:, :d], dk_[:, :d], dk_[:, d:],
-                        dq_[:, d:2 * d], dq_[:, 2 * d:], dr, dw, db, B, T, H, dh, band)
+                        dq_[:, d:2 * d], dq_[:, 2 * d:], dr, dw, db, B, T, H, dh, band, saved=saved)
         return [t.float() for t in (out, lse, dq_, dk_, dr, dw, db)]
-    tc, ex = run(torch.bfloat16), run(torch.float32)
+    tc, tcs, ex = run(torch.bfloat16), run(torch.bfloat16, save=True), run(torch.float32)
     names = ['out', 'lse', 'dqkv', 'dkv_mem', 'dr', 'drwb', 'drrb']
-    for n, a, b in zip(names, tc, ex):
-        err = ((a - b).norm() / b.norm()).item()
-        assert err < (2e-3 if n == 'lse' else 2e-2), (n, err)
+    for which, got in (('recompute', tc), ('saved', tcs)):
+        for n, a, b in zip(names, got, ex):
+            err = ((a - b).norm() / b.norm()).item()
+            assert err < (2e-3 if n == 'lse' else 2e-2), (which, n, err)
     # every probability row sums to one: exp(score - lse) over the live band == 1 is implied by lse agreement; check O is a convex combination
     assert tc[0].abs().max() <= kvm[:, d:].float().abs().max() + 1e-2
