@@ -73,6 +73,8 @@ int txl_posemb_table(void* out, int klen, int clamp_len, int d, int dtype, float
  *   transA=0: A is [M,K] (lda>=K); transA=1: A is stored [K,M] (lda>=M)
  *   transB=0: B is [K,N] (ldb>=N); transB=1: B is stored [N,K] (ldb>=K)   (nn.Linear weight => transB=1)
  * epilogue: v = acc; if bias: v += bias[n]; if (flags&RELU) v = max(v,0); if (flags&MASK_POS) v *= (aux[m,n]>0);
+ *           if (flags&MASK_SCALE) v *= 1/(1-drop_p)   (aux is a post-dropout activation: its zeros already are the dropout mask,
+ *                                                       so the backward of relu+dropout needs no second hash pass);
  *           if (flags&DROPOUT) v = inverted-dropout(v); if (flags&ACCUM) v += C[m,n];  C = (dtype_c) v
  * colsum (optional, fp32[N]): colsum[n] += sum_m v (before ACCUM) — bias gradients.
  * bf16 inputs with all of M,N,K and leading dims "nice" run on tcgen05 tensor cores; everything else on a
@@ -82,6 +84,7 @@ int txl_posemb_table(void* out, int klen, int clamp_len, int d, int dtype, float
 #define TXL_EPI_MASK_POS 4
 #define TXL_EPI_DROPOUT 8
 #define TXL_EPI_BIAS_ROW 16   /* bias is indexed by the output ROW m (used with TRANSPOSE: y^T = W x^T + b) */
+#define TXL_EPI_MASK_SCALE 64 /* with MASK_POS: also scale by 1/(1-drop_p) (aux = post-dropout activation) */
 #define TXL_EPI_TRANSPOSE 32  /* store C transposed: C[n*ldc + m]  (decode: features are the GEMM's M so 128-row MMA tiles stay full) */
 typedef struct {
   const float* bias;     /* [N] or NULL */

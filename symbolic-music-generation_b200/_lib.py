@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libtxl_b200.so')
 
 F32, BF16 = 0, 1
-EPI_RELU, EPI_ACCUM, EPI_MASK_POS, EPI_DROPOUT, EPI_BIAS_ROW, EPI_TRANSPOSE = 1, 2, 4, 8, 16, 32
+EPI_RELU, EPI_ACCUM, EPI_MASK_POS, EPI_DROPOUT, EPI_BIAS_ROW, EPI_TRANSPOSE, EPI_MASK_SCALE = 1, 2, 4, 8, 16, 32, 64
 
 
 class TxlError(RuntimeError):

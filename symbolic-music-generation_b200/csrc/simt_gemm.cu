@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
       if (epi.bias) v += (epi.flags & TXL_EPI_BIAS_ROW) ? epi.bias[gm] : epi.bias[gn];
       if (epi.flags & TXL_EPI_RELU) v = fmaxf(v, 0.f);
       if (epi.flags & TXL_EPI_MASK_POS) v = to_f32(((const TC*)epi.aux)[gm * ldc + gn]) > 0.f ? v : 0.f;
+      if (epi.flags & TXL_EPI_MASK_SCALE) v *= inv_keep;
       if (epi.flags & TXL_EPI_DROPOUT) v *= dropout_scale(epi.seed, epi.site, (uint64_t)(gm * N + gn), epi.drop_p, inv_keep);
       cs[j] += v;
       const int64_t ci = (epi.flags & TXL_EPI_TRANSPOSE) ? gn * ldc + gm : gm * ldc + gn;
@@ -101,6 +102,7 @@ extern "C" int txl_gemm(const void* A, const void* B, void* C, int64_t M, int64_
   if (epi_in) epi = *epi_in; else { epi.bias = nullptr; epi.aux = nullptr; epi.colsum = nullptr; epi.drop_p = 0.f; epi.seed = 0; epi.site = 0; epi.flags = 0; }
   if ((epi.flags & TXL_EPI_DROPOUT) && !(epi.drop_p > 0.f)) epi.flags &= ~TXL_EPI_DROPOUT;
   TXL_CHECK_ARG(!(epi.flags & TXL_EPI_MASK_POS) || epi.aux, "gemm: MASK_POS needs aux");
+  TXL_CHECK_ARG(!(epi.flags & TXL_EPI_MASK_SCALE) || ((epi.flags & TXL_EPI_MASK_POS) && epi.drop_p >= 0.f && epi.drop_p < 1.f), "gemm: MASK_SCALE needs MASK_POS and 0 <= drop_p < 1");
   if (dtype_ab == TXL_BF16) {
     int handled = 0;
     int rc = txl_gemm_tc(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, dtype_c, &epi, stream, &handled);
@@ -108,7 +110,7 @@ extern "C" int txl_gemm(const void* A, const void* B, void* C, int64_t M, int64_
     if (handled) return TXL_OK;
   }
   dim3 grid((unsigned)cdiv64(N, BN), (unsigned)cdiv64(M, BM));
-  float ik = (epi.flags & TXL_EPI_DROPOUT) ? 1.f / (1.f - epi.drop_p) : 1.f;
+  float ik = (epi.flags & (TXL_EPI_DROPOUT | TXL_EPI_MASK_SCALE)) ? 1.f / (1.f - epi.drop_p) : 1.f;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype_ab == TXL_F32 && dtype_c == TXL_F32)
     gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>((const float*)A, (const float*)B, (float*)C, M, N, K, lda, ldb, ldc, transA, transB, epi, ik);

@@ -270,6 +270,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] += brow;
             }
+            if (e.flags & TXL_EPI_MASK_SCALE) {
+              // aux is a post-dropout activation: aux > 0 already is (ReLU live) AND (kept); only the 1/(1-p) scale is left
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= p.inv_keep;
+            }
             if (e.flags & TXL_EPI_DROPOUT) {
               const uint64_t base_idx = (uint64_t)row * (uint64_t)p.N + (uint64_t)col0;
               if (pair_hash) {
@@ -409,7 +414,7 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.C = C; p.dtype_c = dtype_c; p.epi = *epi;
-  p.inv_keep = (epi->flags & TXL_EPI_DROPOUT) ? 1.f / (1.f - epi->drop_p) : 1.f;
+  p.inv_keep = (epi->flags & (TXL_EPI_DROPOUT | TXL_EPI_MASK_SCALE)) ? 1.f / (1.f - epi->drop_p) : 1.f;
   p.a_mn = transA ? 1 : 0;   // transA: A stored [K, M] => M contiguous
   p.b_mn = transB ? 0 : 1;   // transB: B stored [N, K] => K contiguous
   const int BN = N >= 256 ? 256 : 128;

@@ -156,7 +156,7 @@ def backward(cfg, W: List[LayerW], G: List[LayerW], E, gE, g_out_bias, sv: Saved
         dy1, df = ops.add_ln_bwd(dx, s['z2'], w.ln2_w, s['mean2'], s['rstd2'], gw.ln2_w, gw.ln2_b, drop_p=p, seed=seed, site=site + S_FF_OUT, dy2=dx2)
         ops.colsum(df, gw.b2)
         ops.gemm(df, s['h'], transA=True, out=gw.w2, accumulate=True)                                 # dW2 += df^T h
-        dh_ = ops.gemm(df, w.w2, mask_pos_aux=s['h'], colsum=gw.b1, drop_p=p, seed=seed, site=site + S_FF_INNER)   # (N, di)
+        dh_ = ops.gemm(df, w.w2, mask_pos_aux=s['h'], colsum=gw.b1, drop_p=p, seed=seed, site=site + S_FF_INNER, aux_is_dropped=True)   # (N, di)
         ops.gemm(dh_, s['y1'], transA=True, out=gw.w1, accumulate=True)                               # dW1 += dh^T y1
         dff = ops.gemm(dh_, w.w1)                                                                     # dh W1  (N, d)
         del dh_, df

@@ -74,6 +74,9 @@ def test_tc_gemm_epilogues(ops):
     aux = torch.randn(M, N, device='cuda').to(torch.bfloat16)
     out = ops.gemm(A, B, transB=True, mask_pos_aux=aux)
     torch.testing.assert_close(out.float(), ref0 * (aux.float() > 0), rtol=1e-2, atol=1e-2)
+    # backward of relu+dropout from the post-dropout activation: its zeros are the mask, only the 1/(1-p) scale is applied
+    out = ops.gemm(A, B, transB=True, mask_pos_aux=aux, drop_p=0.25, seed=5, site=3, aux_is_dropped=True)
+    torch.testing.assert_close(out.float(), ref0 * (aux.float() > 0) / 0.75, rtol=1e-2, atol=2e-2)
     d1 = ops.gemm(A, B, transB=True, drop_p=0.25, seed=5, site=3, out_dtype=torch.float32)
     os.environ['TXL_DISABLE_TC'] = '0'
     kept = d1 != 0
