@@ -65,12 +65,17 @@ struct GemmParams {
   int tma_store;
 };
 
-template <int BN, int STAGES>
+// CG = 2: a CTA pair (cluster of two CTAs on one TPC) computes one 256 x BN tile with tcgen05.mma.cta_group::2 — each CTA stages its
+// own 128 rows of A and HALF of the B tile, so every byte pulled from L2 feeds twice the MMA work; the leader CTA (rank 0) issues.
+template <int BN, int STAGES, int CG = 1>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CSTAGE_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = CSTAGE_OFF + 2 * STAGE_C_BYTES;
+  // output staging buffers per epilogue group: a TMA store takes ~1400-2400 cycles to finish READING its shared-memory source, so with
+  // one buffer every 64-column block waits out a full store; the pair kernel has the room for two
+  static constexpr int NCST = CG == 2 ? 2 : 1;
+  static constexpr int BAR_OFF = CSTAGE_OFF + 2 * NCST * STAGE_C_BYTES;
   static constexpr int SMEM = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -96,13 +101,57 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int BN, int STAGES, typename TC>
+// ---- cta_group::2 primitives (PTX forms as in cute/arch/copy_sm100_tma.hpp, cutlass/arch/barrier.h)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank)); return r;
+}
+// tile load into THIS CTA's shared memory; the transaction bytes are credited to `bar_cluster_addr`, a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair once all prior MMAs of this thread are done
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot_in_smem) {  // the same warp of BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+template <int BN, int STAGES, typename TC, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using C_ = Cfg<BN, STAGES>;
+  using C_ = Cfg<BN, STAGES, CG>;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;      // 0 = leader of the pair (issues the MMAs)
+  const int unit0 = (int)blockIdx.x / CG, unit_step = (int)gridDim.x / CG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -115,14 +164,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8 * CG); }   // leader's tempty: epilogue warps of both CTAs
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) tmem_alloc<C_::TMEM_COLS>(tmem_slot);
+  if (warp == 1) { if (CG == 2) tmem_alloc_2sm<C_::TMEM_COLS>(tmem_slot); else tmem_alloc<C_::TMEM_COLS>(tmem_slot); }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();      // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int total_units = p.tiles_m * p.tiles_n * p.ksplits;
@@ -131,38 +181,56 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // ================= TMA producer
       int s = 0; uint32_t ph = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
         const int tm = unit % p.tiles_m, tn = (unit / p.tiles_m) % p.tiles_n, ks = unit / (p.tiles_m * p.tiles_n);
         const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.nkb);
-        const int m0 = tm * BM, n0 = tn * BN;
+        const int m0 = tm * (BM * CG) + (int)cta_rank * BM, n0 = tn * BN + (int)cta_rank * (BN / CG) * (CG - 1);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* a_s = sm + s * C_::STAGE_BYTES;
           uint8_t* b_s = a_s + A_BYTES;
-          mbar_expect_tx(&full[s], C_::STAGE_BYTES);
           const int k0 = kb * BK;
-          if (!p.a_mn) {
-            tma_load_2d(a_s, &tmA, &full[s], k0, m0);
-          } else {
+          if (CG == 1) {
+            mbar_expect_tx(&full[s], C_::STAGE_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d(a_s, &tmA, &full[s], k0, m0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) tma_load_2d(a_s + i * 8192, &tmA, &full[s], m0 + 64 * i, k0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(b_s, &tmB, &full[s], k0, n0);
-          } else {
+              for (int i = 0; i < BM / 64; ++i) tma_load_2d(a_s + i * 8192, &tmA, &full[s], m0 + 64 * i, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(b_s, &tmB, &full[s], k0, n0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(b_s + i * 8192, &tmB, &full[s], n0 + 64 * i, k0);
+              for (int i = 0; i < BN / 64; ++i) tma_load_2d(b_s + i * 8192, &tmB, &full[s], n0 + 64 * i, k0);
+            }
+          } else {
+            // both CTAs load into their own shared memory; all bytes are credited to the LEADER's full barrier, which expects both halves
+            const uint32_t lead_full = mapa_rank(smem_u32(&full[s]), 0);
+            if (cta_rank == 0) mbar_expect_tx(&full[s], 2 * C_::STAGE_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d_2sm(a_s, &tmA, lead_full, k0, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i) tma_load_2d_2sm(a_s + i * 8192, &tmA, lead_full, m0 + 64 * i, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d_2sm(b_s, &tmB, lead_full, k0, n0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / CG / 64; ++i) tma_load_2d_2sm(b_s + i * 8192, &tmB, lead_full, n0 + 64 * i, k0);
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer
-      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    if (lane == 0 && cta_rank == 0) {
+      // ================= MMA issuer (the pair's leader for CG = 2: M = 256 rows, 128 per CTA)
+      const uint32_t idesc = umma_idesc_bf16(BM * CG, BN, p.a_mn, p.b_mn);
       int s = 0; uint32_t ph = 0; int it = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+      for (int unit = unit0; unit < total_units; unit += unit_step, ++it) {
         const int ks = unit / (p.tiles_m * p.tiles_n);
         const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.nkb);
         const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
@@ -178,12 +246,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t ad = p.a_mn ? umma_smem_desc(a_addr + kk * 2048, 8192, 1024) : umma_smem_desc(a_addr + kk * 32, 16, 1024);
             const uint64_t bd = p.b_mn ? umma_smem_desc(b_addr + kk * 2048, 8192, 1024) : umma_smem_desc(b_addr + kk * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            if (CG == 2) umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[s]);
+          if (CG == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        if (CG == 2) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);
       }
     }
   } else {
@@ -193,15 +262,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool leader = (warp - 2) % 4 == 0 && lane == 0;      // issues this group's TMA stores
     const TxlEpilogue& e = p.epi;
     TC* __restrict__ C = reinterpret_cast<TC*>(p.C);
-    uint8_t* cst = sm + C_::CSTAGE_OFF + grp * STAGE_C_BYTES;
+    uint8_t* const cst0 = sm + C_::CSTAGE_OFF + grp * C_::NCST * STAGE_C_BYTES;
+    int nblk = 0;                                 // 64-column blocks this group has staged so far (selects the staging buffer)
     const uint32_t dkey = dropout_key(e.seed, e.site);
     const uint32_t dthr = dropout_threshold(e.drop_p);
     const bool pair_hash = (p.N & 1) == 0;
     int it = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+    for (int unit = unit0; unit < total_units; unit += unit_step, ++it) {
       const int tm = unit % p.tiles_m, tn = (unit / p.tiles_m) % p.tiles_n;
       const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-      const int64_t row = (int64_t)tm * BM + r_in_tile;
+      const int64_t row0 = (int64_t)tm * (BM * CG) + (int64_t)cta_rank * BM;      // first output row of this CTA's half of the tile
+      const int64_t row = row0 + r_in_tile;
       const bool row_ok = row < p.M;
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
@@ -210,9 +281,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int bi = grp; bi < NBLK; bi += 2) {
         const int64_t blk_col0 = (int64_t)tn * BN + bi * 64;
         if (p.tma_store) {
-          if (leader) tma_store_wait_read();            // previous store out of this staging buffer has been read
+          if (leader) tma_store_wait_read<C_::NCST - 1>();   // the store that last used this staging buffer has read it
           named_bar_sync(1 + grp, 128);
         }
+        uint8_t* const cst = cst0 + (nblk % C_::NCST) * STAGE_C_BYTES;
+        ++nblk;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
           const int c = bi * 2 + half;
@@ -222,7 +295,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (bi + 2 >= NBLK && half == 1) {   // this warp's last read of the accumulator: hand TMEM back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[acc]), 0)); else mbar_arrive(&tempty[acc]); }
           }
           const int64_t col0 = blk_col0 + half * 32;
           const bool any_col = col0 < p.N;
@@ -371,7 +444,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async_smem();
           named_bar_sync(1 + grp, 128);
           if (leader && blk_col0 < p.N) {               // TMA clips rows >= M and columns >= N
-            tma_store_2d(&tmC, cst, (int)blk_col0, tm * BM);
+            tma_store_2d(&tmC, cst, (int)blk_col0, (int)row0);
             tma_store_commit();
           }
         }
@@ -381,18 +454,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<C_::TMEM_COLS>(tmem_base);
+  if (CG == 2) cluster_sync_all();      // neither CTA may leave while its peer can still read its operands or signal its barriers
+  if (warp == 1) { if (CG == 2) tmem_dealloc_2sm<C_::TMEM_COLS>(tmem_base); else tmem_dealloc<C_::TMEM_COLS>(tmem_base); }
 }
 
-template <int BN, int STAGES, typename TC>
+template <int BN, int STAGES, typename TC, int CG = 1>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int grid, cudaStream_t st) {
-  using C_ = Cfg<BN, STAGES>;
+  using C_ = Cfg<BN, STAGES, CG>;
+  static_assert(C_::SMEM <= 232448, "GEMM shared-memory plan exceeds 227 KB");
   static bool attr_set = false;
   if (!attr_set) {
-    TXL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
+    TXL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, TC, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
     attr_set = true;
   }
-  tc_gemm_kernel<BN, STAGES, TC><<<grid, THREADS, C_::SMEM, st>>>(tmA, tmB, tmC, p);
+  if (CG == 1) {
+    tc_gemm_kernel<BN, STAGES, TC, CG><<<grid, THREADS, C_::SMEM, st>>>(tmA, tmB, tmC, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C_::SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    ++g_txl_launches;
+    TXL_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, STAGES, TC, CG>, tmA, tmB, tmC, p));
+    return TXL_OK;
+  }
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }
@@ -418,14 +505,20 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
   p.a_mn = transA ? 1 : 0;   // transA: A stored [K, M] => M contiguous
   p.b_mn = transB ? 0 : 1;   // transB: B stored [N, K] => K contiguous
   const int BN = N >= 256 ? 256 : 128;
-  p.tiles_m = (int)cdiv64(M, BM); p.tiles_n = (int)cdiv64(N, BN);
+  // CTA pairs (cta_group::2, 256 x 256 tiles) for the big training shapes; TXL_GEMM_2SM=0 switches them off
+  static int use_2sm = -1;
+  if (use_2sm < 0) { const char* e = getenv("TXL_GEMM_2SM"); use_2sm = (e && e[0] == '0') ? 0 : 1; }
+  // (short-K shapes are bound by the epilogue, not the operand stream: measured at K = 512 the pair kernel only ties the single-CTA one)
+  const int CG = (use_2sm && BN == 256 && M >= 512 && K >= 1024 && !(epi->flags & TXL_EPI_TRANSPOSE)) ? 2 : 1;
+  p.tiles_m = (int)cdiv64(M, BM * CG); p.tiles_n = (int)cdiv64(N, BN);
   p.nkb = (int)cdiv64(K, BK);
   p.ksplits = 1;
   const int sms = txl_num_sms();
   const bool pure_accum = dtype_c == TXL_F32 && epi->flags == TXL_EPI_ACCUM && !epi->bias && !epi->colsum;
   const int tiles = p.tiles_m * p.tiles_n;
-  if (pure_accum && tiles < sms && p.nkb >= 8) {
-    int want = sms / tiles;
+  const int workers = sms / CG;      // CTAs, or CTA pairs
+  if (pure_accum && tiles < workers && p.nkb >= 8) {
+    int want = workers / tiles;
     int maxs = p.nkb / 4;
     p.ksplits = want < maxs ? want : maxs;
     if (p.ksplits < 1) p.ksplits = 1;
@@ -441,14 +534,16 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
   if (!p.a_mn) rc = txl_make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
   else rc = txl_make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 64);
   if (rc) return rc;
-  if (!p.b_mn) rc = txl_make_tmap_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, BK);
+  if (!p.b_mn) rc = txl_make_tmap_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN / CG, BK);
   else rc = txl_make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, 64);
   if (rc) return rc;
 
   const int total = tiles * p.ksplits;
-  const int grid = total < sms ? total : sms;
+  const int grid = (total < workers ? total : workers) * CG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 256) {
+  if (CG == 2) {
+    if (dtype_c == TXL_F32) rc = launch<256, 5, float, 2>(tmA, tmB, tmC, p, grid, st); else rc = launch<256, 5, bf16, 2>(tmA, tmB, tmC, p, grid, st);
+  } else if (BN == 256) {
     if (dtype_c == TXL_F32) rc = launch<256, 4, float>(tmA, tmB, tmC, p, grid, st); else rc = launch<256, 4, bf16>(tmA, tmB, tmC, p, grid, st);
   } else {
     if (dtype_c == TXL_F32) rc = launch<128, 6, float>(tmA, tmB, tmC, p, grid, st); else rc = launch<128, 6, bf16>(tmA, tmB, tmC, p, grid, st);
