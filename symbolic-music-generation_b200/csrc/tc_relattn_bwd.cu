@@ -124,7 +124,7 @@ struct TileIter {
   }
 };
 
-struct Maps { CUtensorMap qw, qr, dO, km, vm, kc, vc, r, pst, dst, psv, r64; };   // pst/dst: [tiles*128, 64] bf16 tile stores (P, dS); psv: P~ saved by the forward; r64: R in 64-row boxes
+struct Maps { CUtensorMap qw, qr, dO, km, vm, kc, vc, r, pst, dst, psv, r64, pst2, dst2; };   // pst/dst: [tiles*128, 64] bf16 tile stores (P, dS); psv: P~ saved by the forward; r64: R in 64-row boxes; pst2/dst2: two tiles per box
 
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
@@ -556,6 +556,111 @@ __global__ void __launch_bounds__(192, 1) relattn_bwd_dkv_lite_kernel(const __gr
         tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q4) << 16) + 32 * half, v0);
         tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q4) << 16) + 64 + 32 * half, v1);
         tmem_ld_wait();
+        uint4* pk = reinterpret_cast<uint4*>(dk + h * DH + 32 * half);
+        uint4* pv = reinterpret_cast<uint4*>(dv + h * DH + 32 * half);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 o; o.x = pack2(v0[c * 8], v0[c * 8 + 1]); o.y = pack2(v0[c * 8 + 2], v0[c * 8 + 3]); o.z = pack2(v0[c * 8 + 4], v0[c * 8 + 5]); o.w = pack2(v0[c * 8 + 6], v0[c * 8 + 7]);
+          pk[c] = o;
+          uint4 u; u.x = pack2(v1[c * 8], v1[c * 8 + 1]); u.y = pack2(v1[c * 8 + 2], v1[c * 8 + 3]); u.z = pack2(v1[c * 8 + 4], v1[c * 8 + 5]); u.w = pack2(v1[c * 8 + 6], v1[c * 8 + 7]);
+          pv[c] = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
+// The same for TWO adjacent key tiles (128 keys) per CTA: the P / dS tiles of (I, 2Jp) and (I, 2Jp+1) sit next to each other in the
+// tile store, one 256-row TMA box brings both, and side by side they are exactly the two MN atoms of a full M = 128 A operand.
+// The 64-key kernel above wastes half of every MMA (rows 64..127 of its accumulators are ignored) and re-reads Qw / dO per key tile;
+// it is bound by shared-memory bandwidth (160 KB per key tile), this one moves 96 KB per key tile.  Needs first_kt(I) and the tile
+// count of every query tile to be even (mlen a multiple of 128).
+constexpr int PAIR_STAGES = 2, PAIR_STAGE = 6 * SZ_Q, PAIR_BAR = PAIR_STAGES * PAIR_STAGE, PAIR_SMEM = PAIR_BAR + 128 + 1024;
+__global__ void __launch_bounds__(192, 1) relattn_bwd_dkv_pair_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + PAIR_BAR);
+  uint64_t *full = bars, *empty = bars + PAIR_STAGES, *acc_full = bars + 2 * PAIR_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PAIR_STAGES + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BandGeom g = make_band(a.band);
+  const int Jp = blockIdx.x, J = 2 * Jp, h = blockIdx.y, b = blockIdx.z, nI = (g.T + BQ - 1) / BQ;
+  if (J * BKV + 2 * BKV <= g.mlen && a.dk_mem == nullptr) return;      // both key tiles lie in the detached mems
+  int Ilo = -1, count = 0;
+  for (int i = 0; i < nI; ++i)
+    if (q_tile_first_kt(g, i) <= J && J <= q_tile_last_kt(g, i)) { if (Ilo < 0) Ilo = i; ++count; }
+  auto out_ptrs = [&](int j, bf16*& dk, bf16*& dv) -> bool {
+    if (j < g.mlen) {
+      if (a.dk_mem == nullptr) return false;
+      dk = a.dk_mem + ((int64_t)b * g.mlen + j) * a.ldkv_mem; dv = a.dv_mem + ((int64_t)b * g.mlen + j) * a.ldkv_mem;
+    } else { dk = a.dk_cur + ((int64_t)b * g.T + (j - g.mlen)) * a.ldkv_cur; dv = a.dv_cur + ((int64_t)b * g.T + (j - g.mlen)) * a.ldkv_cur; }
+    return true;
+  };
+  if (count == 0) {
+    if (tid < 2 * BKV) { bf16 *dk, *dv; if (out_ptrs(J * BKV + tid, dk, dv)) for (int c = 0; c < DH; ++c) { dk[h * DH + c] = __float2bfloat16(0.f); dv[h * DH + c] = __float2bfloat16(0.f); } }
+    return;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < PAIR_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int n = 0; n < count; ++n) {
+        const int s = n % PAIR_STAGES; const uint32_t rph = (n / PAIR_STAGES) & 1;
+        const int I = Ilo + n;
+        mbar_wait(&empty[s], rph ^ 1);
+        uint8_t* st = sm + s * PAIR_STAGE;
+        mbar_expect_tx(&full[s], PAIR_STAGE);
+        const int trow = ((((b * a.H + h) * nI + I) * a.nt_max) + (J - q_tile_first_kt(g, I))) * BQ;
+        const int qrow = b * g.T + I * BQ;
+        tma_load_2d(st, &M.pst2, &full[s], 0, trow);                    // P  (I,J), (I,J+1)   2 x [128 q x 64 keys]
+        tma_load_2d(st + 2 * SZ_Q, &M.dst2, &full[s], 0, trow);         // dS (I,J), (I,J+1)
+        tma_load_2d(st + 4 * SZ_Q, &M.qw, &full[s], h * DH, qrow);      // Qw (I)     [128 q x 64]
+        tma_load_2d(st + 5 * SZ_Q, &M.dO, &full[s], h * DH, qrow);      // dO (I)
+      }
+    }
+  } else if (warp == 1) {
+    {   // whole warp, converged: one elected lane issues (umma_bf16_warp)
+      const uint32_t id_nn = umma_idesc_bf16(BQ, DH, 1, 1);
+      for (int n = 0; n < count; ++n) {
+        const int s = n % PAIR_STAGES; const uint32_t rph = (n / PAIR_STAGES) & 1;
+        mbar_wait(&full[s], rph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(sm + s * PAIR_STAGE);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)      // dK[128 keys] += dS^T . Qw   (the two key tiles are the two MN atoms of A, 16 KB apart)
+          umma_bf16_warp(tmem_base, umma_smem_desc(st + 2 * SZ_Q + k * 2048, 16384, 1024), umma_smem_desc(st + 4 * SZ_Q + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)      // dV[128 keys] += P^T . dO
+          umma_bf16_warp(tmem_base + 64, umma_smem_desc(st + k * 2048, 16384, 1024), umma_smem_desc(st + 5 * SZ_Q + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+        umma_commit_warp(&empty[s]);
+      }
+      umma_commit_warp(acc_full);
+    }
+  } else {
+    const int q4 = warp & 3, r = 32 * q4 + lane;     // warps 2..5 -> lane quadrants 2,3,0,1; TMEM lane r = key J*64 + r
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    bf16 *dk, *dv;
+    const bool wr = out_ptrs(J * BKV + r, dk, dv);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float v0[32], v1[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q4) << 16) + 32 * half, v0);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q4) << 16) + 64 + 32 * half, v1);
+      tmem_ld_wait();
+      if (wr) {
         uint4* pk = reinterpret_cast<uint4*>(dk + h * DH + 32 * half);
         uint4* pv = reinterpret_cast<uint4*>(dv + h * DH + 32 * half);
 #pragma unroll
@@ -1094,7 +1199,7 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
     if ((rc = txl_make_tmap_2d(&M.pst, pstore, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
     if ((rc = txl_make_tmap_2d(&M.dst, dstore, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
   } else { M.pst = M.qw; M.dst = M.qw; }
-  a.m_tiles = nullptr; M.psv = M.qw; M.r64 = M.r;
+  a.m_tiles = nullptr; M.psv = M.qw; M.r64 = M.r; M.pst2 = M.qw; M.dst2 = M.qw;
   { const char* e = getenv("TXL_ABL"); a.abl = e ? atoi(e) : 0; }
   if (saved && a.store_tiles && txl_relattn_saved_bytes_tc(D) > 0 && al16(saved)) {
     a.m_tiles = reinterpret_cast<const float*>(reinterpret_cast<const bf16*>(saved) + trows * BKV);
@@ -1129,7 +1234,25 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
       TXL_CUDA(cudaFuncSetAttribute(relattn_bwd_dr_lite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DRL_SMEM));
       attr_set = true;
     }
-    relattn_bwd_dkv_lite_kernel<<<dim3(klen / BKV, D->H, D->B), 192, LITE_SMEM, st>>>(M, a);
+    // two key tiles per CTA when every query tile's band starts on an even key tile and spans an even number of them
+    bool pairs = (klen % (2 * BKV)) == 0;
+    for (int I = 0; I < nI && pairs; ++I) {
+      const int j0 = band_lo(g, I * BQ) / BKV;
+      const int ilast = I * BQ + BQ - 1 < T - 1 ? I * BQ + BQ - 1 : T - 1;
+      const int hi = band_hi(g, ilast) < klen - 1 ? band_hi(g, ilast) : klen - 1;
+      if ((j0 & 1) || ((hi / BKV - j0 + 1) & 1)) pairs = false;
+    }
+    if (pairs) {
+      uintptr_t pws2 = ((uintptr_t)(delta + (int64_t)D->B * D->H * T) + 1023) & ~(uintptr_t)1023;
+      bf16* pstore2 = (bf16*)pws2; bf16* dstore2 = pstore2 + trows * BKV;
+      if ((rc = txl_make_tmap_2d(&M.pst2, pstore2, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, 2 * BQ, BKV))) return rc;
+      if ((rc = txl_make_tmap_2d(&M.dst2, dstore2, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, 2 * BQ, BKV))) return rc;
+      static bool attr_p = false;
+      if (!attr_p) { TXL_CUDA(cudaFuncSetAttribute(relattn_bwd_dkv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); attr_p = true; }
+      relattn_bwd_dkv_pair_kernel<<<dim3(klen / (2 * BKV), D->H, D->B), 192, PAIR_SMEM, st>>>(M, a);
+    } else {
+      relattn_bwd_dkv_lite_kernel<<<dim3(klen / BKV, D->H, D->B), 192, LITE_SMEM, st>>>(M, a);
+    }
     TXL_LAUNCH_CHECK();
     relattn_bwd_dr_lite_kernel<<<dim3(a.n_delta, D->H, 1), DRL_THREADS, DRL_SMEM, st>>>(M, a);
     TXL_LAUNCH_CHECK();
