@@ -243,7 +243,21 @@ __global__ void __launch_bounds__(256, (STEPS <= 2 ? 2 : 1)) add_ln_bwd_kernel(c
   for (int e = 0; e < STEPS; ++e)
 #pragma unroll
     for (int k = 0; k < LN_VEC; ++k) { ag[e][k] = 0.f; ab[e][k] = 0.f; }
-  for (int64_t row = warp; row < rows; row += (int64_t)gridDim.x * wpb) {
+  const int64_t row_step = (int64_t)gridDim.x * wpb;
+  for (int64_t row = warp; row < rows; row += row_step) {
+    // pull the next row of this warp towards L2 while this one is reduced and stored (pure HBM streaming kernel; one prefetch per 128-byte line)
+    if (row + row_step < rows && (lane & 7) == 0) {
+#pragma unroll
+      for (int e = 0; e < STEPS; ++e) {
+        const int c = (e * 32 + lane) * LN_VEC;
+        if (c < d) {
+          const int64_t o = (row + row_step) * d + c;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(dy + o));
+          if (dy2) asm volatile("prefetch.global.L2 [%0];" ::"l"(dy2 + o));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(z + o));
+        }
+      }
+    }
     const float mu = mean[row], rs = rstd[row];
     float g[STEPS][LN_VEC], xh[STEPS][LN_VEC];
     float s1 = 0.f, s2 = 0.f;
