@@ -798,6 +798,139 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_lite_kernel(con
   if (warp == W_MMA) tmem_dealloc<128>(tmem_base);
 }
 
+// The same for TWO adjacent band diagonals per CTA (delta, delta+1 with delta even): their windows overlap in 128 of 192 rows, the union
+// is 256 window rows = two fully used M = 128 accumulators (the single-diagonal kernel computes rows 64..127 twice), the dS tiles
+// (I, J) and (I, J+1) arrive in one 256-row TMA box, and Qr(I) is staged once for both.  104 KB of shared-memory traffic per band tile
+// instead of 160 KB.  The (I, b) loop is split over gridDim.z CTAs to keep every SM busy; partial dR sums meet in fp32 atomics.
+constexpr int DRP_STAGES = 2, DRP_STAGE = 3 * SZ_Q, DRP_SZ_DBD = 4 * SZ_Q, DRP_DBD = DRP_STAGES * DRP_STAGE, DRP_BAR = DRP_DBD + 2 * DRP_SZ_DBD,
+              DRP_SMEM = DRP_BAR + 128 + 1024;
+static_assert(DRP_SMEM <= 232448, "dR pair kernel shared-memory plan exceeds 227 KB");
+__global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_pair_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + DRP_BAR);
+  uint64_t *full = bars, *empty = bars + DRP_STAGES, *b_ready = bars + 2 * DRP_STAGES, *b_done = b_ready + 2, *acc_full = b_ready + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_ready + 5);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BandGeom g = make_band(a.band);
+  const int HD = a.H * DH, nI = (g.T + BQ - 1) / BQ;
+  const int delta = a.delta_min + 2 * (int)blockIdx.x, h = blockIdx.y;
+  const int nb = (a.B + (int)gridDim.z - 1) / (int)gridDim.z, b_lo = (int)blockIdx.z * nb, b_cnt = min(nb, a.B - b_lo);
+  int Ilo = -1, cntI = 0;
+  for (int i = 0; i < nI; ++i) {
+    int j = 2 * i + delta;
+    if (q_tile_first_kt(g, i) <= j && j <= q_tile_last_kt(g, i)) { if (Ilo < 0) Ilo = i; ++cntI; }
+  }
+  const int count = b_cnt > 0 ? cntI * b_cnt : 0;
+  if (count == 0) return;
+  if (tid == 0) {
+    for (int s = 0; s < DRP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1 + N_SOFTMAX / 32); }
+    mbar_init(&b_ready[0], N_SOFTMAX / 32); mbar_init(&b_ready[1], N_SOFTMAX / 32); mbar_init(&b_done[0], 1); mbar_init(&b_done[1], 1); mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc<128>(tmem_slot);
+  for (int e = tid; e < 2 * DRP_SZ_DBD / 16; e += DRL_THREADS) reinterpret_cast<uint4*>(sm + DRP_DBD)[e] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == W_PROD) {
+    if (lane == 0) {
+      for (int n = 0; n < count; ++n) {
+        const int s = n % DRP_STAGES; const uint32_t rph = (n / DRP_STAGES) & 1;
+        const int I = Ilo + n / b_cnt, b = b_lo + n % b_cnt, J = 2 * I + delta;
+        mbar_wait(&empty[s], rph ^ 1);
+        uint8_t* st = sm + s * DRP_STAGE;
+        mbar_expect_tx(&full[s], DRP_STAGE);
+        const int trow = ((((b * a.H + h) * nI + I) * a.nt_max) + (J - q_tile_first_kt(g, I))) * BQ;
+        tma_load_2d(st, &M.dst2, &full[s], 0, trow);                                 // dS (I,J), (I,J+1)
+        tma_load_2d(st + 2 * SZ_Q, &M.qr, &full[s], h * DH, b * g.T + I * BQ);       // Qr (I)
+      }
+    }
+  } else if (warp == W_MMA) {
+    {   // whole warp, converged: one elected lane issues (umma_bf16_warp)
+      const uint32_t id_nn = umma_idesc_bf16(BQ, DH, 1, 1);
+      for (int n = 0; n < count; ++n) {
+        const int s = n % DRP_STAGES, buf = n & 1;
+        const uint32_t dbd = smem_u32(sm + DRP_DBD + buf * DRP_SZ_DBD);
+        const uint32_t qr = smem_u32(sm + s * DRP_STAGE + 2 * SZ_Q);
+        mbar_wait(&b_ready[buf], (n >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)      // dRwin[  0..127] += dBD0[:,   0..127]^T . Qr
+          umma_bf16_warp(tmem_base, umma_smem_desc(dbd + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)      // dRwin[128..255] += dBD0[:, 128..255]^T . Qr
+          umma_bf16_warp(tmem_base + 64, umma_smem_desc(dbd + 2 * 16384 + k * 2048, 16384, 1024), umma_smem_desc(qr + k * 2048, 8192, 1024), id_nn, (n > 0) | (k > 0));
+        umma_commit_warp(&b_done[buf]);
+        umma_commit_warp(&empty[s]);
+      }
+      umma_commit_warp(acc_full);
+    }
+  } else {
+    const int r = 32 * (warp & 3) + lane, qd = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    const int c0 = 127 - r + KPT * qd;
+    for (int n = 0; n < count; ++n) {
+      const int s = n % DRP_STAGES, buf = n & 1; const uint32_t rph = (n / DRP_STAGES) & 1;
+      uint8_t* dbd = sm + DRP_DBD + buf * DRP_SZ_DBD;
+      auto addr = [&](int c) -> uint8_t* { return dbd + (c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
+      mbar_wait(&full[s], rph);
+      // this thread's 16 dS values (bf16) of each of the two tiles, out of the swizzled K-major tiles
+      const uint8_t* tile = sm + s * DRP_STAGE;
+      uint32_t wv[2][8];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint4 u0 = *reinterpret_cast<const uint4*>(tile + t * SZ_Q + r * 128 + (((2 * qd) ^ (r & 7)) << 4));
+        const uint4 u1 = *reinterpret_cast<const uint4*>(tile + t * SZ_Q + r * 128 + (((2 * qd + 1) ^ (r & 7)) << 4));
+        wv[t][0] = u0.x; wv[t][1] = u0.y; wv[t][2] = u0.z; wv[t][3] = u0.w; wv[t][4] = u1.x; wv[t][5] = u1.y; wv[t][6] = u1.z; wv[t][7] = u1.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);         // dS tiles consumed by this warp (Qr is released by the MMA commit)
+      if (n > 1) mbar_wait(&b_done[buf], ((n - 2) >> 1) & 1);      // the MMAs that read this dBD buffer two steps ago are done
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int cc = c0 + BKV * t;
+        if ((cc & 1) == 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) *reinterpret_cast<uint32_t*>(addr(cc + 2 * k)) = wv[t][k];
+        } else {
+          *reinterpret_cast<uint16_t*>(addr(cc)) = (uint16_t)(wv[t][0] & 0xFFFFu);
+#pragma unroll
+          for (int k = 0; k < 7; ++k) *reinterpret_cast<uint32_t*>(addr(cc + 1 + 2 * k)) = (wv[t][k] >> 16) | (wv[t][k + 1] << 16);
+          *reinterpret_cast<uint16_t*>(addr(cc + 15)) = (uint16_t)(wv[t][7] >> 16);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_ready[buf]);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float v0[KPT], v1[KPT];
+    tmem_ld_32x16(tmem_base + lane_base + KPT * qd, v0);
+    tmem_ld_32x16(tmem_base + lane_base + 64 + KPT * qd, v1);
+    tmem_ld_wait();
+    const int x0 = g.T - BQ + BKV * delta;
+    const int xa = x0 + r, xb = x0 + BQ + r;
+    if (xa >= 0 && xa < g.klen) {
+      float4* d = reinterpret_cast<float4*>(a.dr + (int64_t)xa * HD + h * DH + KPT * qd);
+#pragma unroll
+      for (int c = 0; c < KPT / 4; ++c) atomicAdd(d + c, make_float4(v0[4 * c], v0[4 * c + 1], v0[4 * c + 2], v0[4 * c + 3]));
+    }
+    if (xb >= 0 && xb < g.klen) {
+      float4* d = reinterpret_cast<float4*>(a.dr + (int64_t)xb * HD + h * DH + KPT * qd);
+#pragma unroll
+      for (int c = 0; c < KPT / 4; ++c) atomicAdd(d + c, make_float4(v1[4 * c], v1[4 * c + 1], v1[4 * c + 2], v1[4 * c + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc<128>(tmem_base);
+}
+
 // ------------------------------------------------------------------ dQ pass over the P~ tiles the forward kernel saved
 // The forward pass leaves, per band tile, the bf16 numerators P~ = exp2(score - m) it fed to P.V and the running max m it used.
 // With the final log-sum-exp, P = P~ * exp2(m - lse): no S / BD0 recomputation, no _rel_shift, no mask arithmetic, no exp per
@@ -1254,7 +1387,17 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
       relattn_bwd_dkv_lite_kernel<<<dim3(klen / BKV, D->H, D->B), 192, LITE_SMEM, st>>>(M, a);
     }
     TXL_LAUNCH_CHECK();
-    relattn_bwd_dr_lite_kernel<<<dim3(a.n_delta, D->H, 1), DRL_THREADS, DRL_SMEM, st>>>(M, a);
+    if (pairs && (a.n_delta % 2) == 0 && (((uintptr_t)dr) & 15) == 0) {     // diagonals pair up exactly like the key tiles (delta_min is even then)
+      static bool attr_d = false;
+      if (!attr_d) { TXL_CUDA(cudaFuncSetAttribute(relattn_bwd_dr_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DRP_SMEM)); attr_d = true; }
+      const int npairs = a.n_delta / 2, heads = D->H;
+      int zsplit = txl_num_sms() / (npairs * heads);           // split the (I, b) loop until every SM has a CTA
+      if (zsplit < 1) zsplit = 1;
+      if (zsplit > D->B) zsplit = D->B;
+      relattn_bwd_dr_pair_kernel<<<dim3(npairs, heads, zsplit), DRL_THREADS, DRP_SMEM, st>>>(M, a);
+    } else {
+      relattn_bwd_dr_lite_kernel<<<dim3(a.n_delta, D->H, 1), DRL_THREADS, DRL_SMEM, st>>>(M, a);
+    }
     TXL_LAUNCH_CHECK();
   } else {
     if ((rc = launch_mode<MODE_DKV>(M, a, dim3(klen / BKV, D->H, D->B), st))) return rc;
