@@ -1,5 +1,6 @@
 // umma_probe.cu — micro-benchmarks behind the attention-kernel design decisions (profiles/README.md):
-//   (1) cycles per tcgen05.mma (M=128, K=16, bf16) for the N and operand-major combinations the attention kernels issue,
+//   (1) cycles per tcgen05.mma (M=128, K=16, bf16) for the N and operand-major combinations the attention kernels issue, and for three
+//       ways of issuing it (divergent single thread / converged warp + lane predicate / converged warp + elect.sync),
 //   (2) tcgen05.ld throughput with 4 / 8 / 16 warps reading TMEM,
 //   (3) cost of st.shared + fence.proxy.async + mbarrier.arrive by every thread vs. named barrier + one fence.
 // Build (from the repo root):
@@ -13,9 +14,56 @@ int g_txl_launches_dummy;
 namespace {
 constexpr int SMEM = 200 * 1024;
 
-struct MmaCfg { int N, a_mn, b_mn, nk; const char* name; int nacc = 1; int M = 128; };
+struct MmaCfg { int N, a_mn, b_mn, nk; const char* name; };
 
-__global__ void __launch_bounds__(128, 1) mma_probe(int N, int a_mn, int b_mn, int nk, int reps, long long* out, int nacc, int M) {
+__device__ __forceinline__ void umma_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// chains of nk accumulating MMAs (the k-steps of one tile), issued by a converged warp through elect.sync (the fast issue path)
+__global__ void __launch_bounds__(128, 1) mma_probe(int N, int a_mn, int b_mn, int nk, int reps, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int e = threadIdx.x; e < 160 * 1024 / 16; e += blockDim.x) reinterpret_cast<uint4*>(sm)[e] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc<512>(&slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  if (threadIdx.x < 32) {
+    const uint32_t idesc = umma_idesc_bf16(128, N, a_mn, b_mn);
+    const uint32_t a0 = smem_u32(sm), b0 = smem_u32(sm) + 64 * 1024;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      for (int k = 0; k < nk; ++k) {
+        // K-major: +32 B per 16-element k-step inside a 64-wide atom; MN-major: +2048 B per 16 k-rows
+        const uint64_t ad = a_mn ? umma_smem_desc(a0 + k * 2048, 16384, 1024) : umma_smem_desc(a0 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+        const uint64_t bd = b_mn ? umma_smem_desc(b0 + k * 2048, 8192, 1024) : umma_smem_desc(b0 + (k >> 2) * 24576 + (k & 3) * 32, 16, 1024);
+        umma_elect(tm + (r & 1) * 256, ad, bd, idesc, k > 0);
+      }
+    }
+    if (threadIdx.x == 0) umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc<512>(tm);
+}
+
+// the same N = 64 chain issued the slow way: from divergent `if (threadIdx.x == 0)` code (ptxas wraps each MMA in an ELECT / BRA.U.ANY loop)
+__global__ void __launch_bounds__(128, 1) solo_issue_probe(int reps, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -30,23 +78,15 @@ __global__ void __launch_bounds__(128, 1) mma_probe(int N, int a_mn, int b_mn, i
   tc_fence_after();
   const uint32_t tm = slot;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = umma_idesc_bf16(M, N, a_mn, b_mn);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
     const uint32_t a0 = smem_u32(sm), b0 = smem_u32(sm) + 64 * 1024;
-    // warm-up
-    umma_bf16(tm, umma_smem_desc(a0, 16, 1024), umma_smem_desc(b0, 16, 1024), idesc, 0);
-    umma_commit(&bar);
-    mbar_wait(&bar, 0);
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
-      for (int k = 0; k < nk; ++k) {
-        // K-major: +32 B per 16-element k-step inside a 64-wide atom; MN-major: +2048 B per 16 k-rows
-        const uint64_t ad = a_mn ? umma_smem_desc(a0 + k * 2048, 16384, 1024) : umma_smem_desc(a0 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-        const uint64_t bd = b_mn ? umma_smem_desc(b0 + k * 2048, 8192, 1024) : umma_smem_desc(b0 + (k >> 2) * 24576 + (k & 3) * 32, 16, 1024);
-        umma_bf16(tm + ((nacc > 1) ? ((k % nacc) * 64) : (r & 1) * 256), ad, bd, idesc, nacc > 1 ? (r > 0 || k >= nacc) : (k > 0));
-      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tm + (r & 1) * 256, umma_smem_desc(a0 + k * 32, 16, 1024), umma_smem_desc(b0 + k * 32, 16, 1024), idesc, k > 0);
     }
     umma_commit(&bar);
-    mbar_wait(&bar, 1);
+    mbar_wait(&bar, 0);
     const long long t1 = clock64();
     if (blockIdx.x == 0) out[0] = t1 - t0;
   }
@@ -179,15 +219,11 @@ int main() {
       {64, 0, 0, 4, "N=64  A K-major  B K-major  (S = Qw.K^T, dP = dO.V^T)"}, {64, 0, 1, 4, "N=64  A K-major  B MN-major (O += P.V, dQw += dS.K)"},
       {64, 0, 1, 12, "N=64  A K-major  B MN-major, 12 k-steps (dQr += dBD0.Rwin)"}, {64, 1, 1, 8, "N=64  A MN-major B MN-major (dK += dS^T.Qw, dV += P^T.dO, dR)"},
       {192, 0, 0, 4, "N=192 A K-major  B K-major  (BD0 = Qr.Rwin^T)"}, {128, 0, 0, 4, "N=128 A K-major  B K-major"}, {256, 0, 0, 4, "N=256 A K-major  B K-major (GEMM tile)"},
-      {128, 0, 1, 4, "N=128 A K-major  B MN-major"}, {128, 1, 1, 8, "N=128 A MN-major B MN-major"},
-      {64, 0, 0, 4, "N=64  K/K, 2 independent accumulators interleaved", 2}, {64, 0, 0, 4, "N=64  K/K, 4 independent accumulators interleaved", 4},
-      {64, 0, 0, 8, "N=64  K/K, 8 k-steps, 4 accumulators interleaved", 4}, {32, 0, 0, 4, "N=32  K/K"}, {16, 0, 0, 4, "N=16  K/K"},
-      {64, 0, 0, 4, "N=64  K/K, M=64", 1, 64}, {128, 0, 0, 4, "N=128 K/K, M=64", 1, 64}, {64, 0, 1, 12, "N=64 K/MN 12 k-steps, 4 accumulators", 4},
-      {64, 1, 1, 8, "N=64 MN/MN 8 k-steps, 2 accumulators", 2}};
+      {128, 0, 1, 4, "N=128 A K-major  B MN-major"}, {128, 1, 1, 8, "N=128 A MN-major B MN-major"}, {32, 0, 0, 4, "N=32  A K-major  B K-major"}, {16, 0, 0, 4, "N=16  A K-major  B K-major"}};
   const int reps = 2000;
   for (const auto& c : cfgs) {
     for (int grid : {148}) {
-      mma_probe<<<grid, 128, SMEM>>>(c.N, c.a_mn, c.b_mn, c.nk, reps, d_out, c.nacc, c.M);
+      mma_probe<<<grid, 128, SMEM>>>(c.N, c.a_mn, c.b_mn, c.nk, reps, d_out);
       long long cyc = 0;
       cudaError_t e = cudaDeviceSynchronize();
       cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
@@ -203,6 +239,7 @@ int main() {
       cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
       printf("issue %-60s: %7.1f cycles per MMA   [%s]\n", name, (double)cyc / (reps * 4), cudaGetErrorString(e));
     };
+    run("divergent single thread (if (threadIdx.x == 0)), N=64", solo_issue_probe);
     run("converged warp, lane-0 predicate, N=64", issue_probe<1, 64>);
     run("converged warp, elect.sync predicate, N=64", issue_probe<2, 64>);
     run("converged warp, lane-0 predicate, N=128", issue_probe<1, 128>);

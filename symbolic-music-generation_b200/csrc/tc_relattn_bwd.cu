@@ -873,18 +873,24 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_pair_kernel(con
     const int r = 32 * (warp & 3) + lane, qd = warp >> 2;
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const int c0 = 127 - r + KPT * qd;
+    // tile-invariant shared-memory offsets: this thread's two 16-byte chunks of a K-major dS tile, and where its bf16 pairs land in the
+    // window-space tile (tile t of the pair sits 64 window columns further right)
+    const uint32_t ld_off0 = (uint32_t)(r * 128 + (((2 * qd) ^ (r & 7)) << 4)), ld_off1 = (uint32_t)(r * 128 + (((2 * qd + 1) ^ (r & 7)) << 4));
+    auto dbd_off = [&](int c) -> uint32_t { return (uint32_t)((c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2); };
+    const bool odd = c0 & 1;
+    uint32_t w_off[9];       // word (or half-word at the two ends when c0 is odd) positions for tile 0; tile 1 = +16384 bytes (one 64-column atom)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w_off[k] = dbd_off(odd ? (k == 0 ? c0 : c0 + 2 * k - 1) : c0 + 2 * (k < 8 ? k : 7));
     for (int n = 0; n < count; ++n) {
       const int s = n % DRP_STAGES, buf = n & 1; const uint32_t rph = (n / DRP_STAGES) & 1;
       uint8_t* dbd = sm + DRP_DBD + buf * DRP_SZ_DBD;
-      auto addr = [&](int c) -> uint8_t* { return dbd + (c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2; };
       mbar_wait(&full[s], rph);
-      // this thread's 16 dS values (bf16) of each of the two tiles, out of the swizzled K-major tiles
       const uint8_t* tile = sm + s * DRP_STAGE;
       uint32_t wv[2][8];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const uint4 u0 = *reinterpret_cast<const uint4*>(tile + t * SZ_Q + r * 128 + (((2 * qd) ^ (r & 7)) << 4));
-        const uint4 u1 = *reinterpret_cast<const uint4*>(tile + t * SZ_Q + r * 128 + (((2 * qd + 1) ^ (r & 7)) << 4));
+        const uint4 u0 = *reinterpret_cast<const uint4*>(tile + t * SZ_Q + ld_off0);
+        const uint4 u1 = *reinterpret_cast<const uint4*>(tile + t * SZ_Q + ld_off1);
         wv[t][0] = u0.x; wv[t][1] = u0.y; wv[t][2] = u0.z; wv[t][3] = u0.w; wv[t][4] = u1.x; wv[t][5] = u1.y; wv[t][6] = u1.z; wv[t][7] = u1.w;
       }
       __syncwarp();
@@ -892,15 +898,15 @@ __global__ void __launch_bounds__(DRL_THREADS, 1) relattn_bwd_dr_pair_kernel(con
       if (n > 1) mbar_wait(&b_done[buf], ((n - 2) >> 1) & 1);      // the MMAs that read this dBD buffer two steps ago are done
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int cc = c0 + BKV * t;
-        if ((cc & 1) == 0) {
+        uint8_t* base = dbd + t * 16384;
+        if (!odd) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) *reinterpret_cast<uint32_t*>(addr(cc + 2 * k)) = wv[t][k];
+          for (int k = 0; k < 8; ++k) *reinterpret_cast<uint32_t*>(base + w_off[k]) = wv[t][k];
         } else {
-          *reinterpret_cast<uint16_t*>(addr(cc)) = (uint16_t)(wv[t][0] & 0xFFFFu);
+          *reinterpret_cast<uint16_t*>(base + w_off[0]) = (uint16_t)(wv[t][0] & 0xFFFFu);
 #pragma unroll
-          for (int k = 0; k < 7; ++k) *reinterpret_cast<uint32_t*>(addr(cc + 1 + 2 * k)) = (wv[t][k] >> 16) | (wv[t][k + 1] << 16);
-          *reinterpret_cast<uint16_t*>(addr(cc + 15)) = (uint16_t)(wv[t][7] >> 16);
+          for (int k = 0; k < 7; ++k) *reinterpret_cast<uint32_t*>(base + w_off[k + 1]) = (wv[t][k] >> 16) | (wv[t][k + 1] << 16);
+          *reinterpret_cast<uint16_t*>(base + w_off[8]) = (uint16_t)(wv[t][7] >> 16);
         }
       }
       fence_proxy_async_smem();
