@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_dq_saved_kernel(const
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + PL::BAR);
   uint64_t *full = bars, *empty = bars + 3, *rfull = bars + 6, *rfree = bars + 10, *f_full = bars + 14, *t_free = bars + 16;
-  uint64_t *res_full = bars + 18, *acc_full = bars + 19, *b_ready = bars + 20, *b_done = bars + 21;
+  uint64_t *res_full = bars + 18, *acc_full = bars + 19, *b_ready = bars + 20, *b_done = bars + 21, *dbd_done = bars + 22;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const BandGeom g = make_band(a.band);
@@ -981,6 +981,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_dq_saved_kernel(const
     for (int s = 0; s < 2; ++s) { mbar_init(&f_full[s], 1); mbar_init(&t_free[s], N_SOFTMAX / 32); }
     mbar_init(res_full, 1); mbar_init(acc_full, 1);
     mbar_init(b_ready, N_SOFTMAX / 32); mbar_init(b_done, 2);    // b_done: back-end MMAs finished + the tile store has read the work tiles
+    mbar_init(dbd_done, 1);                                      // the 12 dQr MMAs (issued first) are done with the window tile
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc<TS_COLS>(tmem_slot);
@@ -1058,12 +1059,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_dq_saved_kernel(const
         const uint32_t accum0 = n > 0;
         const uint32_t ds = base + PL::DS, dbd = base + PL::DBD, kk_ = st + PL::K, rr = base + PL::RRING;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)      // dQw += dS . K
-          umma_bf16_warp(tmem_base + TS_ACC0, umma_smem_desc(ds + k * 32, 16, 1024), umma_smem_desc(kk_ + k * 2048, 8192, 1024), id_kn, accum0 | (k > 0));
-#pragma unroll
         for (int k = 0; k < 12; ++k)     // dQr += dBD0 . Rwin, window chunk k/4 lives in ring slot (n + k/4) mod 4
           umma_bf16_warp(tmem_base + TS_ACC1, umma_smem_desc(dbd + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
                          umma_smem_desc(rr + ((n + (k >> 2)) & 3) * SZ_KV + (k & 3) * 2048, 8192, 1024), id_kn, accum0 | (k > 0));
+        umma_commit_warp(dbd_done);      // the window tile may be rewritten while the dQw MMAs and the tile store still run
+#pragma unroll
+        for (int k = 0; k < 4; ++k)      // dQw += dS . K
+          umma_bf16_warp(tmem_base + TS_ACC0, umma_smem_desc(ds + k * 32, 16, 1024), umma_smem_desc(kk_ + k * 2048, 8192, 1024), id_kn, accum0 | (k > 0));
         umma_commit_warp(b_done);
         umma_commit_warp(&empty[s]);
         umma_commit_warp(&rfree[n & 3]);          // chunk n was the first chunk of this window: no later tile reads it
@@ -1139,7 +1141,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_dq_saved_kernel(const
 #pragma unroll
       for (int jj = 0; jj < KPT; ++jj) ds[jj] = p[jj] * (ds[jj] - dlt) * fs;
       if (tid == 0) TS(0, n, 4);
-      if (n > 0) mbar_wait(b_done, (n - 1) & 1);      // back end + tile store of tile n-1 have read the work tiles
+      if (n > 0) mbar_wait(dbd_done, (n - 1) & 1);    // the dQr MMAs of tile n-1 have read the window tile
       if (tid == 0) TS(0, n, 5);
       {
         uint8_t* dbd = sm + PL::DBD;
@@ -1153,6 +1155,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_dq_saved_kernel(const
           *reinterpret_cast<bf16*>(dbd + single_off[1]) = __float2bfloat16_rn(ds[KPT - 1]);
         }
       }
+      if (n > 0) mbar_wait(b_done, (n - 1) & 1);      // ... and its dQw MMAs + tile store have read P / dS
 #pragma unroll
       for (int c = 0; c < KPT / 8; ++c) {
         uint4 o; o.x = pack2(p[c * 8], p[c * 8 + 1]); o.y = pack2(p[c * 8 + 2], p[c * 8 + 3]); o.z = pack2(p[c * 8 + 4], p[c * 8 + 5]); o.w = pack2(p[c * 8 + 6], p[c * 8 + 7]);
