@@ -342,8 +342,40 @@ __global__ void colsum_kernel(const T* __restrict__ X, int64_t M, int64_t N, int
   for (int64_t m = m0; m < m1; ++m) s += to_f32(X[m * ldx + n]);
   atomicAdd(&out[n], s);
 }
+// bf16, N and ldx multiples of 8, 16-byte aligned rows: every thread owns 8 adjacent columns (one 16-byte load per row), a block walks
+// its slice of rows with all lanes reading contiguous bytes, partial sums meet in shared memory and leave as one atomic per column per block
+__global__ void __launch_bounds__(256) colsum_bf16_vec_kernel(const bf16* __restrict__ X, int64_t M, int64_t N, int64_t ldx, float* __restrict__ out) {
+  __shared__ float red[256 * 8];
+  const int tpr = (int)(N / 8);                         // threads per row (host guarantees tpr <= 256 and 256 % tpr == 0)
+  const int rpi = 256 / tpr;                            // rows per block iteration
+  const int col8 = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int64_t m = (int64_t)blockIdx.x * rpi + rsub; m < M; m += (int64_t)gridDim.x * rpi) {
+    const uint4 u = *reinterpret_cast<const uint4*>(X + m * ldx + col8 * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { acc[2 * k] += __uint_as_float(w[k] << 16); acc[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u); }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < (int)N; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < rpi; ++r) s += red[(r * tpr + c / 8) * 8 + (c & 7)];
+    atomicAdd(&out[c], s);
+  }
+}
 extern "C" int txl_colsum(const void* X, int64_t M, int64_t N, int64_t ldx, int dtype, float* out, void* stream) {
   TXL_CHECK_ARG(X && out && M > 0 && N > 0 && ldx >= N, "colsum: bad args");
+  if (dtype == TXL_BF16 && N % 8 == 0 && ldx % 8 == 0 && N / 8 <= 256 && 256 % (N / 8) == 0 && (((uintptr_t)X) & 15) == 0 && M >= 1024) {
+    const int rpi = 256 / (int)(N / 8);
+    const int grid = (int)imin64(cdiv64(M, (int64_t)rpi * 4), (int64_t)txl_num_sms() * 4);
+    colsum_bf16_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)X, M, N, ldx, out);
+    TXL_LAUNCH_CHECK();
+    return TXL_OK;
+  }
   int rpb = 256;
   dim3 grid((unsigned)cdiv64(N, 128), (unsigned)cdiv64(M, rpb));
   DISPATCH_DTYPE(dtype, (colsum_kernel<T><<<grid, 128, 0, (cudaStream_t)stream>>>((const T*)X, M, N, ldx, out, rpb)));

@@ -68,6 +68,18 @@ def test_gemm_epilogues(ops):
     torch.testing.assert_close(d1[kept], ((A @ B.t()) / 0.75)[kept], rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize('dt,M,N,view', [(torch.bfloat16, 4096, 512, False), (torch.bfloat16, 5000, 2048, False), (torch.bfloat16, 3001, 256, True),
+                                         (torch.bfloat16, 2048, 1190, False), (torch.float32, 1500, 512, False), (torch.bfloat16, 100, 64, False)])
+def test_colsum(ops, dt, M, N, view):
+    """bias gradients: out[n] += sum_m X[m, n] (vectorised bf16 kernel for the wide shapes, scalar kernel for the rest), accumulating."""
+    torch.manual_seed(13)
+    full = torch.randn(M, 3 * N if view else N, device='cuda').to(dt)
+    X = full[:, N:2 * N] if view else full
+    out = torch.full((N,), 0.5, device='cuda')
+    ops.colsum(X, out)
+    torch.testing.assert_close(out, 0.5 + X.float().sum(0), rtol=1e-4, atol=2e-2)
+
+
 @pytest.mark.parametrize('mode', ['fp32', 'bf16'])
 def test_add_ln_fwd_bwd(ops, mode):
     torch.manual_seed(2)
