@@ -1200,24 +1200,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_dq_saved_kernel(const
 }
 
 // qw = q + r_w_bias, qr = q + r_r_bias (bf16, [B*T, HD]); delta[b,h,i] = sum_c dO.O
-__global__ void relattn_bwd_prep_kernel(const bf16* __restrict__ q, int64_t ldq, const float* __restrict__ rwb, const float* __restrict__ rrb,
+// One thread per 8 adjacent columns (16-byte loads / stores), the 8 threads of a (row, head) meet in three shuffles.
+__global__ void __launch_bounds__(256) relattn_bwd_prep_kernel(const bf16* __restrict__ q, int64_t ldq, const float* __restrict__ rwb, const float* __restrict__ rrb,
                                         const bf16* __restrict__ out, const bf16* __restrict__ dout, bf16* __restrict__ qw, bf16* __restrict__ qr,
                                         float* __restrict__ delta, int B, int T, int H) {
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t total = (int64_t)B * T * H;
-  if (gw >= total) return;
-  const int h = (int)(gw % H); const int64_t n = gw / H;     // n = b*T + i
-  const int HD = H * DH, c = h * DH + 2 * lane;
-  const __nv_bfloat162 qv = *reinterpret_cast<const __nv_bfloat162*>(q + n * ldq + c);
-  const float q0 = __bfloat162float(qv.x), q1 = __bfloat162float(qv.y);
-  *reinterpret_cast<__nv_bfloat162*>(qw + n * HD + c) = __floats2bfloat162_rn(q0 + rwb[c], q1 + rwb[c + 1]);
-  *reinterpret_cast<__nv_bfloat162*>(qr + n * HD + c) = __floats2bfloat162_rn(q0 + rrb[c], q1 + rrb[c + 1]);
-  const __nv_bfloat162 ov = *reinterpret_cast<const __nv_bfloat162*>(out + n * HD + c);
-  const __nv_bfloat162 dv = *reinterpret_cast<const __nv_bfloat162*>(dout + n * HD + c);
-  float s = __bfloat162float(ov.x) * __bfloat162float(dv.x) + __bfloat162float(ov.y) * __bfloat162float(dv.y);
-  s = warp_sum(s);
-  if (lane == 0) { const int64_t b = n / T, i = n % T; delta[(b * H + h) * T + i] = s; }
+  const int HD = H * DH, tpr = HD / 8;                         // threads per row
+  const int64_t total = (int64_t)B * T * tpr;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {   // total is a multiple of 8: groups stay whole
+    const int64_t n = g / tpr; const int c = (int)(g % tpr) * 8;
+    const uint4 qv = *reinterpret_cast<const uint4*>(q + n * ldq + c);
+    const uint4 ov = *reinterpret_cast<const uint4*>(out + n * HD + c);
+    const uint4 dv = *reinterpret_cast<const uint4*>(dout + n * HD + c);
+    const float4 w0 = *reinterpret_cast<const float4*>(rwb + c), w1 = *reinterpret_cast<const float4*>(rwb + c + 4);
+    const float4 r0 = *reinterpret_cast<const float4*>(rrb + c), r1 = *reinterpret_cast<const float4*>(rrb + c + 4);
+    const float wb[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, rb[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const uint32_t qs[4] = {qv.x, qv.y, qv.z, qv.w}, os[4] = {ov.x, ov.y, ov.z, ov.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+    uint32_t ow[4], orr[4];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float q0 = __uint_as_float(qs[k] << 16), q1 = __uint_as_float(qs[k] & 0xFFFF0000u);
+      ow[k] = pack2(q0 + wb[2 * k], q1 + wb[2 * k + 1]);
+      orr[k] = pack2(q0 + rb[2 * k], q1 + rb[2 * k + 1]);
+      s += __uint_as_float(os[k] << 16) * __uint_as_float(ds[k] << 16) + __uint_as_float(os[k] & 0xFFFF0000u) * __uint_as_float(ds[k] & 0xFFFF0000u);
+    }
+    *reinterpret_cast<uint4*>(qw + n * HD + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    *reinterpret_cast<uint4*>(qr + n * HD + c) = make_uint4(orr[0], orr[1], orr[2], orr[3]);
+    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);   // DH = 64 = 8 threads
+    if ((c & (DH - 1)) == 0) { const int64_t b = n / T, i = n % T; delta[(b * H + c / DH) * T + i] = s; }
+  }
 }
 
 template <int MODE>
@@ -1298,8 +1309,8 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
   const int64_t n = (int64_t)D->B * T * HD;
   bf16* qw = (bf16*)ws; bf16* qr = qw + n; float* delta = (float*)(qr + n);
   if (!(dbg & 32)) {
-    const int64_t warps = (int64_t)D->B * T * D->H;
-    relattn_bwd_prep_kernel<<<(unsigned)cdiv64(warps, 8), 256, 0, st>>>((const bf16*)q, D->ldq, rwb, rrb, (const bf16*)out, (const bf16*)dout, qw, qr, delta, D->B, T, D->H);
+    const int64_t items = (int64_t)D->B * T * (HD / 8);
+    relattn_bwd_prep_kernel<<<(unsigned)imin64(cdiv64(items, 256), (int64_t)txl_num_sms() * 16), 256, 0, st>>>((const bf16*)q, D->ldq, rwb, rrb, (const bf16*)out, (const bf16*)dout, qw, qr, delta, D->B, T, D->H);
     TXL_LAUNCH_CHECK();
   }
   Maps M;
