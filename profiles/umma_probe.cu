@@ -25,7 +25,9 @@ __device__ __forceinline__ void umma_elect(uint32_t tmem_d, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// chains of nk accumulating MMAs (the k-steps of one tile), issued by a converged warp through elect.sync (the fast issue path)
+// chains of nk accumulating MMAs (the k-steps of one tile), issued by a converged warp through elect.sync; shape and operand layouts are
+// RUN-TIME arguments here, so the descriptors are rebuilt per MMA: the table shows what that scalar work costs (94 cycles per issue for
+// the small shapes) next to the tight `issue` variants below (48)
 __global__ void __launch_bounds__(128, 1) mma_probe(int N, int a_mn, int b_mn, int nk, int reps, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe(int N, int a_mn, int b_mn, i
   if (threadIdx.x < 32) tmem_dealloc<512>(tm);
 }
 
-// the same N = 64 chain issued the slow way: from divergent `if (threadIdx.x == 0)` code (ptxas wraps each MMA in an ELECT / BRA.U.ANY loop)
+// the N = 64 chain, unrolled with compile-time shape, issued from divergent `if (threadIdx.x == 0)` code
 __global__ void __launch_bounds__(128, 1) solo_issue_probe(int reps, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);

@@ -88,10 +88,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 // The same, called by ALL 32 lanes of a converged warp: the instruction is predicated on elect.sync, which lets ptxas keep the
-// descriptors in uniform registers and emit one predicated UTCHMMA.  Issued from divergent `if (lane == 0)` code the compiler
-// wraps every MMA in an ELECT / BRA.U.ANY loop instead: 117 cycles per issue vs 48 (= the smem operand floor of an M128 N64 K16
-// MMA), measured with profiles/umma_probe.cu.  elect.sync picks the same leader for the same member mask every time, so the
-// MMAs and the tcgen05.commit that tracks them come from one thread.
+// descriptors in uniform registers and emit one predicated UTCHMMA (a plain `lane == 0` predicate becomes an ELECT / BRA.U.ANY loop:
+// 72 cycles per issue).  With pre-built descriptors an M128 N64 K16 MMA then issues every 48 cycles — its shared-memory operand floor
+// (profiles/umma_probe.cu).  elect.sync picks the same leader for the same member mask every time, so the MMAs and the
+// tcgen05.commit that tracks them come from one thread.
 __device__ __forceinline__ void umma_bf16_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t"
