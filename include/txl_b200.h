@@ -73,6 +73,7 @@ int txl_posemb_table(void* out, int klen, int clamp_len, int d, int dtype, float
  *   transA=0: A is [M,K] (lda>=K); transA=1: A is stored [K,M] (lda>=M)
  *   transB=0: B is [K,N] (ldb>=N); transB=1: B is stored [N,K] (ldb>=K)   (nn.Linear weight => transB=1)
  * epilogue: v = acc; if bias: v += bias[n]; if (flags&RELU) v = max(v,0); if (flags&MASK_POS) v *= (aux[m,n]>0);
+ *           if (flags&MASK_LIVE) v *= bit(live_bits, m, n)   (the same mask at one bit per element, written by the forward GEMM's EMIT_LIVE);
  *           if (flags&MASK_SCALE) v *= 1/(1-drop_p)   (aux is a post-dropout activation: its zeros already are the dropout mask,
  *                                                       so the backward of relu+dropout needs no second hash pass);
  *           if (flags&DROPOUT) v = inverted-dropout(v); if (flags&ACCUM) v += C[m,n];  C = (dtype_c) v
@@ -85,6 +86,8 @@ int txl_posemb_table(void* out, int klen, int clamp_len, int d, int dtype, float
 #define TXL_EPI_DROPOUT 8
 #define TXL_EPI_BIAS_ROW 16   /* bias is indexed by the output ROW m (used with TRANSPOSE: y^T = W x^T + b) */
 #define TXL_EPI_MASK_SCALE 64 /* with MASK_POS: also scale by 1/(1-drop_p) (aux = post-dropout activation) */
+#define TXL_EPI_EMIT_LIVE 128  /* also WRITE live_bits: bit = (final v > 0) — the backward mask of relu(+dropout) at 1 bit per element */
+#define TXL_EPI_MASK_LIVE 256  /* v *= live_bits bit (instead of MASK_POS's aux > 0); combines with MASK_SCALE */
 #define TXL_EPI_TRANSPOSE 32  /* store C transposed: C[n*ldc + m]  (decode: features are the GEMM's M so 128-row MMA tiles stay full) */
 typedef struct {
   const float* bias;     /* [N] or NULL */
@@ -92,6 +95,7 @@ typedef struct {
   float* colsum;         /* [N] fp32 accumulate or NULL */
   float drop_p; uint64_t seed; uint32_t site;
   int flags;
+  uint32_t* live_bits;   /* [ceil(N/32), M] words, bit n%32 of word [n/32][m] <-> element (m,n); EMIT_LIVE overwrites every word, MASK_LIVE reads */
 } TxlEpilogue;
 int txl_gemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K,
              int64_t lda, int64_t ldb, int64_t ldc, int transA, int transB,

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libtxl_b200.so')
 
 F32, BF16 = 0, 1
-EPI_RELU, EPI_ACCUM, EPI_MASK_POS, EPI_DROPOUT, EPI_BIAS_ROW, EPI_TRANSPOSE, EPI_MASK_SCALE = 1, 2, 4, 8, 16, 32, 64
+EPI_RELU, EPI_ACCUM, EPI_MASK_POS, EPI_DROPOUT, EPI_BIAS_ROW, EPI_TRANSPOSE, EPI_MASK_SCALE, EPI_EMIT_LIVE, EPI_MASK_LIVE = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 
 class TxlError(RuntimeError):
@@ -27,7 +27,7 @@ class TxlBand(C.Structure):
 
 class TxlEpilogue(C.Structure):
     _fields_ = [('bias', C.c_void_p), ('aux', C.c_void_p), ('colsum', C.c_void_p), ('drop_p', C.c_float),
-                ('seed', C.c_uint64), ('site', C.c_uint32), ('flags', C.c_int)]
+                ('seed', C.c_uint64), ('site', C.c_uint32), ('flags', C.c_int), ('live_bits', C.c_void_p)]
 
 
 class TxlAttnDims(C.Structure):

@@ -73,8 +73,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
       if (epi.bias) v += (epi.flags & TXL_EPI_BIAS_ROW) ? epi.bias[gm] : epi.bias[gn];
       if (epi.flags & TXL_EPI_RELU) v = fmaxf(v, 0.f);
       if (epi.flags & TXL_EPI_MASK_POS) v = to_f32(((const TC*)epi.aux)[gm * ldc + gn]) > 0.f ? v : 0.f;
+      if (epi.flags & TXL_EPI_MASK_LIVE) v = ((epi.live_bits[(gn >> 5) * M + gm] >> (gn & 31)) & 1u) ? v : 0.f;
       if (epi.flags & TXL_EPI_MASK_SCALE) v *= inv_keep;
       if (epi.flags & TXL_EPI_DROPOUT) v *= dropout_scale(epi.seed, epi.site, (uint64_t)(gm * N + gn), epi.drop_p, inv_keep);
+      if ((epi.flags & TXL_EPI_EMIT_LIVE) && v > 0.f) atomicOr(&epi.live_bits[(gn >> 5) * M + gm], 1u << (gn & 31));   // plane zeroed by the host wrapper
       cs[j] += v;
       const int64_t ci = (epi.flags & TXL_EPI_TRANSPOSE) ? gn * ldc + gm : gm * ldc + gn;
       if (epi.flags & TXL_EPI_ACCUM) v += to_f32(C[ci]);
@@ -99,16 +101,20 @@ extern "C" int txl_gemm(const void* A, const void* B, void* C, int64_t M, int64_
   TXL_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm: null pointer or empty shape (M=%ld N=%ld K=%ld)", (long)M, (long)N, (long)K);
   TXL_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= ((epi_in && (epi_in->flags & TXL_EPI_TRANSPOSE)) ? M : N), "gemm: leading dimension too small");
   TxlEpilogue epi;
-  if (epi_in) epi = *epi_in; else { epi.bias = nullptr; epi.aux = nullptr; epi.colsum = nullptr; epi.drop_p = 0.f; epi.seed = 0; epi.site = 0; epi.flags = 0; }
+  if (epi_in) epi = *epi_in; else { epi.bias = nullptr; epi.aux = nullptr; epi.colsum = nullptr; epi.drop_p = 0.f; epi.seed = 0; epi.site = 0; epi.flags = 0; epi.live_bits = nullptr; }
   if ((epi.flags & TXL_EPI_DROPOUT) && !(epi.drop_p > 0.f)) epi.flags &= ~TXL_EPI_DROPOUT;
   TXL_CHECK_ARG(!(epi.flags & TXL_EPI_MASK_POS) || epi.aux, "gemm: MASK_POS needs aux");
-  TXL_CHECK_ARG(!(epi.flags & TXL_EPI_MASK_SCALE) || ((epi.flags & TXL_EPI_MASK_POS) && epi.drop_p >= 0.f && epi.drop_p < 1.f), "gemm: MASK_SCALE needs MASK_POS and 0 <= drop_p < 1");
+  TXL_CHECK_ARG(!(epi.flags & (TXL_EPI_EMIT_LIVE | TXL_EPI_MASK_LIVE)) || epi.live_bits, "gemm: EMIT_LIVE / MASK_LIVE need live_bits");
+  TXL_CHECK_ARG(!((epi.flags & TXL_EPI_EMIT_LIVE) && (epi.flags & (TXL_EPI_MASK_LIVE | TXL_EPI_ACCUM))), "gemm: EMIT_LIVE cannot be combined with MASK_LIVE or ACCUM");
+  TXL_CHECK_ARG(!(epi.flags & TXL_EPI_MASK_SCALE) || ((epi.flags & (TXL_EPI_MASK_POS | TXL_EPI_MASK_LIVE)) && epi.drop_p >= 0.f && epi.drop_p < 1.f),
+                "gemm: MASK_SCALE needs MASK_POS or MASK_LIVE and 0 <= drop_p < 1");
   if (dtype_ab == TXL_BF16) {
     int handled = 0;
     int rc = txl_gemm_tc(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, dtype_c, &epi, stream, &handled);
     if (rc != TXL_OK) return rc;
     if (handled) return TXL_OK;
   }
+  if (epi.flags & TXL_EPI_EMIT_LIVE) TXL_CUDA(cudaMemsetAsync(epi.live_bits, 0, (size_t)cdiv64(N, 32) * M * sizeof(uint32_t), (cudaStream_t)stream));   // set with atomicOr below
   dim3 grid((unsigned)cdiv64(N, BN), (unsigned)cdiv64(M, BM));
   float ik = (epi.flags & (TXL_EPI_DROPOUT | TXL_EPI_MASK_SCALE)) ? 1.f / (1.f - epi.drop_p) : 1.f;
   cudaStream_t st = (cudaStream_t)stream;

@@ -290,6 +290,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int half = 0; half < 2; ++half) {
           const int c = bi * 2 + half;
           float v[32];
+          // MASK_LIVE: this thread's 32 mask bits are one word of the [N/32][M] bit plane (lanes = consecutive rows: one coalesced 128-byte
+          // read per warp instead of 32 x 64 bytes of the activation); requested before the accumulator is read
+          uint32_t live_word = 0xFFFFFFFFu;
+          if ((e.flags & TXL_EPI_MASK_LIVE) && row_ok && blk_col0 + half * 32 < p.N) live_word = __ldg(e.live_bits + ((blk_col0 + half * 32) >> 5) * p.M + row);
           tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
           tmem_ld_wait();
           if (bi + 2 >= NBLK && half == 1) {   // this warp's last read of the accumulator: hand TMEM back to the MMA warp
@@ -321,6 +325,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int i = 0; i < 32; ++i)
                   if (col0 + i < p.N) v[i] = to_f32(reinterpret_cast<const TC*>(e.aux)[row * p.ldc + col0 + i]) > 0.f ? v[i] : 0.f;
               }
+            }
+            if (e.flags & TXL_EPI_MASK_LIVE) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = ((live_word >> i) & 1u) ? v[i] : 0.f;
             }
             const bool col_bias = e.bias && !(e.flags & TXL_EPI_BIAS_ROW);
             const float brow = (e.bias && (e.flags & TXL_EPI_BIAS_ROW) && row_ok) ? e.bias[row] : 0.f;
@@ -364,6 +372,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = (row_ok && col0 + i < p.N) ? v[i] : 0.f;
+            if ((e.flags & TXL_EPI_EMIT_LIVE) && row_ok) {      // one word per (row, 32 columns); columns >= N are zero bits
+              uint32_t w = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) w |= (v[i] > 0.f ? 1u : 0u) << i;
+              e.live_bits[(col0 >> 5) * p.M + row] = w;
+            }
             if (e.colsum) {
               float t[32];
 #pragma unroll
@@ -503,6 +517,7 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
   const int csz = dtype_c == TXL_F32 ? 4 : 2;
   if (!al16(A) || !al16(B) || !al16(C) || (lda % 8) || (ldb % 8) || ((ldc * csz) % 16) || K < 16 || N < 8) return TXL_OK;
   if ((epi->flags & TXL_EPI_MASK_POS) && !epi->aux) return TXL_OK;
+  if ((epi->flags & (TXL_EPI_EMIT_LIVE | TXL_EPI_MASK_LIVE)) && (!epi->live_bits || (epi->flags & (TXL_EPI_ACCUM | TXL_EPI_TRANSPOSE)))) return TXL_OK;
   if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return TXL_OK;
 
   GemmParams p;

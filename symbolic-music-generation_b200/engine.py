@@ -108,12 +108,14 @@ def forward(cfg, W: List[LayerW], E, out_bias, ids, mems_bm, labels_shift, *, dr
         vec, lse, att_saved = att if save else (att[0], att[1], None)
         ao = ops.gemm(vec, w.o, transB=True)
         y1, z1, mean1, rstd1 = ops.add_ln_fwd(x, ao, w.ln1_w, w.ln1_b, cfg.layer_norm_epsilon, drop_p, seed, site + S_ATTN_OUT, save)
-        h = ops.gemm(y1, w.w1, transB=True, bias=w.b1, relu=True, drop_p=drop_p, seed=seed, site=site + S_FF_INNER)
+        # the backward mask of dropout(relu(.)) at one bit per element, written by the same epilogue ([di/32, N] words)
+        hbits = torch.empty((cfg.d_inner + 31) // 32, N, dtype=torch.int32, device=dev) if save else None
+        h = ops.gemm(y1, w.w1, transB=True, bias=w.b1, relu=True, drop_p=drop_p, seed=seed, site=site + S_FF_INNER, emit_live_bits=hbits)
         f = ops.gemm(h, w.w2, transB=True, bias=w.b2)
         y2, z2, mean2, rstd2 = ops.add_ln_fwd(y1, f, w.ln2_w, w.ln2_b, cfg.layer_norm_epsilon, drop_p, seed, site + S_FF_OUT, save)
         if save:
             sv.layers.append(dict(x=x, qkv=qkv, kvm=kvm if mems_real else None, kvm_fwd=kvm, r=r, vec=vec, lse=lse, att_saved=att_saved, z1=z1, mean1=mean1,
-                                  rstd1=rstd1, y1=y1, h=h, z2=z2, mean2=mean2, rstd2=rstd2))
+                                  rstd1=rstd1, y1=y1, h=h, hbits=hbits, z2=z2, mean2=mean2, rstd2=rstd2))
         x = y2
     core = ops.dropout(x, drop_p, seed, SITE_FINAL) if drop_p > 0 else x
     # LM head: logits for every position; label shifting is done by the caller (labels_shift)
@@ -156,7 +158,7 @@ def backward(cfg, W: List[LayerW], G: List[LayerW], E, gE, g_out_bias, sv: Saved
         dy1, df = ops.add_ln_bwd(dx, s['z2'], w.ln2_w, s['mean2'], s['rstd2'], gw.ln2_w, gw.ln2_b, drop_p=p, seed=seed, site=site + S_FF_OUT, dy2=dx2)
         ops.colsum(df, gw.b2)
         ops.gemm(df, s['h'], transA=True, out=gw.w2, accumulate=True)                                 # dW2 += df^T h
-        dh_ = ops.gemm(df, w.w2, mask_pos_aux=s['h'], colsum=gw.b1, drop_p=p, seed=seed, site=site + S_FF_INNER, aux_is_dropped=True)   # (N, di)
+        dh_ = ops.gemm(df, w.w2, mask_live_bits=s['hbits'], colsum=gw.b1, drop_p=p, seed=seed, site=site + S_FF_INNER)   # (N, di)
         ops.gemm(dh_, s['y1'], transA=True, out=gw.w1, accumulate=True)                               # dW1 += dh^T y1
         dff = ops.gemm(dh_, w.w1)                                                                     # dh W1  (N, d)
         del dh_, df

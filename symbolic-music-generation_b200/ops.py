@@ -68,7 +68,7 @@ def posemb_table(klen, clamp_len, d, dtype, device, drop_p=0.0, seed=0, site=0):
 # ----------------------------------------------------------------------------- GEMM
 def gemm(A, B, *, transA=False, transB=False, out=None, out_dtype=None, bias=None, relu=False, accumulate=False,
          mask_pos_aux=None, colsum=None, drop_p=0.0, seed=0, site=0, M=None, N=None, K=None, bias_row=False, transpose_out=False,
-         aux_is_dropped=False):
+         aux_is_dropped=False, emit_live_bits=None, mask_live_bits=None):
     """C = epi(op(A) op(B)).  A, B are 2-D row-major tensors (possibly column-sliced views: stride(0) is the ld)."""
     assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1
     if M is None:
@@ -84,10 +84,19 @@ def gemm(A, B, *, transA=False, transB=False, out=None, out_dtype=None, bias=Non
     if mask_pos_aux is not None:
         flags |= L.EPI_MASK_POS
         assert mask_pos_aux.dtype == out.dtype and mask_pos_aux.stride(0) == out.stride(0)
+    bits = None
+    if emit_live_bits is not None:       # forward of relu(+dropout): also write the 1-bit-per-element backward mask
+        bits, flags = emit_live_bits, flags | L.EPI_EMIT_LIVE
+    if mask_live_bits is not None:       # backward: mask from those bits (they already carry the dropout mask of the site)
+        assert mask_pos_aux is None and emit_live_bits is None
+        bits, flags = mask_live_bits, flags | L.EPI_MASK_LIVE
+    if bits is not None:
+        assert bits.dtype == torch.int32 and bits.is_contiguous() and bits.numel() >= ((N + 31) // 32) * M
     if drop_p > 0.0:
         # aux_is_dropped: aux is the forward's post-dropout activation, so (aux > 0) already carries this site's dropout mask
-        flags |= L.EPI_MASK_SCALE if (aux_is_dropped and mask_pos_aux is not None) else L.EPI_DROPOUT
-    epi = TxlEpilogue(ptr(bias), ptr(mask_pos_aux), ptr(colsum), float(drop_p), int(seed), int(site), flags)
+        masked = mask_pos_aux is not None or mask_live_bits is not None
+        flags |= L.EPI_MASK_SCALE if (masked and (aux_is_dropped or mask_live_bits is not None)) else L.EPI_DROPOUT
+    epi = TxlEpilogue(ptr(bias), ptr(mask_pos_aux), ptr(colsum), float(drop_p), int(seed), int(site), flags, ptr(bits))
     check(_lib().txl_gemm(ptr(A), ptr(B), ptr(out), M, N, K, A.stride(0), B.stride(0), out.stride(0), int(transA), int(transB),
                           dtype_code(A.dtype), dtype_code(out.dtype), C.byref(epi), stream_ptr()), 'gemm')
     return out

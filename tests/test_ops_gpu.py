@@ -54,6 +54,12 @@ def test_gemm_epilogues(ops):
     aux = torch.randn(100, 72, device='cuda')
     out = ops.gemm(A, B, transB=True, mask_pos_aux=aux)
     torch.testing.assert_close(out, (A @ B.t()) * (aux > 0), rtol=1e-4, atol=1e-4)
+    # the relu(+dropout) mask as a bit plane [ceil(N/32), M]: emitted by the forward epilogue, consumed by the backward one (fp32 SIMT path)
+    bits = torch.empty(3, 100, dtype=torch.int32, device='cuda')
+    hfw = ops.gemm(A, B, transB=True, bias=bias, relu=True, drop_p=0.25, seed=5, site=3, emit_live_bits=bits)
+    out2 = ops.gemm(A, B, transB=True, mask_live_bits=bits, drop_p=0.25, seed=5, site=3)
+    ref2 = ops.gemm(A, B, transB=True, mask_pos_aux=hfw, drop_p=0.25, seed=5, site=3, aux_is_dropped=True)
+    assert torch.equal(out2, ref2) and (out2 != 0).any()
     # strided views (column slices) as operands/outputs
     big = torch.zeros(100, 200, device='cuda')
     ops.gemm(A, B, transB=True, out=big[:, 64:136])

@@ -77,6 +77,15 @@ def test_tc_gemm_epilogues(ops):
     # backward of relu+dropout from the post-dropout activation: its zeros are the mask, only the 1/(1-p) scale is applied
     out = ops.gemm(A, B, transB=True, mask_pos_aux=aux, drop_p=0.25, seed=5, site=3, aux_is_dropped=True)
     torch.testing.assert_close(out.float(), ref0 * (aux.float() > 0) / 0.75, rtol=1e-2, atol=2e-2)
+    # the same mask at one bit per element: written by a forward GEMM (relu + dropout), read by the backward GEMM
+    bits = torch.empty((N + 31) // 32, M, dtype=torch.int32, device='cuda')
+    hfw = ops.gemm(A, B, transB=True, bias=bias, relu=True, drop_p=0.25, seed=5, site=3, emit_live_bits=bits)
+    words = bits.cpu().numpy().astype('uint32')                       # [N/32, M]
+    live = ((words[:, :, None] >> torch.arange(32).numpy()[None, None, :]) & 1).transpose(1, 0, 2).reshape(M, -1)[:, :N]
+    assert (torch.from_numpy(live.astype('bool')).cuda() == (hfw > 0)).all()
+    out2 = ops.gemm(A, B, transB=True, mask_live_bits=bits, drop_p=0.25, seed=5, site=3)
+    ref2 = ops.gemm(A, B, transB=True, mask_pos_aux=hfw, drop_p=0.25, seed=5, site=3, aux_is_dropped=True)
+    assert torch.equal(out2, ref2)
     d1 = ops.gemm(A, B, transB=True, drop_p=0.25, seed=5, site=3, out_dtype=torch.float32)
     os.environ['TXL_DISABLE_TC'] = '0'
     kept = d1 != 0
