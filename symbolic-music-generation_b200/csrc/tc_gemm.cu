@@ -50,7 +50,7 @@ int txl_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t r
 
 namespace {
 constexpr int BM = 128, BK = 64;
-constexpr int THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups of four lane-quadrant warps)
+constexpr int threads_for(int eg) { return 64 + eg * 128; }   // warp 0 TMA, warp 1 MMA, then EG epilogue groups of four lane-quadrant warps
 constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 constexpr int STAGE_C_BYTES = BM * 128;  // one 64-column bf16 block of the output tile, SWIZZLE_128B
 
@@ -67,15 +67,15 @@ struct GemmParams {
 
 // CG = 2: a CTA pair (cluster of two CTAs on one TPC) computes one 256 x BN tile with tcgen05.mma.cta_group::2 — each CTA stages its
 // own 128 rows of A and HALF of the B tile, so every byte pulled from L2 feeds twice the MMA work; the leader CTA (rank 0) issues.
-template <int BN, int STAGES, int CG = 1>
+template <int BN, int STAGES, int CG = 1, int EG = 2>
 struct Cfg {
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CSTAGE_OFF = STAGES * STAGE_BYTES;
   // output staging buffers per epilogue group: a TMA store takes ~1400-2400 cycles to finish READING its shared-memory source, so with
   // one buffer every 64-column block waits out a full store; the pair kernel has the room for two
-  static constexpr int NCST = CG == 2 ? 2 : 1;
-  static constexpr int BAR_OFF = CSTAGE_OFF + 2 * NCST * STAGE_C_BYTES;
+  static constexpr int NCST = (CG == 2 && EG == 2) ? 2 : 1;
+  static constexpr int BAR_OFF = CSTAGE_OFF + EG * NCST * STAGE_C_BYTES;
   static constexpr int SMEM = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -146,10 +146,10 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
 }
 
-template <int BN, int STAGES, typename TC, int CG>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int BN, int STAGES, typename TC, int CG, int EG>
+__global__ void __launch_bounds__(threads_for(EG), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using C_ = Cfg<BN, STAGES, CG>;
+  using C_ = Cfg<BN, STAGES, CG, EG>;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;      // 0 = leader of the pair (issues the MMAs)
   const int unit0 = (int)blockIdx.x / CG, unit_step = (int)gridDim.x / CG;
   extern __shared__ uint8_t smem_raw[];
@@ -164,7 +164,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8 * CG); }   // leader's tempty: epilogue warps of both CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * EG * CG); }   // leader's tempty: epilogue warps of both CTAs
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -278,7 +278,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       constexpr int NBLK = BN / 64;
 #pragma unroll 1
-      for (int bi = grp; bi < NBLK; bi += 2) {
+      for (int bi = grp; bi < NBLK; bi += EG) {
         const int64_t blk_col0 = (int64_t)tn * BN + bi * 64;
         if (p.tma_store) {
           if (leader) tma_store_wait_read<C_::NCST - 1>();   // the store that last used this staging buffer has read it
@@ -296,7 +296,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if ((e.flags & TXL_EPI_MASK_LIVE) && row_ok && blk_col0 + half * 32 < p.N) live_word = __ldg(e.live_bits + ((blk_col0 + half * 32) >> 5) * p.M + row);
           tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
           tmem_ld_wait();
-          if (bi + 2 >= NBLK && half == 1) {   // this warp's last read of the accumulator: hand TMEM back to the MMA warp
+          if (bi + EG >= NBLK && half == 1) {   // this warp's last read of the accumulator: hand TMEM back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[acc]), 0)); else mbar_arrive(&tempty[acc]); }
@@ -478,26 +478,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) { if (CG == 2) tmem_dealloc_2sm<C_::TMEM_COLS>(tmem_base); else tmem_dealloc<C_::TMEM_COLS>(tmem_base); }
 }
 
-template <int BN, int STAGES, typename TC, int CG = 1>
+template <int BN, int STAGES, typename TC, int CG = 1, int EG = 2>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int grid, cudaStream_t st) {
-  using C_ = Cfg<BN, STAGES, CG>;
+  using C_ = Cfg<BN, STAGES, CG, EG>;
   static_assert(C_::SMEM <= 232448, "GEMM shared-memory plan exceeds 227 KB");
   static bool attr_set = false;
   if (!attr_set) {
-    TXL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, TC, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
+    TXL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, TC, CG, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
     attr_set = true;
   }
   if (CG == 1) {
-    tc_gemm_kernel<BN, STAGES, TC, CG><<<grid, THREADS, C_::SMEM, st>>>(tmA, tmB, tmC, p);
+    tc_gemm_kernel<BN, STAGES, TC, CG, EG><<<grid, threads_for(EG), C_::SMEM, st>>>(tmA, tmB, tmC, p);
   } else {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C_::SMEM; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads_for(EG)); cfg.dynamicSmemBytes = C_::SMEM; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     ++g_txl_launches;
-    TXL_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, STAGES, TC, CG>, tmA, tmB, tmC, p));
+    TXL_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, STAGES, TC, CG, EG>, tmA, tmB, tmC, p));
     return TXL_OK;
   }
   TXL_LAUNCH_CHECK();
@@ -529,8 +529,14 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
   // CTA pairs (cta_group::2, 256 x 256 tiles) for the big training shapes; TXL_GEMM_2SM=0 switches them off
   static int use_2sm = -1;
   if (use_2sm < 0) { const char* e = getenv("TXL_GEMM_2SM"); use_2sm = (e && e[0] == '0') ? 0 : 1; }
-  // (short-K shapes are bound by the epilogue, not the operand stream: measured at K = 512 the pair kernel only ties the single-CTA one)
-  const int CG = (use_2sm && BN == 256 && M >= 512 && K >= 1024 && !(epi->flags & TXL_EPI_TRANSPOSE)) ? 2 : 1;
+  // Short-K (K < 1024) bf16-output shapes are bound by the epilogue (bias / ReLU / mask / dropout / column sums per element, staging, store):
+  // they run on the pair kernel with FOUR epilogue groups (16 epilogue warps, one 64-column block each): +16..28 % on the cfg2 shapes.
+  // Long-K and split-K launches measured 2-4 % slower that way and keep two groups.  TXL_GEMM_EG4=0 switches the variant off.
+  static int eg4 = -1;
+  if (eg4 < 0) { const char* e = getenv("TXL_GEMM_EG4"); eg4 = (e && e[0] == '0') ? 0 : 1; }
+  const bool pair_ok = use_2sm && BN == 256 && M >= 512 && !(epi->flags & TXL_EPI_TRANSPOSE);
+  const bool short_k_eg4 = pair_ok && eg4 && K < 1024 && dtype_c == TXL_BF16;
+  const int CG = (pair_ok && (K >= 1024 || short_k_eg4)) ? 2 : 1;
   p.tiles_m = (int)cdiv64(M, BM * CG); p.tiles_n = (int)cdiv64(N, BN);
   p.nkb = (int)cdiv64(K, BK);
   p.ksplits = 1;
@@ -562,7 +568,9 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
   const int total = tiles * p.ksplits;
   const int grid = (total < workers ? total : workers) * CG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (CG == 2) {
+  if (short_k_eg4) {
+    rc = launch<256, 5, bf16, 2, 4>(tmA, tmB, tmC, p, grid, st);
+  } else if (CG == 2) {
     if (dtype_c == TXL_F32) rc = launch<256, 5, float, 2>(tmA, tmB, tmC, p, grid, st); else rc = launch<256, 5, bf16, 2>(tmA, tmB, tmC, p, grid, st);
   } else if (BN == 256) {
     if (dtype_c == TXL_F32) rc = launch<256, 4, float>(tmA, tmB, tmC, p, grid, st); else rc = launch<256, 4, bf16>(tmA, tmB, tmC, p, grid, st);
