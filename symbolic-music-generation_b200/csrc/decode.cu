@@ -67,6 +67,69 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_attn_kernel(const T* __res
   float qwv[8], qrv[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { qwv[k] = qw[ch * 8 + k]; qrv[k] = qr[ch * 8 + k]; }
+  if constexpr (sizeof(T) == 2) {
+    // bf16: ONE pass over the ring (flash-decoding): K, R and V rows of a key are requested together, every lane group keeps a running
+    // (max, sum, partial output) and the groups are merged at the end — no second sweep that has to wait for the soft-max, so all
+    // loads of the step are independent and in flight together.  (fp32 keeps the two-pass form below: bit-for-bit soft-max order.)
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 4
+    for (int s0 = warp * KPW; s0 < ML; s0 += (DEC_THREADS / 32) * KPW) {
+      const int s = s0 + sub;
+      const bool ok = s < ML;
+      float a = 0.f, vf[8];
+      if (ok) {
+        int dist = cur - s; if (dist < 0) dist += ML;
+        float kf[8], rf[8];
+        load8(K + (int64_t)s * DH + ch * 8, kf);
+        load8(r + (int64_t)(ML - dist) * HD + h * DH + ch * 8, rf);
+        load8(V + (int64_t)s * DH + ch * 8, vf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a = fmaf(qwv[k], kf[k], fmaf(qrv[k], rf[k], a));
+      }
+#pragma unroll
+      for (int o = LPK / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (ok) {
+        a *= scale;
+        const float mn = fmaxf(m, a), c = __expf(m - mn), p = __expf(a - mn);
+        l = l * c + p;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(acc[k], c, p * vf[k]);
+        m = mn;
+      }
+    }
+    // merge the KPW key groups of the warp ...
+#pragma unroll
+    for (int o = LPK; o < 32; o <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+      const float mn = fmaxf(m, m2);
+      const float c1 = (m == -INFINITY) ? 0.f : __expf(m - mn), c2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+      l = l * c1 + l2 * c2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = acc[k] * c1 + __shfl_xor_sync(0xffffffffu, acc[k], o) * c2;
+      m = mn;
+    }
+    // ... then the warps through shared memory
+    float* wm = red + (DEC_THREADS / 32) * DH; float* wl = wm + DEC_THREADS / 32;
+    if (sub == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[warp * DH + ch * 8 + k] = acc[k];
+      if (ch == 0) { wm[warp] = m; wl[warp] = l; }
+    }
+    __syncthreads();
+    if (tid < DH) {
+      float M = -INFINITY;
+      for (int w = 0; w < DEC_THREADS / 32; ++w) M = fmaxf(M, wm[w]);
+      float L = 0.f, o = 0.f;
+      for (int w = 0; w < DEC_THREADS / 32; ++w) {
+        const float c = (wm[w] == -INFINITY) ? 0.f : __expf(wm[w] - M);
+        L += wl[w] * c; o += red[w * DH + tid] * c;
+      }
+      out[(int64_t)b * HD + h * DH + tid] = from_f32<T>(o / L);
+    }
+    return;
+  }
 #pragma unroll 4
   for (int s0 = warp * KPW; s0 < ML; s0 += (DEC_THREADS / 32) * KPW) {
     const int s = s0 + sub;
@@ -268,7 +331,7 @@ extern "C" int txl_decode_attn(const void* qkv, void* kc, void* vc, const void* 
   TXL_CHECK_ARG(qkv && kc && vc && r && rwb && rrb && out && pos && B > 0 && H > 0 && ML > 0, "decode_attn: bad args");
   TXL_CHECK_ARG(dh == 32 || dh == 64 || dh == 128, "decode_attn: d_head %d not in {32,64,128}", dh);
   dim3 grid(H, B);
-  size_t smem = ((size_t)ML + 2 * dh + (DEC_THREADS / 32) * dh) * sizeof(float);
+  size_t smem = ((size_t)ML + 2 * dh + (DEC_THREADS / 32) * dh + 2 * (DEC_THREADS / 32)) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
 #define DEC_LAUNCH(DHV)                                                                                                                   \
   {                                                                                                                                       \
