@@ -21,4 +21,4 @@ def tm(fn, n=20):
 f = tm(lambda: ops.add_ln_fwd(x, r, g, b, 1e-5, 0.1, 1, 3, True))
 bw = tm(lambda: ops.add_ln_bwd(dy, z, g, mean, rstd, dg, db, drop_p=0.1, seed=1, site=3, dy2=dy2))
 mb = N * d * 2 / 1e6
-print(f'add_ln_fwd {f:7.1f} us  ({4 * mb / f * 1e-3:5.2f} TB/s of x,r -> y,z)   add_ln_bwd {bw:7.1f} us  ({5 * mb / bw * 1e-3:5.2f} TB/s of dy,dy2,z -> dx,dr)')
+print(f'add_ln_fwd {f:7.1f} us  ({4 * mb / f:5.2f} TB/s of x,r -> y,z)   add_ln_bwd {bw:7.1f} us  ({5 * mb / bw:5.2f} TB/s of dy,dy2,z -> dx,dr)')

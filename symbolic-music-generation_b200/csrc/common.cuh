@@ -100,6 +100,17 @@ __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t site, uin
   return u >= dropout_threshold(p) ? inv_keep : 0.0f;
 }
 
+// keep-scales of 8 consecutive elements starting at the EVEN index idx0 (4 hashes instead of 8, key and threshold formed once)
+__device__ __forceinline__ void dropout_scale8(uint32_t key, uint32_t thr, uint64_t idx0, float inv_keep, float* sc) {
+  const uint64_t pair0 = idx0 >> 1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t h = dropout_hash(key, pair0 + j);
+    sc[2 * j] = (h & 0xFFFFu) >= thr ? inv_keep : 0.0f;
+    sc[2 * j + 1] = (h >> 16) >= thr ? inv_keep : 0.0f;
+  }
+}
+
 // ------------------------------------------------------------------ warp reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -163,12 +163,13 @@ template <typename T> __device__ __forceinline__ void st8(T* p, const float* f) 
 template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f32(from_f32<T>(v)); }
 
 template <typename T, int STEPS>
-__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, (STEPS <= 2 ? 4 : 2)) add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ z, float* __restrict__ mean,
                                   float* __restrict__ rstd, int64_t rows, int d, float eps, float p, float inv_keep, uint64_t seed,
                                   uint32_t site) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
+  const uint32_t dkey = dropout_key(seed, site), dthr = dropout_threshold(p);
   for (int64_t row = warp; row < rows; row += (int64_t)gridDim.x * wpb) {
     float v[STEPS][LN_VEC];
     float s = 0.f;
@@ -176,13 +177,14 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ x
     for (int e = 0; e < STEPS; ++e) {
       const int c = (e * 32 + lane) * LN_VEC;
       if (c < d) {
-        float xv[LN_VEC], rv[LN_VEC];
+        float xv[LN_VEC], rv[LN_VEC], ks[LN_VEC];
         ld8(x + row * d + c, xv);
         if (r) ld8(r + row * d + c, rv);
+        if (p > 0.f) dropout_scale8(dkey, dthr, (uint64_t)(row * d + c), inv_keep, ks);
 #pragma unroll
         for (int k = 0; k < LN_VEC; ++k) {
           float rr = r ? rv[k] : 0.f;
-          if (p > 0.f) rr *= dropout_scale(seed, site, (uint64_t)(row * d + c + k), p, inv_keep);
+          if (p > 0.f) rr *= ks[k];
           v[e][k] = round_to<T>(xv[k] + rr);
           s += v[e][k];
         }
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(256, (STEPS <= 2 ? 2 : 1)) add_ln_bwd_kernel(c
                                   T* dr_out, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int d, float p,
                                   float inv_keep, uint64_t seed, uint32_t site) {
   extern __shared__ float sm[];  // [2][d] block partials
+  const uint32_t dkey = dropout_key(seed, site), dthr = dropout_threshold(p);
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
   for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
@@ -289,9 +292,10 @@ __global__ void __launch_bounds__(256, (STEPS <= 2 ? 2 : 1)) add_ln_bwd_kernel(c
 #pragma unroll
         for (int k = 0; k < LN_VEC; ++k) dz[k] = rs * (g[e][k] - s1 - xh[e][k] * s2);
         if (dr_out) {
-          float o[LN_VEC];
+          float o[LN_VEC], ks[LN_VEC];
+          if (p > 0.f) dropout_scale8(dkey, dthr, (uint64_t)(row * d + c), inv_keep, ks);
 #pragma unroll
-          for (int k = 0; k < LN_VEC; ++k) o[k] = dz[k] * (p > 0.f ? dropout_scale(seed, site, (uint64_t)(row * d + c + k), p, inv_keep) : 1.f);
+          for (int k = 0; k < LN_VEC; ++k) o[k] = dz[k] * (p > 0.f ? ks[k] : 1.f);
           st8(dr_out + row * d + c, o);
         }
         if (dx_out) {
