@@ -161,6 +161,11 @@ int txl_logsoftmax_nll_bwd(const void* logits, int64_t ldl, int dtype, void* dlo
                            const float* lse, const float* grow, int64_t N, int V, void* stream);
 /* loss = mean(losses[losses != 0]) and grow[n] = g_loss/cnt * (losses[n]!=0) + g_losses[n]  (transformer_xl.py:197-200) */
 int txl_masked_mean(const float* losses, int64_t N, float* loss_out, float* count_out, void* stream);
+/* Next-token-prediction accuracy counts  [reference train_util_wrap.py:113-120, train.py:279-284; SURVEY §8f-2]
+ * preds  [B, T] int64: greedy prediction made AT each position (the fused argmax of txl_logsoftmax_nll_fwd), row stride ld_preds
+ * labels [B, T] int64 (-100 = pad).  Position t predicts token t+1:  out[0] += #{(b,t<T-1): labels[b,t+1] != -100 and preds[b,t] == labels[b,t+1]},
+ * out[1] += #{labels[b,t+1] != -100}.  out is int64[2] on the device (accumulated: zero it per logging window). */
+int txl_ntp_acc(const int64_t* preds, int64_t ld_preds, const int64_t* labels, int64_t ld_labels, int B, int T, int64_t* out, void* stream);
 
 /* ---- parameters --------------------------------------------------------------------------------- */
 int txl_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -434,3 +434,12 @@ class RefTransfoXLLMHeadModel(nn.Module):
 def expected_param_count(L, d, di, V):
     """Appendix A.8 closed form; KAT: (12, 768, 3072, 418) -> 92,435,362 (log says 92.4M)."""
     return L * (3 * d * d + 2 * d * d + 2 * d + 2 * d + d * di + di + di * d + d + 2 * d) + V * d + V
+
+
+def ntp_acc_counts(preds, labels, pad=-100):
+    """(matches, non-pad count) of next-token prediction: `preds[:, :-1]` vs `labels[:, 1:]` over `labels != -100`.
+    Follows reference musicnlp/util/train/train_util_wrap.py:113-120 (training) and musicnlp/trainer/train.py:279-284 (eval,
+    `clm_pred_shifted=False`): ntp_acc = matches / count."""
+    p, l = preds[:, :-1], labels[:, 1:]
+    msk = l != pad
+    return int((p[msk] == l[msk]).sum().item()), int(msk.sum().item())

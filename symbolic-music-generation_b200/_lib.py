@@ -59,6 +59,7 @@ SIGNATURES = {
     'txl_logsoftmax_nll_fwd': (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     'txl_logsoftmax_nll_bwd': (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp]),
     'txl_masked_mean': (_i, [_vp, _i64, _vp, _vp, _vp]),
+    'txl_ntp_acc': (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp]),
     'txl_cast_f32_to_bf16': (_i, [_vp, _vp, _i64, _vp]),
     'txl_cast_bf16_to_f32': (_i, [_vp, _vp, _i64, _vp]),
     'txl_transpose': (_i, [_vp, _vp, _i64, _i64, _i, _vp]),

@@ -505,6 +505,29 @@ extern "C" int txl_masked_mean(const float* losses, int64_t N, float* loss_out, 
   return TXL_OK;
 }
 
+// next-token-prediction accuracy counts: position t predicts token t+1; pads (-100) are not counted
+__global__ void ntp_acc_kernel(const int64_t* __restrict__ preds, int64_t ldp, const int64_t* __restrict__ labels, int64_t ldl, int B, int T,
+                               unsigned long long* __restrict__ out) {
+  unsigned long long hit = 0, cnt = 0;
+  const int64_t total = (int64_t)B * (T - 1);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / (T - 1), t = i % (T - 1);
+    const int64_t lab = labels[b * ldl + t + 1];
+    if (lab != -100) { ++cnt; hit += (preds[b * ldp + t] == lab) ? 1ull : 0ull; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { hit += __shfl_xor_sync(0xffffffffu, hit, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  if ((threadIdx.x & 31) == 0 && cnt) { atomicAdd(&out[0], hit); atomicAdd(&out[1], cnt); }
+}
+extern "C" int txl_ntp_acc(const int64_t* preds, int64_t ld_preds, const int64_t* labels, int64_t ld_labels, int B, int T, int64_t* out, void* stream) {
+  TXL_CHECK_ARG(preds && labels && out && B > 0 && T > 0 && ld_preds >= T && ld_labels >= T, "ntp_acc: bad args");
+  if (T < 2) return TXL_OK;
+  const int grid = (int)imin64(cdiv64((int64_t)B * (T - 1), 256), (int64_t)txl_num_sms() * 4);
+  ntp_acc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(preds, ld_preds, labels, ld_labels, B, T, reinterpret_cast<unsigned long long*>(out));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
 // ------------------------------------------------------------------ casts / transposes / layout
 __global__ void cast_f2b_kernel(const float* __restrict__ s, bf16* __restrict__ d, int64_t n) {
   int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;

@@ -197,7 +197,7 @@ class _TxlStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, ids, labels_shift, mems_bm, seed, drop_p, want_logprobs, *params):
         out = engine.forward(model.config, model._W, model._E, model._out_bias, ids, mems_bm, labels_shift, drop_p=drop_p, seed=seed,
-                             save=True, want_logprobs=want_logprobs, zero_kvm=model._zero_kvm)
+                             save=True, want_logprobs=want_logprobs, want_argmax=model.monitor_greedy, zero_kvm=model._zero_kvm)
         ctx.model, ctx.sv = model, out['saved']
         model._last = out
         B, T = ids.shape
@@ -263,6 +263,10 @@ class MyTransfoXLLMHeadModel(nn.Module):
         self._last = None
         self._zeros = {}
         self._step_seed = 0
+        # with monitor_greedy the LM-head kernel also emits the greedy id of every position (`last_greedy`), so the trainer's
+        # `outputs.logits.argmax(-1)` (train_util_wrap.py:106) / `preprocess_logits_for_metrics` (train.py:248) needs no (B,T,V) tensor
+        self.monitor_greedy = False
+        self.last_greedy = None
         if device is not None:
             self.to(device)
 
@@ -559,11 +563,13 @@ class MyTransfoXLLMHeadModel(nn.Module):
         else:
             with torch.no_grad():
                 out = engine.forward(self.config, self._W, self._E, self._out_bias, ids, mems_bm, labels_shift, drop_p=drop_p, seed=seed,
-                                     save=False, want_logprobs=want_logprobs, zero_kvm=self._zero_kvm)
+                                     save=False, want_logprobs=want_logprobs, want_argmax=self.monitor_greedy, zero_kvm=self._zero_kvm)
             loss = out['loss']
             losses = out['losses'].view(bsz, tgt_len)[:, :tgt_len - 1] if labels is not None else None
             logprobs = out['logprobs']
         new_mems = self._new_mems(mems_bm, out['hid_in'], bsz, tgt_len)
+        # greedy ids of every position, straight from the LM-head kernel (what `logits.argmax(-1)` is in train_util_wrap.py:106 / train.py:248)
+        self.last_greedy = out['argmax'].view(bsz, tgt_len) if out.get('argmax') is not None else None
         self._last = None
         prediction_scores = logprobs.view(bsz, tgt_len, -1) if want_logprobs else ()
         if labels is None:
@@ -579,6 +585,17 @@ class MyTransfoXLLMHeadModel(nn.Module):
             return (output + (loss,)) if loss is not None else output
         return TransfoXLLMHeadModelOutput(loss=loss, prediction_scores=prediction_scores, losses=losses, mems=new_mems,
                                           hidden_states=None, attentions=None)
+
+    def ntp_acc_counts(self, labels, out=None):
+        """int64[2] device tensor (matches, non-pad positions) of next-token prediction for the last forward (needs monitor_greedy=True):
+        preds[:, :-1] vs labels[:, 1:] over labels != -100 — the reference's `ntp_acc` = out[0] / out[1]
+        (train_util_wrap.py:113-120, train.py:279-284).  Accumulates into `out` when given; no host sync."""
+        if self.last_greedy is None:
+            raise TxlError('ntp_acc_counts: set model.monitor_greedy = True before the forward')
+        lab = labels.to(self.last_greedy.device, non_blocking=True).long().contiguous()
+        if tuple(lab.shape) != tuple(self.last_greedy.shape):
+            raise RuntimeError('labels must have the shape of the last input_ids')
+        return ops.ntp_acc(self.last_greedy, lab, out)
 
     # ------------------------------------------------------------------ generation surface (reference :223-241)
     def prepare_inputs_for_generation(self, input_ids, past=None, **model_kwargs):

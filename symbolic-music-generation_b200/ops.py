@@ -191,6 +191,16 @@ def logsoftmax_nll_bwd(logits, V, labels, lse, grow, out_dtype=None):
     return out
 
 
+def ntp_acc(preds, labels, out=None):
+    """(matches, non-pad count) of next-token prediction, accumulated into the int64[2] device tensor `out` (created zeroed if None)."""
+    assert preds.dtype == torch.int64 and labels.dtype == torch.int64 and preds.shape == labels.shape and preds.dim() == 2
+    assert preds.stride(1) == 1 and labels.stride(1) == 1
+    if out is None:
+        out = torch.zeros(2, dtype=torch.int64, device=preds.device)
+    check(_lib().txl_ntp_acc(ptr(preds), preds.stride(0), ptr(labels), labels.stride(0), preds.shape[0], preds.shape[1], ptr(out), stream_ptr()), 'ntp_acc')
+    return out
+
+
 def masked_mean(losses):
     out = torch.empty(2, dtype=torch.float32, device=losses.device)
     check(_lib().txl_masked_mean(ptr(losses), losses.numel(), ptr(out[0:1]), ptr(out[1:2]), stream_ptr()), 'masked_mean')

@@ -248,3 +248,29 @@ def test_cfg2_shapes_one_layer_bf16_tensor_core_path(pkg):
         lg = model(input_ids=ids.cuda(), mems=[m.cuda() for m in mems]).logits.float().cpu()
         lr = ref(input_ids=ids, mems=mems).logits
     assert ((lg - lr).abs() / lr.abs()).max().item() < 1e-2
+
+
+def test_monitor_greedy_and_ntp_acc_fp32(pkg):
+    """with monitor_greedy the training forward also yields `logits.argmax(-1)` (train_util_wrap.py:106) without the
+    (B,T,V) tensor, and `ntp_acc_counts` reproduces the reference's shifted, pad-masked accuracy (:113-120)."""
+    from oracle.txl_ref import ntp_acc_counts
+    ref, model = make_pair(pkg, 'fp32')
+    ids, labels = _batch(422, 3, 48)
+    ref.eval()
+    with torch.no_grad():
+        ro = ref(input_ids=ids, labels=labels.clone())     # eval mode: log-probs of every position (dropout is 0 in make_pair)
+    preds = ro.logits.argmax(-1)
+    model.train()
+    model.monitor_greedy = True
+    out = model(input_ids=ids.cuda(), labels=labels.cuda())
+    assert out.logits == () and model.last_greedy.shape == (3, 48)
+    # ties aside (none at fp32 with random weights) the greedy ids are the oracle's
+    assert torch.equal(model.last_greedy.cpu(), preds)
+    cnt = model.ntp_acc_counts(labels)
+    assert cnt.tolist() == list(ntp_acc_counts(preds, labels))
+    out.loss.backward()
+    model.monitor_greedy = False
+    model(input_ids=ids.cuda(), labels=labels.cuda())
+    assert model.last_greedy is None
+    with pytest.raises(pkg.TxlError):
+        model.ntp_acc_counts(labels)

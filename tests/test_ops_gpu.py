@@ -346,3 +346,25 @@ def test_relattn_tensor_core_vs_exact_fp32_kernels_full_band(ops):
             assert err < (2e-3 if n == 'lse' else 2e-2), (which, n, err)
     # every probability row sums to one: exp(score - lse) over the live band == 1 is implied by lse agreement; check O is a convex combination
     assert tc[0].abs().max() <= kvm[:, d:].float().abs().max() + 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,T', [(1, 1), (3, 2), (8, 513), (32, 1024)])
+def test_ntp_acc_counts_bit_exact(ops, B, T):
+    """shifted, pad-masked next-token accuracy counts == the oracle's (train_util_wrap.py:113-120), and they accumulate."""
+    from oracle.txl_ref import ntp_acc_counts
+    g = torch.Generator().manual_seed(77)
+    labels = torch.randint(0, 9, (B, T), generator=g)
+    preds = torch.randint(0, 9, (B, T), generator=g)
+    for b in range(0, B, 3):
+        labels[b, T - T // 4:] = -100
+    if B > 2:
+        labels[2, :] = -100
+    hit, cnt = ntp_acc_counts(preds, labels)
+    out = ops.ntp_acc(preds.cuda(), labels.cuda())
+    assert out.tolist() == [hit, cnt]
+    # strided views (a [B, T] window of a wider buffer) and accumulation into the same counters
+    wide = torch.full((B, T + 5), 3, dtype=torch.int64, device='cuda')
+    wide[:, :T] = preds.cuda()
+    out = ops.ntp_acc(wide[:, :T], labels.cuda(), out)
+    assert out.tolist() == [2 * hit, 2 * cnt]

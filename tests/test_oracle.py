@@ -121,3 +121,13 @@ def test_warpers_keep_sets():
     w = RefTransfoXLLMHeadModel.warp_scores(s, top_k=0, top_p=0.5)
     assert (w > -float('inf')).sum() == 2            # first token crossing p is kept
     torch.testing.assert_close(w.exp().sum(), torch.tensor(1.0))
+
+
+def test_ntp_acc_counts_known_answer():
+    """KAT by hand for the reference's shifted, pad-masked accuracy (train_util_wrap.py:113-120)."""
+    from oracle.txl_ref import ntp_acc_counts
+    preds = torch.tensor([[5, 6, 7, 0], [1, 1, 1, 1]])
+    labels = torch.tensor([[9, 5, 9, 7], [1, 1, -100, -100]])
+    # row 0: preds[:3] = 5,6,7 vs labels[1:] = 5,9,7 -> 2 of 3; row 1: preds[:3] = 1,1,1 vs 1,-100,-100 -> 1 of 1
+    assert ntp_acc_counts(preds, labels) == (3, 4)
+    assert ntp_acc_counts(preds[:, :1], labels[:, :1]) == (0, 0)
