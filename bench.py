@@ -172,6 +172,14 @@ def run_ours(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
     lib = L_.load()
+    if args.decode_only:     # development aid: the cfg4 decode object alone (not a bench line the driver reads)
+        cfg0 = pkg.MyTransfoXLConfig(compute_dtype=args.dtype, dropout=0.0, **dict(CFG2, mem_len=args.mem_len))
+        line = decode_probe(torch, pkg, pdist, cfg0, args, dev, rank, world)
+        if rank == 0:
+            emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     B, T = args.batch, args.seq
     kw = dict(CFG2)
@@ -413,6 +421,7 @@ def main():
     ap.add_argument('--dropout', type=float, default=0.1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-decode', action='store_true')
+    ap.add_argument('--decode-only', action='store_true')
     ap.add_argument('--decode-seqs', type=int, default=64)
     ap.add_argument('--decode-new', type=int, default=2048)
     args = ap.parse_args()

@@ -208,6 +208,38 @@ int txl_decode_uniform(float* u, int B, uint64_t seed, int64_t seq_offset, const
 int txl_decode_commit(const int64_t* next, int64_t* tok, int64_t* unfinished, int64_t* out_ids, int64_t ld_out, int col0, int32_t* pos, int B,
                       int64_t eos, int64_t pad, int use_eos, void* stream);
 
+/* Second-generation bf16 decode kernels (csrc/decode_stream.cu): what the CUDA-graph step launches.
+ * txl_dec_linear: C[M<=64, N] = A[M,K] W[N,K]^T (+bias)(ReLU), bf16 operands, fp32 accumulation; 8 or 16 output features per CTA so that
+ *   64-150 CTAs stream the weight matrix through a 4-stage cp.async ring, mma.sync fragments read as 16-byte pieces.  K % 32 == 0.  C is
+ *   bf16, or fp32 when out_f32 (the LM-head logits).  splits > 1: split-K, C = fp32 planes [splits][M][ldc] of partial sums (no bias / ReLU),
+ *   to be summed by txl_dec_add_ln.  Replaces every nn.Linear of the T=1 step [A.3, A.6].
+ * txl_dec_add_ln: y[M, d] (bf16) = LayerNorm(x + sum of `nparts` fp32 planes [M][d] + bias) * gamma + beta — the residual LayerNorm after
+ *   o_net / CoreNet.3 [A.3-8, A.6] fused with the split-K reduction and the bias.
+ *   Both kernels optionally issue an L2 prefetch (cp.async.bulk.prefetch.L2) of [prefetch, prefetch + prefetch_bytes), spread over their CTAs:
+ *   the decode step hands them slices of the NEXT attention kernel's ring, which HBM can deliver while these latency-bound kernels run.
+ * txl_decode_rtab_head_major: r [mem_len+1, H*dh] -> [H, mem_len+1, dh] (per-head rows contiguous for the bulk copies below).
+ * txl_decode_cache_init_kv: kv_mem [B*mem_len, 2*H*dh] -> ring cache kvc [B, H, mem_len, 2*dh] (a key's k row followed by its v row: a stage
+ *   of keys is one contiguous run).
+ * txl_decode_attn_pipe: the contract of txl_decode_attn (bf16 only) over the interleaved ring kvc and the head-major r; k|v rows and r rows
+ *   stream through a multi-stage shared-memory ring filled by cp.async.bulk (mbarrier full/empty), 2-4 CTAs per SM.  splits > 1: the ring
+ *   is cut into `splits` ranges handled by separate CTAs (for few sequences per GPU), merged by the last CTA to arrive; needs ws of
+ *   txl_decode_attn_pipe_ws_bytes and int counters[B*H] zeroed once (the kernel leaves them zero).
+ * txl_set_pdl(1): launch the kernels above with programmatic stream serialization (each executes griddepcontrol.wait before touching what a
+ *   predecessor produced), so launch latency, barrier set-up and weight / ring prefetch overlap the previous kernel's tail; returns the old value. */
+int txl_dec_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K,
+                   int relu, int out_f32, int splits, const void* prefetch, int64_t prefetch_bytes, void* stream);
+int txl_dec_add_ln(const void* x, const float* part, int nparts, const float* bias, const float* gamma, const float* beta, void* y, int M, int d,
+                   float eps, const void* prefetch, int64_t prefetch_bytes, void* stream);
+int txl_decode_rtab_head_major(const void* r, void* out, int rows, int H, int dh, void* stream);
+int64_t txl_decode_attn_pipe_ws_bytes(int B, int H, int dh, int splits);
+int txl_decode_cache_init_kv(const void* kv_mem, int64_t ld, void* kvc, int B, int H, int mem_len, int dh, void* stream);
+int txl_decode_attn_pipe(const void* qkv, void* kvc, const void* r_head_major, const float* rwb, const float* rrb, void* out,
+                         const int32_t* pos, int B, int H, int mem_len, int dh, int splits, void* ws, int* counters, void* stream);
+/* stage geometry of txl_decode_attn_pipe (keys per stage x stages at d_head 64): 0 = 32 x 4, 1 = 64 x 3, 2 = 64 x 4, 3 = 128 x 2 (default), 4 = 128 x 4,
+ * 5 = 64 x 2; -1 = re-read the TXL_DECODE_ATTN_CFG environment variable at the next call.  Returns the previous setting. */
+int txl_decode_attn_pipe_config(int cfg);
+int txl_set_pdl(int on);
+
 /* Fused decode step: embedding + all L layers (qkv, ring append + band attention, o_net, LN, FF1, FF2, LN) + LM-head GEMM as ONE persistent
  * cooperative kernel (grid barriers between stages; every Linear split over 16-column x 256-K work items with fp32 partials summed by the
  * consumer stage).  Per-layer pointers arrive as host arrays of L device pointers.  Call once with build_layer_table=1 (uploads the pointer

@@ -71,6 +71,14 @@ SIGNATURES = {
     'txl_skinny_gemm': (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     'txl_decode_uniform': (_i, [_vp, _i, _u64, _i64, _vp, _vp]),
     'txl_decode_commit': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _i, _i64, _i64, _i, _vp]),
+    'txl_dec_linear': (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
+    'txl_dec_add_ln': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _i64, _vp]),
+    'txl_decode_rtab_head_major': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'txl_decode_attn_pipe_ws_bytes': (_i64, [_i, _i, _i, _i]),
+    'txl_decode_cache_init_kv': (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _vp]),
+    'txl_decode_attn_pipe': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'txl_set_pdl': (_i, [_i]),
+    'txl_decode_attn_pipe_config': (_i, [_i]),
     'txl_decode_fused_workspace': (_i64, [_i, _i, _i, _i, _i, _i]),
     'txl_decode_fused_set_timestamps': (_i, [_vp]),
     'txl_decode_fused_step': (_i, [_vp] * 15 + [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),

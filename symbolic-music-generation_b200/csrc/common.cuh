@@ -33,6 +33,28 @@ extern unsigned long long g_txl_launches;
     TXL_CUDA(cudaGetLastError());   \
   } while (0)
 
+// ------------------------------------------------------------------ programmatic dependent launch (decode step)
+// With txl_set_pdl(1) the decode-step kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs
+// may start (barrier init, weight / ring prefetch) while the previous kernel drains; every such kernel executes griddepcontrol.wait before
+// it touches anything a predecessor wrote or may still read.  Without the attribute both instructions are no-ops.
+extern int g_txl_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t txl_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (g_txl_pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 int txl_num_sms();

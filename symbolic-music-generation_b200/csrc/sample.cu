@@ -38,21 +38,23 @@ __global__ void __launch_bounds__(NT) sample_kernel(const float* __restrict__ sc
     idx[v] = v;
   }
   __syncthreads();
-  // bitonic sort, descending under `before`
+  // bitonic sort, descending under `before`.  Compare-exchange c of a stage pairs t = (c with a 0 inserted at bit log2 j) and t | j; with
+  // c = tid (+ NT i) a warp's 32 exchanges of every stage with j <= 32 stay inside one 64-element block that only this warp touches, so
+  // those stages (51 of the 66 at 2048 elements) need __syncwarp() only; block-wide barriers remain around the j >= 64 stages.
   for (int k = 2; k <= NP; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < NP; t += NT) {
-        int p = t ^ j;
-        if (p > t) {
-          bool up = (t & k) == 0;
-          float va = val[t], vb = val[p]; int ia = idx[t], ib = idx[p];
-          bool swap = up ? before(vb, ib, va, ia) : before(va, ia, vb, ib);
-          if (swap) { val[t] = vb; val[p] = va; idx[t] = ib; idx[p] = ia; }
-        }
+      for (int c = tid; c < NP / 2; c += NT) {
+        const int t = ((c & ~(j - 1)) << 1) | (c & (j - 1)), p = t | j;
+        const bool up = (t & k) == 0;
+        const float va = val[t], vb = val[p]; const int ia = idx[t], ib = idx[p];
+        const bool swap = up ? before(vb, ib, va, ia) : before(va, ia, vb, ib);
+        if (swap) { val[t] = vb; val[p] = va; idx[t] = ib; idx[p] = ia; }
       }
-      __syncthreads();
+      const int next_j = j > 1 ? (j >> 1) : k;      // first stride of the next merge size is k
+      if (j >= 64 || next_j >= 64) __syncthreads(); else __syncwarp();
     }
   }
+  __syncthreads();
   if (!do_sample) {  // greedy: first maximal index
     if (tid == 0) next[b] = idx[0];
     if (keep) for (int v = tid; v < V; v += NT) keep[(int64_t)b * V + v] = (v == idx[0]);

@@ -15,6 +15,8 @@ void txl_set_error(const char* fmt, ...) {
 extern "C" const char* txl_last_error(void) { return g_err; }
 extern "C" int txl_version(void) { return 100; }
 unsigned long long g_txl_launches = 0;
+int g_txl_pdl = 0;
+extern "C" int txl_set_pdl(int on) { const int old = g_txl_pdl; g_txl_pdl = on ? 1 : 0; return old; }
 extern "C" unsigned long long txl_launch_count(void) { return g_txl_launches; }
 
 int txl_num_sms() {

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -22,18 +23,65 @@ def supported(model, B):
     return B <= SK_MAXM and cfg.same_length and cfg.mem_len > 0 and cfg.d_head in (32, 64, 128) and cfg.d_model % 8 == 0 and cfg.d_inner % 8 == 0
 
 
-def _skinny(A, W, bias=None, relu=False, out=None):
-    """y[B, N] = x[B, K] W[N, K]^T (+bias)(ReLU).  bf16: the tcgen05 GEMM computes y^T = W x^T (output features fill the 128-row MMA tile,
-    the <=64 sequences are the MMA N) and stores it transposed; fp32 parity mode: the exact-FMA weight-streaming kernel."""
-    if A.dtype == torch.bfloat16 and A.shape[1] >= 16:
-        return ops.gemm(W, A, transB=True, bias=bias, relu=relu, out=out, bias_row=bias is not None, transpose_out=True)
+_GEN1 = os.environ.get('TXL_DECODE_GEN1', '') == '1'      # A/B switch: first-generation kernels (tcgen05 transposed-store Linears, register-fed attention)
+_PDL = os.environ.get('TXL_DECODE_PDL', '1') != '0'       # programmatic dependent launch of the step's kernels
+_ATTN_SPLITS = int(os.environ.get('TXL_DECODE_ATTN_SPLITS', '0'))   # 0 = automatic
+# per layer: MB of the next attention kernel's ring that the six kernels before it ask into L2 (cp.async.bulk.prefetch.L2).  Measured at cfg4:
+# 0 MB 618.8 us/step, 48 MB 623.1, 80 MB 641.8, 112 MB 692.3 - the small kernels slow down by more than the attention kernel gains: off.
+_PREFETCH_MB = float(os.environ.get('TXL_DECODE_PREFETCH_MB', '0'))
+_ABL = int(os.environ.get('TXL_DECODE_ABL', '0'))       # timing ablations (results are garbage): 1 = no attention launch, 2 = no Linear / LayerNorm launches
+
+
+def _dec_linear_ok(A, W):
+    return (A.dtype == torch.bfloat16 and not _GEN1 and A.shape[1] % 32 == 0 and A.stride(1) == 1 and W.stride(1) == 1 and A.stride(0) % 8 == 0
+            and W.stride(0) % 8 == 0)
+
+
+def _skinny(A, W, bias=None, relu=False, out=None, pf=(None, 0)):
+    """y[B, N] = x[B, K] W[N, K]^T (+bias)(ReLU).  bf16: `txl_dec_linear` (8-16 output features per CTA, mma.sync fragments out of a cp.async
+    ring, so 64-150 CTAs stream the weights); fp32 parity mode: the exact-FMA weight-streaming kernel."""
     M, K = A.shape
     N = W.shape[0]
+    if _dec_linear_ok(A, W):
+        if out is None:
+            out = torch.empty(M, N, dtype=A.dtype, device=A.device)
+        assert out.dtype in (torch.bfloat16, torch.float32) and out.stride(1) == 1
+        check(load().txl_dec_linear(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), ptr(out), out.stride(0), M, N, K, int(relu),
+                                    int(out.dtype == torch.float32), 1, pf[0], pf[1], stream_ptr()), 'dec_linear')
+        return out
+    if A.dtype == torch.bfloat16 and K >= 16:
+        return ops.gemm(W, A, transB=True, bias=bias, relu=relu, out=out, bias_row=bias is not None, transpose_out=True)
     if out is None:
         out = torch.empty(M, N, dtype=A.dtype, device=A.device)
     check(load().txl_skinny_gemm(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), ptr(out), out.stride(0), M, N, K, int(relu), dtype_code(A.dtype),
                                  stream_ptr()), 'skinny_gemm')
     return out
+
+
+_SMS = {}
+
+
+def _sm_count(dev):
+    if dev not in _SMS:
+        _SMS[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _SMS[dev]
+
+
+def _linear_add_ln(x, A, W, bias, gamma, beta, eps, pf0=(None, 0), pf1=(None, 0)):
+    """LayerNorm(x + A W^T + bias): split-K `txl_dec_linear` leaves fp32 partial planes, `txl_dec_add_ln` sums them with the bias and the
+    residual and normalises (one launch for what was GEMM epilogue + add + LayerNorm)."""
+    M, K = A.shape
+    N = W.shape[0]
+    lib = load()
+    sms = _sm_count(A.device)
+    splits = max(1, min(K // 256, sms // ((N + 7) // 8)))
+    while splits > 1 and K % (32 * splits):
+        splits -= 1
+    part = torch.empty(splits, M, N, dtype=torch.float32, device=A.device)
+    check(lib.txl_dec_linear(ptr(A), A.stride(0), ptr(W), W.stride(0), None, ptr(part), N, M, N, K, 0, 1, splits, pf0[0], pf0[1], stream_ptr()), 'dec_linear')
+    y = torch.empty(M, N, dtype=torch.bfloat16, device=A.device)
+    check(lib.txl_dec_add_ln(ptr(x), ptr(part), splits, ptr(bias), ptr(gamma), ptr(beta), ptr(y), M, N, float(eps), pf1[0], pf1[1], stream_ptr()), 'dec_add_ln')
+    return y
 
 
 class Decoder:
@@ -54,15 +102,37 @@ class Decoder:
         lib = load()
         # per-layer ring caches of projected keys / values + cached r tables (weights are frozen during generation)
         pos_tab = ops.posemb_table(ML + 1, cfg.clamp_len, d, dt, dev)
-        self.kc, self.vc, self.r = [], [], []
+        self.kc, self.vc, self.kvc, self.r, self.r_hm = [], [], [], [], []
+        self.pipe_attn = dt == torch.bfloat16 and not _GEN1 and not use_fused
         for li, w in enumerate(model._W):
             kv = ops.gemm(bm[li].reshape(B * ML, d).contiguous(), w.qkv[d:], transB=True)          # (B*ML, 2d)
-            kc = torch.empty(B, H, ML, dh, dtype=dt, device=dev)
-            vc = torch.empty(B, H, ML, dh, dtype=dt, device=dev)
-            check(lib.txl_decode_cache_init(ptr(kv), kv.stride(0), ptr(kc), ptr(vc), B, H, ML, dh, dtype_code(dt), stream_ptr()), 'decode_cache_init')
-            self.kc.append(kc)
-            self.vc.append(vc)
+            if self.pipe_attn:
+                kvc = torch.empty(B, H, ML, 2 * dh, dtype=dt, device=dev)      # a key's k row then its v row: one contiguous run per stage of keys
+                check(lib.txl_decode_cache_init_kv(ptr(kv), kv.stride(0), ptr(kvc), B, H, ML, dh, stream_ptr()), 'decode_cache_init_kv')
+                self.kvc.append(kvc)
+            else:
+                kc = torch.empty(B, H, ML, dh, dtype=dt, device=dev)
+                vc = torch.empty(B, H, ML, dh, dtype=dt, device=dev)
+                check(lib.txl_decode_cache_init(ptr(kv), kv.stride(0), ptr(kc), ptr(vc), B, H, ML, dh, dtype_code(dt), stream_ptr()), 'decode_cache_init')
+                self.kc.append(kc)
+                self.vc.append(vc)
             self.r.append(ops.gemm(pos_tab, w.r, transB=True))                                       # (ML+1, d)
+            if self.pipe_attn:
+                rh = torch.empty(H, ML + 1, dh, dtype=dt, device=dev)                                # per-head rows contiguous for the bulk copies
+                check(lib.txl_decode_rtab_head_major(ptr(self.r[-1]), ptr(rh), ML + 1, H, dh, stream_ptr()), 'decode_rtab_head_major')
+                self.r_hm.append(rh)
+        # ring splits of the attention kernel (several CTAs per (sequence, head), merged by the last to arrive).  Measured at cfg4, 64 sequences:
+        # 1 split 667 us/step, 2 splits 703, 4 splits 720 — the merge costs more than the better SM balance returns; with few sequences per GPU
+        # (8 x 8 heads = 64 CTAs for 592 slots) a CTA streaming its whole ring alone is latency-bound, so the ring is cut to fill the chip.
+        auto = max(1, min(8, 512 // max(1, B * H), (ML * dh) // (4 * 2048)))
+        self.attn_splits = _ATTN_SPLITS if _ATTN_SPLITS > 0 else auto
+        self.attn_ws = self.attn_cnt = None
+        self.pf_bytes = int(min(B * H * ML * 2 * dh * 2, _PREFETCH_MB * 2 ** 20)) if self.pipe_attn else 0
+        self._abl_qkv = torch.zeros(B, 3 * d, dtype=dt, device=dev) if _ABL else None
+        self.gen2_ln = self.pipe_attn and d % 32 == 0 and cfg.d_inner % 32 == 0 and d <= 1024      # split-K Linear + fused add/LayerNorm
+        if self.pipe_attn and self.attn_splits > 1:
+            self.attn_ws = torch.empty(lib.txl_decode_attn_pipe_ws_bytes(B, H, dh, self.attn_splits), dtype=torch.uint8, device=dev)
+            self.attn_cnt = torch.zeros(B * H, dtype=torch.int32, device=dev)
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
         self.tok = torch.empty(B, dtype=torch.int64, device=dev)
         self.next = torch.empty(B, dtype=torch.int64, device=dev)
@@ -115,18 +185,46 @@ class Decoder:
         if self.fused:
             self._fused_call(0)
             return self._finish_step(self.logits32)
-        x = ops.embed_fwd(self.tok, m._E, math.sqrt(d))
-        for li, w in enumerate(m._W):
-            qkv = _skinny(x, w.qkv)
-            vec = torch.empty(B, d, dtype=self.dt, device=self.dev)
-            check(lib.txl_decode_attn(ptr(qkv), ptr(self.kc[li]), ptr(self.vc[li]), ptr(self.r[li]), ptr(w.rwb), ptr(w.rrb), ptr(vec), ptr(self.pos),
-                                      B, H, ML, dh, dtype_code(self.dt), stream_ptr()), 'decode_attn')
-            ao = _skinny(vec, w.o)
-            y1, _, _, _ = ops.add_ln_fwd(x, ao, w.ln1_w, w.ln1_b, cfg.layer_norm_epsilon, save=False)
-            hdn = _skinny(y1, w.w1, bias=w.b1, relu=True)
-            f = _skinny(hdn, w.w2, bias=w.b2)
-            x, _, _, _ = ops.add_ln_fwd(y1, f, w.ln2_w, w.ln2_b, cfg.layer_norm_epsilon, save=False)
-        _skinny(x, m._E, bias=m._out_bias, out=self.logits[:, :self.V])
+        pdl_old = lib.txl_set_pdl(1) if (self.pipe_attn and _PDL) else None
+        try:
+            x = ops.embed_fwd(self.tok, m._E, math.sqrt(d))
+            nl = len(m._W)
+
+            def pf(li_next, k):
+                """k-th sixth of the L2-prefetch window of layer `li_next`'s ring (the six kernels between two attention kernels share it)."""
+                if not self.pipe_attn or self.pf_bytes <= 0:
+                    return (None, 0)
+                sz = self.pf_bytes // 6 // 128 * 128
+                return (self.kvc[li_next % nl].data_ptr() + k * sz, sz)
+
+            for li, w in enumerate(m._W):
+                qkv = (_skinny(x, w.qkv, pf=pf(li, 5)) if li > 0 else _skinny(x, w.qkv)) if not (_ABL & 2) else self._abl_qkv
+                vec = torch.empty(B, d, dtype=self.dt, device=self.dev)
+                if _ABL & 1:
+                    pass
+                elif self.pipe_attn:
+                    check(lib.txl_decode_attn_pipe(ptr(qkv), ptr(self.kvc[li]), ptr(self.r_hm[li]), ptr(w.rwb), ptr(w.rrb), ptr(vec),
+                                                   ptr(self.pos), B, H, ML, dh, self.attn_splits, ptr(self.attn_ws), ptr(self.attn_cnt), stream_ptr()),
+                          'decode_attn_pipe')
+                else:
+                    check(lib.txl_decode_attn(ptr(qkv), ptr(self.kc[li]), ptr(self.vc[li]), ptr(self.r[li]), ptr(w.rwb), ptr(w.rrb), ptr(vec), ptr(self.pos),
+                                              B, H, ML, dh, dtype_code(self.dt), stream_ptr()), 'decode_attn')
+                if _ABL & 2:
+                    continue
+                if self.gen2_ln:
+                    y1 = _linear_add_ln(x, vec, w.o, None, w.ln1_w, w.ln1_b, cfg.layer_norm_epsilon, pf(li + 1, 0), pf(li + 1, 1))
+                    hdn = _skinny(y1, w.w1, bias=w.b1, relu=True, pf=pf(li + 1, 2))
+                    x = _linear_add_ln(y1, hdn, w.w2, w.b2, w.ln2_w, w.ln2_b, cfg.layer_norm_epsilon, pf(li + 1, 3), pf(li + 1, 4))
+                    continue
+                ao = _skinny(vec, w.o)
+                y1, _, _, _ = ops.add_ln_fwd(x, ao, w.ln1_w, w.ln1_b, cfg.layer_norm_epsilon, save=False)
+                hdn = _skinny(y1, w.w1, bias=w.b1, relu=True)
+                f = _skinny(hdn, w.w2, bias=w.b2)
+                x, _, _, _ = ops.add_ln_fwd(y1, f, w.ln2_w, w.ln2_b, cfg.layer_norm_epsilon, save=False)
+            _skinny(x, m._E, bias=m._out_bias, out=self.logits[:, :self.V], pf=pf(0, 5))      # the next step's first attention kernel
+        finally:
+            if pdl_old is not None:
+                lib.txl_set_pdl(pdl_old)
         return self._finish_step(self.logits)
 
     def _finish_step(self, logits):

@@ -274,3 +274,31 @@ def test_monitor_greedy_and_ntp_acc_fp32(pkg):
     assert model.last_greedy is None
     with pytest.raises(pkg.TxlError):
         model.ntp_acc_counts(labels)
+
+
+@pytest.mark.parametrize('mem_len,dh,H', [(32, 32, 4), (48, 64, 2)])
+def test_decode_step_bf16_scores_match_forward_path(pkg, mem_len, dh, H):
+    """bf16 decode step (dec_linear + bulk-copy attention + ring cache) vs the segment forward with T=1 and the same mems (the path the
+    oracle parity tests cover): log-probs of every step within the bf16 tolerance, over enough steps to wrap the ring."""
+    import importlib
+    decode = importlib.import_module('symbolic-music-generation_b200.decode')
+    _, model = make_pair(pkg, 'bf16', mem_len=mem_len, n_layer=2, d_head=dh, n_head=H, d_model=dh * H)
+    model.eval()
+    ids, _ = _batch(422, 3, mem_len + 5, pad=False)
+    with torch.no_grad():
+        out = model(input_ids=ids.cuda())
+        past = out.mems
+        tok = out.logits[:, -1].argmax(-1)
+        n = mem_len + 9
+        out_ids = torch.zeros(3, n + 1, dtype=torch.int64, device='cuda')
+        dec = decode.Decoder(model, past, out_ids, 0, do_sample=False, temperature=1.0, top_k=0, top_p=1.0, eos_token_id=None, pad_token_id=None,
+                             use_graph=False)
+        worst = 0.0
+        for step in range(n):
+            o = model(input_ids=tok[:, None], mems=past)
+            past = o.mems
+            dec.run(tok, 1)
+            got, want = dec.scores.float(), o.logits[:, -1].float()
+            worst = max(worst, ((got - want).abs() / want.abs()).max().item())
+            tok = want.argmax(-1)                      # both paths are fed the forward path's greedy token
+    assert worst < 2e-2, worst

@@ -368,3 +368,104 @@ def test_ntp_acc_counts_bit_exact(ops, B, T):
     wide[:, :T] = preds.cuda()
     out = ops.ntp_acc(wide[:, :T], labels.cuda(), out)
     assert out.tolist() == [2 * hit, 2 * cnt]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('M,N,K', [(64, 1536, 512), (64, 512, 2048), (64, 2048, 512), (64, 1190, 512), (1, 24, 32), (7, 100, 96), (16, 512, 128),
+                                   (17, 256, 288), (33, 1190, 512), (48, 8, 1056), (64, 3000, 64)])
+def test_dec_linear_vs_fp32_matmul(pkg, M, N, K):
+    """txl_dec_linear (decode-step Linear: bf16 operands, fp32 accumulation) == fp32 matmul of the same bf16 values, for every row-tile /
+    feature-tile variant, ragged N, K not a multiple of the 256-column stage, strided views, bias / ReLU / fp32 output."""
+    import importlib
+    L_ = importlib.import_module('symbolic-music-generation_b200._lib')
+    lib = L_.load()
+    g = torch.Generator().manual_seed(77)
+    A = torch.randn(M, K + 8, generator=g).cuda().to(torch.bfloat16)[:, :K]            # row pitch K+8: a view, not a dense matrix
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda().to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).cuda()
+    ref = A.float() @ W.float().t()
+    st = torch.cuda.current_stream().cuda_stream
+    for use_bias, relu, f32 in [(False, False, False), (True, True, False), (True, False, True)]:
+        out = torch.full((M, N + 3), 7.0, dtype=torch.float32 if f32 else torch.bfloat16, device='cuda')
+        L_.check(lib.txl_dec_linear(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), bias.data_ptr() if use_bias else None, out.data_ptr(),
+                                    out.stride(0), M, N, K, int(relu), int(f32), 1, W.data_ptr(), W.numel() * 2, st), 'dec_linear')
+        want = ref + bias if use_bias else ref
+        if relu:
+            want = want.relu()
+        got = out[:, :N].float()
+        tol = 2e-5 * math.sqrt(K) if f32 else 1e-2
+        assert ((got - want).abs() / (want.abs() + 1.0)).max().item() < tol
+        assert (out[:, N:] == 7.0).all()                                                  # nothing written past column N
+    # split-K planes + fused residual LayerNorm (txl_dec_add_ln) == LayerNorm(x + A W^T + bias) in fp32
+    if N % 8 == 0 and N <= 1024:
+        x = torch.randn(M, N, generator=g).cuda().to(torch.bfloat16)
+        gamma = (1 + 0.1 * torch.randn(N, generator=g)).cuda()
+        beta = (0.1 * torch.randn(N, generator=g)).cuda()
+        want = torch.nn.functional.layer_norm(x.float() + ref + bias, (N,), gamma, beta, 1e-5)
+        for splits in (1, 2, 4):
+            if K % (32 * splits):
+                continue
+            part = torch.full((splits, M, N), float('nan'), dtype=torch.float32, device='cuda')
+            L_.check(lib.txl_dec_linear(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), None, part.data_ptr(), N, M, N, K, 0, 1, splits, None, 0, st), 'dec_linear')
+            assert ((part.sum(0) - ref).abs() / (ref.abs() + 1.0)).max().item() < 2e-5 * math.sqrt(K)
+            y = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
+            L_.check(lib.txl_dec_add_ln(x.data_ptr(), part.data_ptr(), splits, bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), M, N, 1e-5,
+                                        W.data_ptr(), W.numel() * 2 // 16 * 16, st), 'dec_add_ln')
+            assert ((y.float() - want).abs() / (want.abs() + 1.0)).max().item() < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,H,dh,ML', [(3, 2, 64, 128), (2, 3, 32, 40), (2, 2, 128, 100), (64, 8, 64, 1024), (1, 1, 64, 7)])
+def test_decode_attn_pipe_vs_first_generation(pkg, B, H, dh, ML):
+    """The bulk-copy-pipelined decode attention == the register-fed kernel on the same ring, at ring positions before, at and after the wrap
+    point (incl. mem_len that is not a multiple of the 32-key stage); the ring append is bit-identical."""
+    import importlib
+    L_ = importlib.import_module('symbolic-music-generation_b200._lib')
+    lib = L_.load()
+    g = torch.Generator().manual_seed(77)
+    HD = H * dh
+    bf = torch.bfloat16
+    kc0 = torch.randn(B, H, ML, dh, generator=g).cuda().to(bf)
+    vc0 = torch.randn(B, H, ML, dh, generator=g).cuda().to(bf)
+    r = torch.randn(ML + 1, HD, generator=g).cuda().to(bf)
+    rhm = torch.empty(H, ML + 1, dh, dtype=bf, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    L_.check(lib.txl_decode_rtab_head_major(r.data_ptr(), rhm.data_ptr(), ML + 1, H, dh, st), 'rtab')
+    assert torch.equal(rhm, r.view(ML + 1, H, dh).permute(1, 0, 2).contiguous())
+    rwb = (torch.randn(HD, generator=g) * 0.3).cuda()
+    rrb = (torch.randn(HD, generator=g) * 0.3).cuda()
+    kvm = torch.randn(B * ML, 2 * HD, generator=g).cuda().to(bf)                             # what the GEMM over the hidden-state mems returns
+    kvi = torch.empty(B, H, ML, 2 * dh, dtype=bf, device='cuda')
+    L_.check(lib.txl_decode_cache_init_kv(kvm.data_ptr(), kvm.stride(0), kvi.data_ptr(), B, H, ML, dh, st), 'cache_init_kv')
+    kk, vv = kvm.view(B, ML, 2, H, dh)[:, :, 0].permute(0, 2, 1, 3), kvm.view(B, ML, 2, H, dh)[:, :, 1].permute(0, 2, 1, 3)
+    assert torch.equal(kvi, torch.cat([kk, vv], dim=-1))
+    cnt = torch.zeros(B * H, dtype=torch.int32, device='cuda')
+    for p in list(range(0, 12)) + [31, 32, ML - 1, ML, ML + 5] + list(range(3 * ML + 33, 3 * ML + 39)):
+        qkv = torch.randn(B, 3 * HD, generator=g).cuda().to(bf)
+        pos = torch.tensor([p], dtype=torch.int32, device='cuda')
+        k1, v1 = kc0.clone(), vc0.clone()
+        o1 = torch.zeros(B, HD, dtype=bf, device='cuda')
+        o2 = torch.zeros(B, HD, dtype=bf, device='cuda')
+        L_.check(lib.txl_decode_attn(qkv.data_ptr(), k1.data_ptr(), v1.data_ptr(), r.data_ptr(), rwb.data_ptr(), rrb.data_ptr(), o1.data_ptr(),
+                                     pos.data_ptr(), B, H, ML, dh, L_.BF16, st), 'decode_attn')
+        splits = [1, 2, 3][p % 3]
+        ws = torch.empty(max(1, lib.txl_decode_attn_pipe_ws_bytes(B, H, dh, splits)), dtype=torch.uint8, device='cuda')
+        kv2 = torch.cat([kc0, vc0], dim=-1).contiguous()                                   # interleaved ring [B, H, ML, 2*dh]
+        old_cfg = lib.txl_decode_attn_pipe_config(p % 6)                            # every stage geometry gets ring positions on both sides of the wrap
+        L_.check(lib.txl_decode_attn_pipe(qkv.data_ptr(), kv2.data_ptr(), rhm.data_ptr(), rwb.data_ptr(), rrb.data_ptr(), o2.data_ptr(),
+                                          pos.data_ptr(), B, H, ML, dh, splits, ws.data_ptr(), cnt.data_ptr(), st), 'decode_attn_pipe')
+        lib.txl_decode_attn_pipe_config(old_cfg)
+        k2, v2 = kv2[..., :dh].contiguous(), kv2[..., dh:].contiguous()
+        assert int(cnt.abs().sum().item()) == 0          # the merge counters are left zeroed for the next launch
+        torch.cuda.synchronize()
+        assert torch.equal(k1, k2) and torch.equal(v1, v2)
+        assert torch.equal(k2[:, :, p % ML].reshape(B, HD), qkv[:, HD:2 * HD]) and torch.equal(v2[:, :, p % ML].reshape(B, HD), qkv[:, 2 * HD:])
+        # exact fp32 softmax over the ring as the arbiter for both kernels
+        q = qkv[:, :HD].float().view(B, H, dh)
+        s = torch.arange(ML, device='cuda')
+        x = ML - ((p % ML - s) % ML)
+        ac = torch.einsum('bhd,bhsd->bhs', q + rwb.view(H, dh), k2.float())
+        bd = torch.einsum('bhd,shd->bhs', q + rrb.view(H, dh), r.float().view(ML + 1, H, dh)[x])
+        want = torch.einsum('bhs,bhsd->bhd', torch.softmax((ac + bd) / math.sqrt(dh), -1), v2.float()).reshape(B, HD)
+        for o in (o1, o2):
+            assert ((o.float() - want).abs() / (want.abs() + 0.05)).max().item() < 2e-2, p
