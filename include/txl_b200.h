@@ -238,6 +238,14 @@ int txl_decode_attn_pipe(const void* qkv, void* kvc, const void* r_head_major, c
 /* stage geometry of txl_decode_attn_pipe (keys per stage x stages at d_head 64): 0 = 32 x 4, 1 = 64 x 3, 2 = 64 x 4, 3 = 128 x 2 (default), 4 = 128 x 4,
  * 5 = 64 x 2; -1 = re-read the TXL_DECODE_ATTN_CFG environment variable at the next call.  Returns the previous setting. */
 int txl_decode_attn_pipe_config(int cfg);
+/* txl_decode_tail: everything after the LM-head GEMM of a bf16 decode step in one kernel, one CTA per sequence: log-softmax of logits
+ * [B, ldl] fp32 (bit-identical to txl_logsoftmax_nll_fwd; also written to scores [B, V] when not NULL), the keyed uniform of
+ * txl_decode_uniform, txl_sample's warpers + draw, txl_decode_commit's eos / pad bookkeeping and token store, x0[b, :] = E[token] * emb_scale
+ * (the next step's input, bf16) and *pos += 1 (by the last CTA to arrive; `arrive` is one int zeroed once, left zero). */
+int txl_decode_tail(const float* logits, int64_t ldl, float* scores, int B, int V, int do_sample, float temperature, int top_k, float top_p,
+                    uint64_t seed, int64_t seq_offset, int64_t* tok, int64_t* unfinished, int64_t* out_ids, int64_t ld_out, int col0,
+                    int32_t* pos, int* arrive, int64_t eos, int64_t pad, int use_eos, const void* E, void* x0, int d, float emb_scale,
+                    void* stream);
 int txl_set_pdl(int on);
 
 /* Fused decode step: embedding + all L layers (qkv, ring append + band attention, o_net, LN, FF1, FF2, LN) + LM-head GEMM as ONE persistent

@@ -133,6 +133,10 @@ class Decoder:
         if self.pipe_attn and self.attn_splits > 1:
             self.attn_ws = torch.empty(lib.txl_decode_attn_pipe_ws_bytes(B, H, dh, self.attn_splits), dtype=torch.uint8, device=dev)
             self.attn_cnt = torch.zeros(B * H, dtype=torch.int32, device=dev)
+        # fused step tail (log-softmax + keyed uniform + sampler + eos/pad bookkeeping + next embedding + step counter in one kernel)
+        self.gen2_tail = self.pipe_attn and os.environ.get('TXL_DECODE_TAIL', '1') != '0' and cfg.vocab_size <= 8192
+        self.x0 = torch.empty(B, d, dtype=dt, device=dev) if self.gen2_tail else None
+        self.tail_arrive = torch.zeros(1, dtype=torch.int32, device=dev) if self.gen2_tail else None
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
         self.tok = torch.empty(B, dtype=torch.int64, device=dev)
         self.next = torch.empty(B, dtype=torch.int64, device=dev)
@@ -145,7 +149,7 @@ class Decoder:
         self.V = cfg.vocab_size
         self.Vp = (self.V + 7) // 8 * 8
         self.logits = torch.zeros(B, self.Vp, dtype=torch.float32 if dt == torch.bfloat16 else dt, device=dev)
-        self.scores = None
+        self.scores = torch.zeros(B, cfg.vocab_size, dtype=torch.float32, device=dev) if self.gen2_tail else None      # log-probs of the last step
         self.graph = None
         self.use_graph = use_graph
         self.steps_done = 0
@@ -187,7 +191,8 @@ class Decoder:
             return self._finish_step(self.logits32)
         pdl_old = lib.txl_set_pdl(1) if (self.pipe_attn and _PDL) else None
         try:
-            x = ops.embed_fwd(self.tok, m._E, math.sqrt(d))
+            # second generation: x0 already holds the embedding of the current token (run() for the first step, the tail kernel afterwards)
+            x = self.x0 if self.gen2_tail else ops.embed_fwd(self.tok, m._E, math.sqrt(d))
             nl = len(m._W)
 
             def pf(li_next, k):
@@ -229,6 +234,19 @@ class Decoder:
 
     def _finish_step(self, logits):
         lib, B = load(), self.B
+        if self.gen2_tail and logits is self.logits:
+            use_eos = self.eos is not None
+            pdl_old = lib.txl_set_pdl(1) if _PDL else None
+            try:
+                check(lib.txl_decode_tail(ptr(logits), logits.stride(0), ptr(self.scores), B, self.V, int(self.do_sample), self.temperature, self.top_k,
+                                          self.top_p, self.seed, self.seq_offset, ptr(self.tok), ptr(self.unfinished), ptr(self.out_ids),
+                                          self.out_ids.stride(0), self.col0, ptr(self.pos), ptr(self.tail_arrive), int(self.eos if use_eos else 0),
+                                          int(self.pad if self.pad is not None else 0), int(use_eos), ptr(self.model._E), ptr(self.x0), self.d,
+                                          math.sqrt(self.d), stream_ptr()), 'decode_tail')
+            finally:
+                if pdl_old is not None:
+                    lib.txl_set_pdl(pdl_old)
+            return
         _, _, logprobs, _ = ops.logsoftmax_nll_fwd(logits, self.V, None, want_logprobs=True)
         self.scores = logprobs
         if self.do_sample:
@@ -245,6 +263,8 @@ class Decoder:
         done = 0
         if n_steps <= 0:
             return 0
+        if self.gen2_tail:
+            self.x0.copy_(ops.embed_fwd(self.tok, self.model._E, math.sqrt(self.d)))
         self._step_kernels()                      # eager first step: warms caches, sets kernel attributes
         done += 1
         if self.use_graph and n_steps > 1:

@@ -469,3 +469,50 @@ def test_decode_attn_pipe_vs_first_generation(pkg, B, H, dh, ML):
         want = torch.einsum('bhs,bhsd->bhd', torch.softmax((ac + bd) / math.sqrt(dh), -1), v2.float()).reshape(B, HD)
         for o in (o1, o2):
             assert ((o.float() - want).abs() / (want.abs() + 0.05)).max().item() < 2e-2, p
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('do_sample,top_k,top_p,temp', [(0, 0, 1.0, 1.0), (1, 8, 1.0, 1.0), (1, 32, 0.9, 1.1), (1, 0, 0.8, 0.9), (1, 100, 1.0, 1.0)])
+def test_decode_tail_equals_separate_kernels(pkg, ops, do_sample, top_k, top_p, temp):
+    """txl_decode_tail (one kernel) == txl_logsoftmax_nll_fwd -> txl_decode_uniform -> txl_sample -> txl_decode_commit -> txl_embed_fwd, bit for
+    bit: scores, tokens, eos/pad bookkeeping, the stored column, the next embedding row and the step counter, over several steps."""
+    import importlib
+    L_ = importlib.import_module('symbolic-music-generation_b200._lib')
+    lib = L_.load()
+    g = torch.Generator().manual_seed(77)
+    B, V, Vp, d = 9, 1190, 1192, 64
+    E = torch.randn(V, d, generator=g).cuda().to(torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    eos, pad = 3, 1
+
+    def fresh():
+        return dict(tok=torch.zeros(B, dtype=torch.int64, device='cuda'), unf=torch.ones(B, dtype=torch.int64, device='cuda'),
+                    out=torch.full((B, 12), -7, dtype=torch.int64, device='cuda'), pos=torch.zeros(1, dtype=torch.int32, device='cuda'))
+    a, b = fresh(), fresh()
+    arrive = torch.zeros(1, dtype=torch.int32, device='cuda')
+    x0 = torch.zeros(B, d, dtype=torch.bfloat16, device='cuda')
+    scores = torch.zeros(B, V, dtype=torch.float32, device='cuda')
+    u = torch.zeros(B, dtype=torch.float32, device='cuda')
+    nxt = torch.zeros(B, dtype=torch.int64, device='cuda')
+    for step in range(6):
+        logits = torch.zeros(B, Vp)
+        logits[:, :V] = torch.randn(B, V, generator=g) * 3
+        logits[:, 3] += 4.0 * (step % 2)                     # make eos likely on some steps so rows finish
+        logits[0, 10:14] = logits[0, 10]                     # ties around the top
+        logits = logits.cuda()
+        # separate kernels
+        _, _, lp, _ = ops.logsoftmax_nll_fwd(logits, V, None, want_logprobs=True)
+        if do_sample:
+            L_.check(lib.txl_decode_uniform(u.data_ptr(), B, 1234, 5, a['pos'].data_ptr(), st), 'uniform')
+        L_.check(lib.txl_sample(lp.data_ptr(), B, V, do_sample, temp, top_k, top_p, u.data_ptr(), nxt.data_ptr(), None, None, st), 'sample')
+        L_.check(lib.txl_decode_commit(nxt.data_ptr(), a['tok'].data_ptr(), a['unf'].data_ptr(), a['out'].data_ptr(), a['out'].stride(0), 2,
+                                       a['pos'].data_ptr(), B, eos, pad, 1, st), 'commit')
+        xa = ops.embed_fwd(a['tok'], E, math.sqrt(d))
+        # fused tail
+        L_.check(lib.txl_decode_tail(logits.data_ptr(), logits.stride(0), scores.data_ptr(), B, V, do_sample, temp, top_k, top_p, 1234, 5,
+                                     b['tok'].data_ptr(), b['unf'].data_ptr(), b['out'].data_ptr(), b['out'].stride(0), 2, b['pos'].data_ptr(),
+                                     arrive.data_ptr(), eos, pad, 1, E.data_ptr(), x0.data_ptr(), d, math.sqrt(d), st), 'decode_tail')
+        assert torch.equal(scores, lp)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (step, k)
+        assert torch.equal(x0, xa) and int(arrive.item()) == 0 and int(b['pos'].item()) == step + 1
