@@ -55,17 +55,17 @@ __device__ __forceinline__ void l2_prefetch_slice(const void* base, int64_t byte
 
 constexpr int DL_WARPS = 8, DL_THREADS = DL_WARPS * 32;
 constexpr int DL_KC = DL_WARPS * 32;                // K columns of one stage: one 32-wide block per warp
-constexpr int DL_STAGES = 4;
 constexpr int DL_PITCH = DL_KC * 2 + 64;            // bytes per staged row: +64 shifts consecutive rows by 16 banks -> conflict-free LDS.128 fragments
-constexpr size_t dl_smem_bytes(int MT, int NT) {
-  size_t ring = (size_t)DL_STAGES * (MT * 16 + NT * 8) * DL_PITCH, red = (size_t)DL_WARPS * MT * 16 * (NT * 8 + 1) * 4;
+constexpr size_t dl_smem_bytes(int MT, int NT, int STAGES) {
+  size_t ring = (size_t)STAGES * (MT * 16 + NT * 8) * DL_PITCH, red = (size_t)DL_WARPS * MT * 16 * (NT * 8 + 1) * 4;
   return ring > red ? ring : red;
 }
 
-// MT = 16-row tiles of x (1, 2 or 4), NT = 8-feature tiles per CTA (1 or 2).  x and the CTA's weight rows stream through a 4-stage cp.async
-// ring in 256-column chunks (every copy of up to four chunks is in flight before the first MMA: ptxas sinks plain global loads between the
-// MMAs, and in-order issue then serialises their latencies); warp w multiplies the w-th 32-wide block of each chunk.
-template <int MT, int NT, bool OUT_F32>
+// MT = 16-row tiles of x (1, 2 or 4), NT = 8-feature tiles per CTA (1 or 2).  x and the CTA's weight rows stream through a DL_STAGES-deep
+// cp.async ring in 256-column chunks (every copy of the first chunks is in flight before the first MMA: ptxas sinks plain global loads between
+// the MMAs, and in-order issue then serialises their latencies); warp w multiplies the w-th 32-wide block of each chunk.  Two stages (the
+// whole K of a <= 512-column problem, 83-92 KB) leave room for a second CTA or an attention CTA of another sequence group on the SM.
+template <int MT, int NT, bool OUT_F32, int DL_STAGES>
 __global__ void __launch_bounds__(DL_THREADS) dec_linear_kernel(const bf16* __restrict__ A, int64_t lda, const bf16* __restrict__ W, int64_t ldw,
                                                                 const float* __restrict__ bias, void* __restrict__ Cout, int64_t ldc, int M, int N,
                                                                 int Ktot, int relu, const void* __restrict__ pf, int64_t pf_bytes) {
@@ -454,19 +454,25 @@ extern "C" int txl_dec_linear(const void* A, int64_t lda, const void* W, int64_t
   const int mt = M <= 16 ? 1 : M <= 32 ? 2 : 4;
   const int nt = cdiv64(N, 8) * splits <= txl_num_sms() ? 1 : 2;      // 8 features per CTA while that fits one wave, else 16
   dim3 grid((unsigned)cdiv64(N, nt * 8), (unsigned)splits);
-#define DL_GO(MT, NT, F32)                                                                                                                     \
+  // two ring stages (83-92 KB instead of 166-184 KB) for problems of <= 512 columns per CTA: measured neutral with four sequence groups
+  // (546.0 vs 546.2 us/step) and slower with one (662.7 vs 613.2), so it stays an A/B switch
+  static const bool allow2 = [] { const char* e = getenv("TXL_DEC_LINEAR_2STAGE"); return e && e[0] == '1'; }();
+  const bool two_stage = allow2 && K / splits <= 2 * DL_KC;
+#define DL_GO2(MT, NT, F32, STG)                                                                                                                     \
   {                                                                                                                                            \
     static bool attr_set = false;                                                                                                              \
-    constexpr size_t smem = dl_smem_bytes(MT, NT);                                                                                             \
-    if (!attr_set) { TXL_CUDA(cudaFuncSetAttribute(dec_linear_kernel<MT, NT, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; } \
-    TXL_CUDA(txl_launch_pdl(dec_linear_kernel<MT, NT, F32>, grid, dim3(DL_THREADS), smem, st, a, lda, w, ldw, bias, C, ldc, M, N, K, relu, prefetch, prefetch_bytes));   \
+    constexpr size_t smem = dl_smem_bytes(MT, NT, STG);                                                                                        \
+    if (!attr_set) { TXL_CUDA(cudaFuncSetAttribute(dec_linear_kernel<MT, NT, F32, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; } \
+    TXL_CUDA(txl_launch_pdl(dec_linear_kernel<MT, NT, F32, STG>, grid, dim3(DL_THREADS), smem, st, a, lda, w, ldw, bias, C, ldc, M, N, K, relu, prefetch, prefetch_bytes));   \
   }
+#define DL_GO(MT, NT, F32) { if (two_stage) DL_GO2(MT, NT, F32, 2) else DL_GO2(MT, NT, F32, 4) }
 #define DL_F(MT, NT) { if (out_f32) DL_GO(MT, NT, true) else DL_GO(MT, NT, false) }
 #define DL_MT(NT) { if (mt == 1) DL_F(1, NT) else if (mt == 2) DL_F(2, NT) else DL_F(4, NT) }
   if (nt == 2) DL_MT(2) else DL_MT(1)
 #undef DL_MT
 #undef DL_F
 #undef DL_GO
+#undef DL_GO2
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }

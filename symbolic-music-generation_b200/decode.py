@@ -29,6 +29,7 @@ _ATTN_SPLITS = int(os.environ.get('TXL_DECODE_ATTN_SPLITS', '0'))   # 0 = automa
 # per layer: MB of the next attention kernel's ring that the six kernels before it ask into L2 (cp.async.bulk.prefetch.L2).  Measured at cfg4:
 # 0 MB 618.8 us/step, 48 MB 623.1, 80 MB 641.8, 112 MB 692.3 - the small kernels slow down by more than the attention kernel gains: off.
 _PREFETCH_MB = float(os.environ.get('TXL_DECODE_PREFETCH_MB', '0'))
+_SPLIT_COLS = int(os.environ.get('TXL_DEC_SPLIT_COLS', '1000000'))   # A/B switch: 512 makes every Linear fit two ring stages (see TXL_DEC_LINEAR_2STAGE)
 _ABL = int(os.environ.get('TXL_DECODE_ABL', '0'))       # timing ablations (results are garbage): 1 = no attention launch, 2 = no Linear / LayerNorm launches
 
 
@@ -74,7 +75,7 @@ def _linear_add_ln(x, A, W, bias, gamma, beta, eps, pf0=(None, 0), pf1=(None, 0)
     N = W.shape[0]
     lib = load()
     sms = _sm_count(A.device)
-    splits = max(1, min(K // 256, sms // ((N + 7) // 8)))
+    splits = max(1, min(K // 256, sms // ((N + 7) // 8)), K // _SPLIT_COLS)       # also: at most _SPLIT_COLS columns per CTA
     while splits > 1 and K % (32 * splits):
         splits -= 1
     part = torch.empty(splits, M, N, dtype=torch.float32, device=A.device)
@@ -84,11 +85,24 @@ def _linear_add_ln(x, A, W, bias, gamma, beta, eps, pf0=(None, 0), pf1=(None, 0)
     return y
 
 
+def sequence_groups(model, B, requested=None):
+    """How many independent sequence groups generate() decodes as parallel graph branches (GroupedDecoder).  bf16 second-generation path only."""
+    if requested is None:
+        requested = int(os.environ.get('TXL_DECODE_GROUPS', '0')) or None
+    if model._E.dtype != torch.bfloat16 or _GEN1 or os.environ.get('TXL_DECODE_TAIL', '1') == '0' or model.config.vocab_size > 8192:
+        return 1
+    if requested is not None:
+        return max(1, min(int(requested), B))
+    # groups of 16 sequences: the Linears then work on ONE 16-row MMA tile, and 16 x 8 heads = 128 attention CTAs sit one per SM.  Measured at 64
+    # sequences (us/step): 1 group 613, 2 groups 601, 3 groups 710, 4 groups 546, 5 groups 567, 8 groups 701.
+    return min(4, B // 16) if B >= 32 else 1
+
+
 class Decoder:
     """Device-resident generation state for `B` sequences.  Built from the mems the prompt forward returned."""
 
     def __init__(self, model, mems, out_ids, col0, *, do_sample, temperature, top_k, top_p, eos_token_id, pad_token_id, seed=0, seq_offset=0,
-                 use_graph=True, use_fused=False):
+                 use_graph=True, use_fused=False, attn_splits=None):
         cfg = model.config
         self.model, self.cfg = model, cfg
         bm = mems._bm if hasattr(mems, '_bm') else model._mems_to_bm(mems, out_ids.shape[0])
@@ -125,7 +139,7 @@ class Decoder:
         # 1 split 667 us/step, 2 splits 703, 4 splits 720 — the merge costs more than the better SM balance returns; with few sequences per GPU
         # (8 x 8 heads = 64 CTAs for 592 slots) a CTA streaming its whole ring alone is latency-bound, so the ring is cut to fill the chip.
         auto = max(1, min(8, 512 // max(1, B * H), (ML * dh) // (4 * 2048)))
-        self.attn_splits = _ATTN_SPLITS if _ATTN_SPLITS > 0 else auto
+        self.attn_splits = _ATTN_SPLITS if _ATTN_SPLITS > 0 else (attn_splits or auto)
         self.attn_ws = self.attn_cnt = None
         self.pf_bytes = int(min(B * H * ML * 2 * dh * 2, _PREFETCH_MB * 2 ** 20)) if self.pipe_attn else 0
         self._abl_qkv = torch.zeros(B, 3 * d, dtype=dt, device=dev) if _ABL else None
@@ -286,6 +300,86 @@ class Decoder:
                 self._step_kernels()
             done += 1
             if self.eos is not None and done % poll_every == 0 and int(self.unfinished.max().item()) == 0:
+                break
+        self.steps_done = done
+        return done
+
+
+class _BmSlice:
+    """Batch slice of the batch-major mems (what Decoder reads through `._bm`)."""
+
+    def __init__(self, bm, lo, hi):
+        self._bm = [t[lo:hi] for t in bm]
+
+
+class GroupedDecoder:
+    """The sequences of one GPU cut into `groups` independent Decoders whose steps are captured as PARALLEL branches of one CUDA graph.
+    A step is a chain of one HBM-bound kernel (attention over the ring) and six latency-bound ones per layer; sequences never interact
+    (batched sampling shards by sequence with no collective), so while one group's attention kernel streams its ring the other
+    groups run their Linears: HBM stays busy and the per-layer latency chain of a group is hidden behind the other groups' traffic.
+    Draws are keyed on the global sequence index, so the tokens do not depend on the grouping."""
+
+    def __init__(self, model, mems, out_ids, col0, groups, *, seq_offset=0, **kw):
+        B = out_ids.shape[0]
+        bm = mems._bm if hasattr(mems, '_bm') else model._mems_to_bm(mems, B)
+        per, rem = divmod(B, groups)
+        self.bounds, lo = [], 0
+        for g in range(groups):
+            hi = lo + per + (1 if g < rem else 0)
+            self.bounds.append((lo, hi))
+            lo = hi
+        # the other groups keep the chip busy while one group's attention kernel runs: no ring splits (4 splits: 727.6 us/step, none: 546.0)
+        kw.setdefault('attn_splits', 1)
+        self.decs = [Decoder(model, _BmSlice(bm, lo, hi), out_ids[lo:hi], col0, seq_offset=seq_offset + lo, **kw) for lo, hi in self.bounds]
+        self.eos = self.decs[0].eos
+        self.use_graph = self.decs[0].use_graph
+        self.graph = None
+        self.steps_done = 0
+
+    def set_unfinished(self, unfinished):
+        for d, (lo, hi) in zip(self.decs, self.bounds):
+            d.unfinished.copy_(unfinished[lo:hi])
+
+    def _all_unfinished_max(self):
+        return max(int(d.unfinished.max().item()) for d in self.decs)
+
+    def run(self, first_token, n_steps, poll_every=64):
+        if n_steps <= 0:
+            return 0
+        for d, (lo, hi) in zip(self.decs, self.bounds):
+            d.tok.copy_(first_token[lo:hi])
+            d.x0.copy_(ops.embed_fwd(d.tok, d.model._E, math.sqrt(d.d)))
+            d._step_kernels()                         # eager first step: warms caches, sets kernel attributes
+        done = 1
+        if self.use_graph and n_steps > 1:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            main = torch.cuda.Stream()
+            branches = [main] + [torch.cuda.Stream() for _ in self.decs[1:]]
+            main.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(main):
+                with torch.cuda.graph(g, stream=main):
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    for st, d in zip(branches, self.decs):
+                        if st is not main:
+                            st.wait_event(fork)
+                        with torch.cuda.stream(st):
+                            d._step_kernels()
+                    for st in branches[1:]:
+                        join = torch.cuda.Event()
+                        join.record(st)
+                        main.wait_event(join)
+            torch.cuda.current_stream().wait_stream(main)
+            self.graph = g
+        while done < n_steps:
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                for d in self.decs:
+                    d._step_kernels()
+            done += 1
+            if self.eos is not None and done % poll_every == 0 and self._all_unfinished_max() == 0:
                 break
         self.steps_done = done
         return done

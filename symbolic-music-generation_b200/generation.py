@@ -19,7 +19,8 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
              typical_p: Optional[float] = None, repetition_penalty: Optional[float] = None, renormalize_logits: Optional[bool] = None,
              num_beams: Optional[int] = None, num_beam_groups: Optional[int] = None, diversity_penalty=None, penalty_alpha=None,
              num_return_sequences: Optional[int] = None, eos_token_id='config', pad_token_id='config', generator=None,
-             return_step_scores: bool = False, use_decode_cache: bool = True, seed: int = 0, seq_offset: int = 0, use_cuda_graph: bool = True, use_fused_step: bool = False, **unused):
+             return_step_scores: bool = False, use_decode_cache: bool = True, seed: int = 0, seq_offset: int = 0, use_cuda_graph: bool = True, use_fused_step: bool = False,
+             decode_groups: Optional[int] = None, **unused):
     cfg = model.config
     if input_ids is None:
         raise ValueError('generate needs input_ids (the reference always passes a tokenised prompt, eval.py:276)')
@@ -77,10 +78,15 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
                     out_ids[:, cur] = nxt
                     cur += 1
                     if cur < max_length:
-                        dec = decode.Decoder(model, past, out_ids, cur, do_sample=do_sample, temperature=temperature, top_k=top_k, top_p=top_p,
-                                             eos_token_id=eos_token_id, pad_token_id=pad_token_id, seed=seed, seq_offset=seq_offset,
-                                             use_graph=use_cuda_graph, use_fused=use_fused_step)
-                        dec.unfinished.copy_(unfinished)
+                        dkw = dict(do_sample=do_sample, temperature=temperature, top_k=top_k, top_p=top_p, eos_token_id=eos_token_id,
+                                   pad_token_id=pad_token_id, seed=seed, seq_offset=seq_offset, use_graph=use_cuda_graph, use_fused=use_fused_step)
+                        groups = decode.sequence_groups(model, B, decode_groups) if not use_fused_step else 1
+                        if groups > 1:
+                            dec = decode.GroupedDecoder(model, past, out_ids, cur, groups, **dkw)
+                            dec.set_unfinished(unfinished)
+                        else:
+                            dec = decode.Decoder(model, past, out_ids, cur, **dkw)
+                            dec.unfinished.copy_(unfinished)
                         cur += dec.run(nxt, max_length - cur)
                     break
                 u = torch.rand(B, device=dev, generator=generator) if do_sample else None

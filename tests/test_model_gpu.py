@@ -302,3 +302,18 @@ def test_decode_step_bf16_scores_match_forward_path(pkg, mem_len, dh, H):
             worst = max(worst, ((got - want).abs() / want.abs()).max().item())
             tok = want.argmax(-1)                      # both paths are fed the forward path's greedy token
     assert worst < 2e-2, worst
+
+
+def test_grouped_decode_same_tokens_bf16(pkg):
+    """generate() with the sequences cut into parallel graph branches (GroupedDecoder) returns the tokens of the single-branch decode:
+    draws are keyed on the global sequence index and every per-sequence result is independent of the batch it is computed in."""
+    _, model = make_pair(pkg, 'bf16', mem_len=32, n_layer=2)
+    ids, _ = _batch(422, 7, 5, pad=False)
+    kw = dict(max_length=60, do_sample=True, top_k=8, top_p=0.95, temperature=1.0, renormalize_logits=True, seed=4321)
+    one = model.generate(input_ids=ids.cuda(), decode_groups=1, **kw)
+    for groups in (2, 3, 7):
+        many = model.generate(input_ids=ids.cuda(), decode_groups=groups, **kw)
+        assert torch.equal(one, many), groups
+    g1 = model.generate(input_ids=ids.cuda(), decode_groups=1, eos_token_id=None, do_sample=False, max_length=40)
+    g3 = model.generate(input_ids=ids.cuda(), decode_groups=3, eos_token_id=None, do_sample=False, max_length=40, use_cuda_graph=False)
+    assert torch.equal(g1, g3)
