@@ -325,6 +325,7 @@ def decode_probe(torch, pkg, pdist, cfg_train, args, dev, rank, world):
         ms = float(t.item())
     assert out.shape == (Bl, 16 + args.decode_new)
     peaks = measured_peaks()
+    n_groups = importlib.import_module(PKG + '.decode').sequence_groups(model, Bl)
     L, M, d = cfg.n_layer, cfg.mem_len, cfg.d_model
     n_params = sum(p.numel() for p in model.parameters())
     step_bytes = Bl * L * M * d * 2 + n_params * 2 + L * M * d * 2        # hidden-state mems + weights + R tables, bf16
@@ -332,7 +333,8 @@ def decode_probe(torch, pkg, pdist, cfg_train, args, dev, rank, world):
     ach = step_bytes / (ms_step / 1e3) / 1e9
     return {'metric': 'TXL decode tokens/s', 'value': args.decode_seqs * args.decode_new / (ms / 1e3), 'unit': 'tokens/s', 'ms_per_token_step': ms_step,
             'config': {'workload': f'cfg4: {args.decode_seqs} sequences ({Bl} per GPU), prompt 16, {args.decode_new} new tokens, top_k 8, mem_len {M}, '
-                                   'projected-K/V ring cache, CUDA-graph step'},
+                                   f'projected-K/V ring cache, CUDA-graph step with {n_groups} sequence group(s) as parallel branches, '
+                                   'programmatic dependent launch'},
             'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': ach / peaks['hbm'], 'traffic': None,
                          'algorithmic_bytes_per_step': step_bytes,
                          'note': 'denominator bytes = hidden-state mems once + weights + R tables (SURVEY §8d); the K/V cache actually read is 2x the mems term'}}

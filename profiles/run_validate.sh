@@ -9,5 +9,3 @@ timeout 600 python bench.py > gpurun_out/bench_r01_gen2.json 2> gpurun_out/bench
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r01_gen2_reference.json 2> gpurun_out/bench_r01_gen2_reference.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/decode_launches_gen2.csv python profiles/decode_probe.py > gpurun_out/decode_probe_gen2.log 2>&1
 python profiles/summarize_launches.py gpurun_out/decode_launches_gen2.csv > gpurun_out/decode_launches_gen2_summary.txt
-timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:decode_attn_pipe_kernel|dec_linear_kernel|dec_add_ln_kernel|decode_tail_kernel' --launch-skip 86 --launch-count 10 -f -o gpurun_out/decode_gen2_r01 python profiles/decode_probe.py > gpurun_out/decode_ncu_full.log 2>&1
-tail -3 gpurun_out/decode_ncu_full.log
