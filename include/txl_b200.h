@@ -167,6 +167,14 @@ int txl_masked_mean(const float* losses, int64_t N, float* loss_out, float* coun
  * out[1] += #{labels[b,t+1] != -100}.  out is int64[2] on the device (accumulated: zero it per logging window). */
 int txl_ntp_acc(const int64_t* preds, int64_t ld_preds, const int64_t* labels, int64_t ld_labels, int B, int T, int64_t* out, void* stream);
 
+/* ---- formats either side of the path ------------------------------------------------------
+ * txl_clm_labels: HF DataCollatorForLanguageModeling(mlm=False) as the reference builds it (musicnlp/trainer/train.py:360): labels = input_ids
+ *   with every pad id replaced by -100 (the tokenizer already padded to max_length, musicnlp/preprocess/dataset.py:361).  n int64 elements.
+ * txl_last_index_of: out[b] = last t with ids[b, t] == token, -1 if none — the cut point of MusicGenerator._truncate_last_bar
+ *   (musicnlp/trainer/eval.py:178-185: ids[:last start-of-bar]). */
+int txl_clm_labels(const int64_t* ids, int64_t* labels, int64_t n, int64_t pad_id, void* stream);
+int txl_last_index_of(const int64_t* ids, int64_t ld, int B, int T, int64_t token, int64_t* out, void* stream);
+
 /* ---- parameters --------------------------------------------------------------------------------- */
 int txl_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int txl_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);

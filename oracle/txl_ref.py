@@ -443,3 +443,66 @@ def ntp_acc_counts(preds, labels, pad=-100):
     p, l = preds[:, :-1], labels[:, 1:]
     msk = l != pad
     return int((p[msk] == l[msk]).sum().item()), int(msk.sum().item())
+
+
+def clm_collate(input_ids, pad_token_id, pad=-100):
+    """HF DataCollatorForLanguageModeling(mlm=False).torch_call on already padded examples, as instantiated at reference
+    musicnlp/trainer/train.py:360 (examples padded by the tokenizer, musicnlp/preprocess/dataset.py:361):
+    labels = input_ids.clone(); labels[labels == pad_token_id] = -100."""
+    labels = input_ids.clone()
+    labels[labels == pad_token_id] = pad
+    return {'input_ids': input_ids, 'labels': labels}
+
+
+def truncate_last_bar(ids, sob_token_id):
+    """reference musicnlp/trainer/eval.py:178-185 (`MusicGenerator._truncate_last_bar`) for one 1-D id tensor."""
+    assert ids.dim() == 1
+    idxs = torch.nonzero(ids.eq(sob_token_id)).flatten().tolist()
+    assert len(idxs) > 0, 'No start of bar token found when truncate_to_sob enabled'
+    return ids[:idxs[-1]].tolist()
+
+
+def hf_param_groups(model, weight_decay):
+    """HF Trainer.create_optimizer: decay every parameter that is not inside an nn.LayerNorm and whose name does not contain "bias"
+    (so r_w_bias / r_r_bias / CoreNet biases / crit bias are not decayed); tied weights appear once."""
+    ln_params = {id(p) for m in model.modules() if isinstance(m, torch.nn.LayerNorm) for p in m.parameters()}
+    seen, decay, no_decay = set(), [], []
+    for n, p in model.named_parameters():
+        if id(p) in seen:
+            continue
+        seen.add(id(p))
+        (no_decay if (id(p) in ln_params or 'bias' in n) else decay).append(p)
+    return [dict(params=decay, weight_decay=weight_decay), dict(params=no_decay, weight_decay=0.0)]
+
+
+def train_steps(model, batches, total_steps, learning_rate=3e-4, weight_decay=1e-2, warmup_ratio=0.1, max_grad_norm=1.0):
+    """The optimisation steps HF Trainer runs for the reference (musicnlp/trainer/train.py:166-190, :79-110; compute_loss + ntp_acc of
+    musicnlp/util/train/train_util_wrap.py:88-144): AdamW(torch) + clip_grad_norm_ + cosine schedule with ceil(ratio * steps) warm-up steps,
+    scheduler stepped after the optimizer.  Returns one dict per step: loss, learning_rate used, grad_norm before clipping, ntp_acc."""
+    import math
+    opt = torch.optim.AdamW(hf_param_groups(model, weight_decay), lr=learning_rate, betas=(0.9, 0.999), eps=1e-8)
+    warm = math.ceil(total_steps * warmup_ratio)
+
+    def lam(step):
+        if step < warm:
+            return step / max(1, warm)
+        prog = (step - warm) / max(1, total_steps - warm)
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lam)
+    model.train()
+    out = []
+    for ids, labels in batches:
+        o = model(input_ids=ids, labels=labels.clone())
+        with torch.no_grad():
+            model.eval()
+            preds = model(input_ids=ids).logits.argmax(-1)      # what outputs.logits.argmax(-1) is once logits are returned in training
+            model.train()
+        hit, cnt = ntp_acc_counts(preds, labels)
+        opt.zero_grad()
+        o.loss.backward()
+        gn = torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
+        lr_used = opt.param_groups[0]['lr']
+        opt.step()
+        sched.step()
+        out.append(dict(loss=float(o.loss.detach()), learning_rate=lr_used, grad_norm=float(gn), ntp_acc=hit / cnt if cnt else float('nan')))
+    return out

@@ -60,6 +60,8 @@ SIGNATURES = {
     'txl_logsoftmax_nll_bwd': (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp]),
     'txl_masked_mean': (_i, [_vp, _i64, _vp, _vp, _vp]),
     'txl_ntp_acc': (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp]),
+    'txl_clm_labels': (_i, [_vp, _vp, _i64, _i64, _vp]),
+    'txl_last_index_of': (_i, [_vp, _i64, _i, _i, _i64, _vp, _vp]),
     'txl_cast_f32_to_bf16': (_i, [_vp, _vp, _i64, _vp]),
     'txl_cast_bf16_to_f32': (_i, [_vp, _vp, _i64, _vp]),
     'txl_transpose': (_i, [_vp, _vp, _i64, _i64, _i, _vp]),

@@ -530,6 +530,43 @@ extern "C" int txl_ntp_acc(const int64_t* preds, int64_t ld_preds, const int64_t
   return TXL_OK;
 }
 
+// ------------------------------------------------------------------ formats either side of the path
+// DataCollatorForLanguageModeling(mlm=False): labels = input_ids with every pad id replaced by -100
+__global__ void clm_labels_kernel(const int64_t* __restrict__ ids, int64_t* __restrict__ labels, int64_t n, int64_t pad) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = ids[i];
+    labels[i] = t == pad ? -100 : t;
+  }
+}
+extern "C" int txl_clm_labels(const int64_t* ids, int64_t* labels, int64_t n, int64_t pad_id, void* stream) {
+  TXL_CHECK_ARG(ids && labels && n > 0, "clm_labels: bad args");
+  const int grid = (int)imin64(cdiv64(n, 256), (int64_t)txl_num_sms() * 8);
+  clm_labels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ids, labels, n, pad_id);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+// last position of `token` in every row (-1 if absent): one warp per row, scanning from the end
+__global__ void last_index_kernel(const int64_t* __restrict__ ids, int64_t ld, int B, int T, int64_t token, int64_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < B; b += gridDim.x * wpb) {
+    int64_t found = -1;
+    for (int base = ((T - 1) / 32) * 32; base >= 0 && found < 0; base -= 32) {
+      const int t = base + lane;
+      const bool hit = t < T && ids[(int64_t)b * ld + t] == token;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) found = base + (31 - __clz((int)m));
+    }
+    if (lane == 0) out[b] = found;
+  }
+}
+extern "C" int txl_last_index_of(const int64_t* ids, int64_t ld, int B, int T, int64_t token, int64_t* out, void* stream) {
+  TXL_CHECK_ARG(ids && out && B > 0 && T > 0 && ld >= T, "last_index_of: bad args");
+  const int grid = (int)imin64(cdiv64(B, 8), (int64_t)txl_num_sms() * 4);
+  last_index_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ids, ld, B, T, token, out);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
 // ------------------------------------------------------------------ casts / transposes / layout
 __global__ void cast_f2b_kernel(const float* __restrict__ s, bf16* __restrict__ d, int64_t n) {
   int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;

@@ -317,3 +317,30 @@ def test_grouped_decode_same_tokens_bf16(pkg):
     g1 = model.generate(input_ids=ids.cuda(), decode_groups=1, eos_token_id=None, do_sample=False, max_length=40)
     g3 = model.generate(input_ids=ids.cuda(), decode_groups=3, eos_token_id=None, do_sample=False, max_length=40, use_cuda_graph=False)
     assert torch.equal(g1, g3)
+
+
+def test_trainer_trajectory_matches_oracle_fp32(pkg):
+    """the loss / learning-rate / gradient-norm / ntp_acc trajectory of TxlTrainer (fused clip + AdamW, cosine warm-up, device
+    accuracy counts, inputs through io.DeviceBatchPipeline) == the oracle's HF-Trainer loop on the same batches and weights (fp32 mode, dropout 0)."""
+    import importlib
+    from oracle.txl_ref import train_steps
+    trainer_mod = importlib.import_module('symbolic-music-generation_b200.trainer')
+    io = importlib.import_module('symbolic-music-generation_b200.io')
+    ref, model = make_pair(pkg, 'fp32')
+    g = torch.Generator().manual_seed(77)
+    host = []
+    for _ in range(6):
+        ids = torch.randint(2, 422, (3, 40), generator=g)
+        ids[1, 30:] = 1                                        # pad tail -> -100 labels through the collator
+        host.append(ids)
+    labels = [torch.where(i == 1, torch.full_like(i, -100), i) for i in host]
+    want = train_steps(ref, list(zip(host, labels)), total_steps=6, learning_rate=1e-3, weight_decay=1e-2, warmup_ratio=0.3)
+    tr = trainer_mod.TxlTrainer(model, total_steps=6, learning_rate=1e-3, weight_decay=1e-2, warmup_ratio=0.3)
+    got = tr.train(io.DeviceBatchPipeline(iter(host), pad_token_id=1))
+    assert len(got) == 6
+    for w, h in zip(want, got):
+        assert abs(h['learning_rate'] - w['learning_rate']) < 1e-12
+        assert abs(h['loss'] - w['loss']) / w['loss'] < 2e-4, (h, w)
+        assert abs(h['grad_norm'] - w['grad_norm']) / w['grad_norm'] < 2e-3, (h, w)
+        assert abs(h['ntp_acc'] - w['ntp_acc']) < 0.03, (h, w)      # a near-tie of two logits may flip one of ~100 positions
+    assert got[-1]['loss'] < got[1]['loss']

@@ -516,3 +516,35 @@ def test_decode_tail_equals_separate_kernels(pkg, ops, do_sample, top_k, top_p, 
         for k in a:
             assert torch.equal(a[k], b[k]), (step, k)
         assert torch.equal(x0, xa) and int(arrive.item()) == 0 and int(b['pos'].item()) == step + 1
+
+
+@pytest.mark.gpu
+def test_io_formats_bit_exact(pkg):
+    """device collator labels, batched last-bar truncation and the pinned double-buffered pipeline == the oracle restatements."""
+    import importlib
+    io = importlib.import_module('symbolic-music-generation_b200.io')
+    from oracle.txl_ref import clm_collate, truncate_last_bar
+    g = torch.Generator().manual_seed(77)
+    for B, T in [(1, 1), (3, 33), (32, 1024), (5, 100)]:
+        ids = torch.randint(0, 12, (B, T), generator=g)
+        ids[0, T // 2:] = 1                                   # a padded tail
+        assert torch.equal(io.clm_labels(ids.cuda(), 1).cpu(), clm_collate(ids, 1)['labels'])
+        li = io.last_index_of(ids.cuda(), 9).cpu()
+        for b in range(B):
+            nz = (ids[b] == 9).nonzero().flatten()
+            assert li[b].item() == (nz[-1].item() if len(nz) else -1)
+        wide = torch.full((B, T + 7), 9, dtype=torch.int64).cuda()   # strided rows: the 9s past column T must not be seen
+        wide[:, :T] = ids.cuda()
+        assert torch.equal(io.last_index_of(wide[:, :T], 9).cpu(), li)
+    ids = torch.randint(0, 12, (6, 64), generator=g)
+    ids[:, 5] = 9
+    assert io.truncate_last_bar(ids.cuda(), 9) == [truncate_last_bar(r, 9) for r in ids]
+    with pytest.raises(AssertionError):
+        io.truncate_last_bar(torch.zeros(2, 8, dtype=torch.int64).cuda(), 9)
+    # pipeline: order, contents, labels; odd number of batches, a single batch, and none
+    for n in (5, 1, 0):
+        host = [torch.randint(0, 12, (4, 48), generator=g) for _ in range(n)]
+        got = [(i.cpu(), l.cpu()) for i, l in io.DeviceBatchPipeline(iter(host), pad_token_id=1)]
+        assert len(got) == n
+        for h, (i, l) in zip(host, got):
+            assert torch.equal(i, h) and torch.equal(l, clm_collate(h, 1)['labels'])

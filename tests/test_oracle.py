@@ -131,3 +131,34 @@ def test_ntp_acc_counts_known_answer():
     # row 0: preds[:3] = 5,6,7 vs labels[1:] = 5,9,7 -> 2 of 3; row 1: preds[:3] = 1,1,1 vs 1,-100,-100 -> 1 of 1
     assert ntp_acc_counts(preds, labels) == (3, 4)
     assert ntp_acc_counts(preds[:, :1], labels[:, :1]) == (0, 0)
+
+
+def test_clm_collate_and_truncate_known_answers():
+    """KATs by hand for the two format steps either side of the path (train.py:360, eval.py:178-185)."""
+    from oracle.txl_ref import clm_collate, truncate_last_bar
+    ids = torch.tensor([[7, 3, 1, 1], [1, 5, 6, 2]])
+    out = clm_collate(ids, pad_token_id=1)
+    assert out['labels'].tolist() == [[7, 3, -100, -100], [-100, 5, 6, 2]] and out['input_ids'] is ids
+    assert truncate_last_bar(torch.tensor([4, 9, 5, 9, 6]), 9) == [4, 9, 5]
+    assert truncate_last_bar(torch.tensor([9, 5]), 9) == []
+    with pytest.raises(AssertionError):
+        truncate_last_bar(torch.tensor([4, 5]), 9)
+
+
+def test_oracle_train_steps_schedule_and_groups():
+    """HF rules restated in the oracle's training loop: ceil warm-up, lambda(0) = 0 at the first step, no decay on biases / LayerNorm."""
+    from oracle.txl_ref import hf_param_groups, train_steps
+    torch.manual_seed(0)
+    m = RefTransfoXLLMHeadModel(RefConfig(vocab_size=50, d_model=32, d_embed=32, n_head=2, d_head=16, d_inner=64, n_layer=1, mem_len=8, dropout=0.0))
+    groups = hf_param_groups(m, 0.01)
+    n_decay, n_nodecay = sum(p.numel() for p in groups[0]['params']), sum(p.numel() for p in groups[1]['params'])
+    assert n_decay + n_nodecay == sum(p.numel() for p in m.parameters())
+    names_nd = {n for n, p in m.named_parameters() if any(p is q for q in groups[1]['params'])}
+    assert 'transformer.layers.0.dec_attn.r_w_bias' in names_nd and 'transformer.layers.0.pos_ff.layer_norm.weight' in names_nd
+    assert 'transformer.layers.0.dec_attn.qkv_net.weight' not in names_nd
+    g = torch.Generator().manual_seed(1)
+    batches = [(torch.randint(0, 50, (2, 12), generator=g),) * 2 for _ in range(5)]
+    logs = train_steps(m, batches, total_steps=5, warmup_ratio=0.3)       # ceil(1.5) = 2 warm-up steps
+    lrs = [l['learning_rate'] for l in logs]
+    assert lrs[0] == 0.0 and abs(lrs[1] - 1.5e-4) < 1e-12 and abs(lrs[2] - 3e-4) < 1e-12 and lrs[3] < lrs[2] and lrs[4] < lrs[3]
+    assert logs[-1]['loss'] < logs[1]['loss']
