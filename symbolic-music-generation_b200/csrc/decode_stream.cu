@@ -538,7 +538,7 @@ extern "C" int txl_decode_attn_pipe(const void* qkv, void* kvc, const void* r_he
                             (const bf16*)r_head_major, rwb, rrb, (bf16*)out, pos, H, ML, (float*)ws, counters));                              \
   }
 #define DA_LAUNCH(DHV) { if (cfg == 1) DA_LAUNCH2(DHV, 2, 3) else if (cfg == 2) DA_LAUNCH2(DHV, 2, 4) else if (cfg == 3) DA_LAUNCH2(DHV, 4, 2) \
-                         else if (cfg == 4) DA_LAUNCH2(DHV, 4, 4) else if (cfg == 5) DA_LAUNCH2(DHV, 2, 2) else DA_LAUNCH2(DHV, 1, 4) }
+                         else if (cfg == 4) DA_LAUNCH2(DHV, 4, 4) else if (cfg == 5) DA_LAUNCH2(DHV, 2, 2) else if (cfg == 6) DA_LAUNCH2(DHV, 4, 3) else DA_LAUNCH2(DHV, 1, 4) }
   if (dh == 32) DA_LAUNCH(32) else if (dh == 64) DA_LAUNCH(64) else DA_LAUNCH(128)
 #undef DA_LAUNCH
 #undef DA_LAUNCH2
