@@ -3,6 +3,15 @@ kernel, the whole step replayed as a CUDA graph (no host round trip between toke
 
 Follows HF 4.25 `sample` / `greedy_search` step for step: embed last token -> L x (qkv, relative-position attention
 over [mems ; current] with the same_length band, o_net + LN, FF + LN) -> log-softmax -> warpers -> draw -> eos/pad bookkeeping -> append.
+
+Two generations of kernels share this file:
+  * bf16 (the measured path): `txl_dec_linear` / `txl_dec_add_ln` / `txl_decode_attn_pipe` / `txl_decode_tail` (csrc/decode_stream.cu,
+    csrc/sample.cu) over an interleaved k|v ring, launched with programmatic stream serialization; `GroupedDecoder` captures groups of 16
+    sequences as parallel branches of one graph.  74 launches per step and group.
+  * fp32 parity mode (token-identical greedy decode against the oracle) and `TXL_DECODE_GEN1=1`: the first-generation kernels of csrc/decode.cu.
+Environment switches (A/B measurements, see profiles/r01_decode_ab.txt; defaults are the measured best): TXL_DECODE_GEN1, TXL_DECODE_PDL,
+TXL_DECODE_TAIL, TXL_DECODE_GROUPS, TXL_DECODE_ATTN_SPLITS, TXL_DECODE_ATTN_CFG, TXL_DECODE_PREFETCH_MB, TXL_DEC_SPLIT_COLS,
+TXL_DEC_LINEAR_2STAGE, TXL_DECODE_ABL (timing ablation: results are garbage).
 """
 from __future__ import annotations
 

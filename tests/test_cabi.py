@@ -100,3 +100,44 @@ def test_prepare_inputs_for_generation(pkg):
     past = [torch.zeros(3, 2, 4)]
     out = m.prepare_inputs_for_generation(ids, past=past)
     assert out['mems'] is past and out['input_ids'].tolist() == [[4], [9]]
+
+
+def test_decode_sequence_groups_rule(pkg):
+    """Host logic of the grouped decode (no GPU): groups of 16 sequences from 32 up, capped at 4; explicit requests are clamped to [1, B];
+    fp32 models and large vocabularies stay on the single-branch path."""
+    import importlib
+    import types
+    import torch
+    decode = importlib.import_module('symbolic-music-generation_b200.decode')
+
+    def fake(dtype, V=1190):
+        return types.SimpleNamespace(_E=torch.empty(1, dtype=dtype), config=types.SimpleNamespace(vocab_size=V))
+    m = fake(torch.bfloat16)
+    assert [decode.sequence_groups(m, B) for B in (1, 8, 16, 31, 32, 47, 48, 64, 100)] == [1, 1, 1, 1, 2, 2, 3, 4, 4]
+    assert decode.sequence_groups(m, 7, requested=3) == 3 and decode.sequence_groups(m, 2, requested=5) == 2 and decode.sequence_groups(m, 9, requested=0) == 1
+    assert decode.sequence_groups(fake(torch.float32), 64) == 1 and decode.sequence_groups(fake(torch.bfloat16, V=40000), 64) == 1
+    bounds = []
+    per, rem = divmod(7, 3)
+    lo = 0
+    for g in range(3):
+        hi = lo + per + (1 if g < rem else 0)
+        bounds.append((lo, hi))
+        lo = hi
+    assert bounds == [(0, 3), (3, 5), (5, 7)]
+
+
+def test_trainer_schedule_is_hf_cosine_with_ceil_warmup(pkg):
+    """trainer.warmup_steps / optim.cosine_with_warmup == HF get_cosine_schedule_with_warmup with ceil(ratio * steps) warm-up steps
+    (the oracle's LambdaLR restates the same rule; GPU trajectory test compares the two loops step by step)."""
+    import importlib
+    import math
+    trainer = importlib.import_module('symbolic-music-generation_b200.trainer')
+    optim = importlib.import_module('symbolic-music-generation_b200.optim')
+    assert trainer.warmup_steps(6, 0.3) == 2 and trainer.warmup_steps(1000, 0.1) == 100 and trainer.warmup_steps(10, 0.01) == 1
+    for total, warm in [(6, 2), (1000, 100), (10, 0)]:
+        for step in range(total + 1):
+            if step < warm:
+                want = 3e-4 * step / max(1, warm)
+            else:
+                want = 3e-4 * max(0.0, 0.5 * (1.0 + math.cos(math.pi * (step - warm) / max(1, total - warm))))
+            assert abs(optim.cosine_with_warmup(step, total, warm, 3e-4) - want) < 1e-15
