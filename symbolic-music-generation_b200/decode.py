@@ -149,6 +149,9 @@ class Decoder:
         # (8 x 8 heads = 64 CTAs for 592 slots) a CTA streaming its whole ring alone is latency-bound, so the ring is cut to fill the chip.
         auto = max(1, min(8, 512 // max(1, B * H), (ML * dh) // (4 * 2048)))
         self.attn_splits = _ATTN_SPLITS if _ATTN_SPLITS > 0 else (attn_splits or auto)
+        # stage geometry of the attention kernel: with ring splits a CTA only sees mem_len / splits keys, so it needs short stages to pipeline at
+        # all (8 sequences, 8 splits: 32 keys x 4 stages 421 us/step, 128 keys x 2 stages 689); unsplit rings take the library default (128 x 2)
+        self.attn_cfg = 0 if (self.attn_splits > 1 and 'TXL_DECODE_ATTN_CFG' not in os.environ) else None
         self.attn_ws = self.attn_cnt = None
         self.pf_bytes = int(min(B * H * ML * 2 * dh * 2, _PREFETCH_MB * 2 ** 20)) if self.pipe_attn else 0
         self._abl_qkv = torch.zeros(B, 3 * d, dtype=dt, device=dev) if _ABL else None
@@ -213,6 +216,7 @@ class Decoder:
             self._fused_call(0)
             return self._finish_step(self.logits32)
         pdl_old = lib.txl_set_pdl(1) if (self.pipe_attn and _PDL) else None
+        cfg_old = lib.txl_decode_attn_pipe_config(self.attn_cfg) if (self.pipe_attn and self.attn_cfg is not None) else None
         try:
             # second generation: x0 already holds the embedding of the current token (run() for the first step, the tail kernel afterwards)
             x = self.x0 if self.gen2_tail else ops.embed_fwd(self.tok, m._E, math.sqrt(d))
@@ -253,6 +257,8 @@ class Decoder:
         finally:
             if pdl_old is not None:
                 lib.txl_set_pdl(pdl_old)
+            if cfg_old is not None:
+                lib.txl_decode_attn_pipe_config(cfg_old)
         return self._finish_step(self.logits)
 
     def _finish_step(self, logits):
@@ -296,9 +302,13 @@ class Decoder:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                # capture one step; nothing here depends on host-side values that change between steps
-                with torch.cuda.graph(g, stream=side):
+                # capture one step; nothing here depends on host-side values that change between steps.  capture_begin / capture_end directly:
+                # the torch.cuda.graph context manager also runs gc.collect() and torch.cuda.empty_cache(), a fixed cost per generate() call
+                g.capture_begin()
+                try:
                     self._step_kernels()
+                finally:
+                    g.capture_end()
             torch.cuda.current_stream().wait_stream(side)
             self.graph = g
             # the capture itself does not execute: pos / caches are untouched
@@ -367,7 +377,8 @@ class GroupedDecoder:
             branches = [main] + [torch.cuda.Stream() for _ in self.decs[1:]]
             main.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(main):
-                with torch.cuda.graph(g, stream=main):
+                g.capture_begin()                     # not torch.cuda.graph(): that also runs gc.collect() + empty_cache() on every call
+                try:
                     fork = torch.cuda.Event()
                     fork.record(main)
                     for st, d in zip(branches, self.decs):
@@ -379,6 +390,8 @@ class GroupedDecoder:
                         join = torch.cuda.Event()
                         join.record(st)
                         main.wait_event(join)
+                finally:
+                    g.capture_end()
             torch.cuda.current_stream().wait_stream(main)
             self.graph = g
         while done < n_steps:
