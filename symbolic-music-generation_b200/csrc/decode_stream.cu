@@ -1,17 +1,21 @@
-// decode_stream.cu — the two bandwidth kernels of the bf16 decode step, second generation.
+// decode_stream.cu — the kernels of the bf16 decode step, second generation (the first generation lives on in decode.cu for the fp32 parity mode).
 //
 // (1) dec_linear_kernel: y[M<=64, N] = x[M,K] W[N,K]^T (+bias)(ReLU) for the per-step Linears.  The step's Linears are weight-streaming
 //     problems of 0.5-2 MB with <= 64 rows: a 128-row tcgen05 tile leaves 4-16 CTAs to pull the whole matrix (measured 12.3 us per launch).
-//     Here a CTA owns 8 or 16 output features (64-192 CTAs), its 8 warps split K in 32-wide blocks and read x and W straight from
-//     global/L2 in 16-byte pieces that already ARE mma.sync fragments (the k index inside an MMA is only a label: slot pair (2t,2t+1) /
-//     (2t+8,2t+9) of step j is fed from elements 8t+4j .. 8t+4j+3 of the 32-block on both operands), every load of a warp is issued
-//     before the first MMA, partial sums meet in shared memory.                                              [A.3, A.6 at T=1; A.7]
-// (2) decode_attn_pipe_kernel: the T=1 relative-position attention over the projected-K/V ring.  The first-generation kernel kept only
+//     Here a CTA owns 8 or 16 output features (96-150 CTAs), x and its weight rows arrive through a cp.async ring, its 8 warps split every
+//     256-column chunk in 32-wide blocks and read 16-byte pieces that already ARE mma.sync fragments (the k index inside an MMA is only a
+//     label: slot pair (2t,2t+1) / (2t+8,2t+9) of step j is fed from elements 8t+4j .. 8t+4j+3 of the 32-block on both operands), partial sums
+//     meet in shared memory.  gridDim.y > 1 = split-K: fp32 planes, summed by (2).                          [A.3, A.6 at T=1; A.7]
+// (2) dec_add_ln_kernel: LayerNorm(x + sum of the split-K planes + bias), the residual blocks after o_net and CoreNet.3.        [A.3-8, A.6]
+// (3) decode_attn_pipe_kernel: the T=1 relative-position attention over the projected k|v ring.  The first-generation kernel kept only
 //     three 16-byte loads per thread in flight (ptxas does not hoist loads over the shuffle / branch of the previous key) and reached
-//     2.8 TB/s.  Here a producer lane streams K, V and the r rows of 32-key chunks with cp.async.bulk into a 4-stage shared-memory ring
-//     (full/empty mbarriers), 4 CTAs per SM keep ~190 KB per SM in flight, 8 consumer warps run the one-pass (max, sum, output) update.
-//     The r table is stored head-major [H, mem_len+1, d_head] so that a chunk's rows are one (two at the ring's wrap point) contiguous run.
-//     The current token never goes through the ring copy: its k/v come from the qkv row, so no generic->async proxy ordering is needed.
+//     2.8 TB/s.  Here a producer lane streams the k|v rows (interleaved per key: one contiguous run per stage) and the r rows of a stage with
+//     cp.async.bulk into a shared-memory ring (full/empty mbarriers; default 128 keys x 2 stages, 2 CTAs per SM = 192 KB per SM in flight),
+//     8 consumer warps run the one-pass (max, sum, output) update.  The r table is stored head-major [H, mem_len+1, d_head] so that a stage's
+//     rows are one (two at the ring's wrap point) contiguous run.  The current token never goes through the ring copy: its k/v come from
+//     the qkv row, so no generic->async proxy ordering is needed and the ring streams before the previous kernel has finished.
+// All three run under programmatic dependent launch (common.cuh): whatever does not depend on the previous kernel of the step (weights, ring)
+// is requested before griddepcontrol.wait.
 #include "tc_common.cuh"
 #include <stdlib.h>
 
