@@ -141,3 +141,30 @@ def test_trainer_schedule_is_hf_cosine_with_ceil_warmup(pkg):
             else:
                 want = 3e-4 * max(0.0, 0.5 * (1.0 + math.cos(math.pi * (step - warm) / max(1, total - warm))))
             assert abs(optim.cosine_with_warmup(step, total, warm, 3e-4) - want) < 1e-15
+
+
+def test_argument_errors_are_reported_before_any_launch(built_lib):
+    """Error behaviour of the boundary (0 / negative return codes + txl_last_error(), nothing silently different): bad shapes and
+    null pointers are refused with TXL_EINVAL and a message by the argument checks that precede every launch — callable without a GPU."""
+    L = importlib.import_module(PKG + '._lib')
+    lib = L.load()
+    EINVAL = -1
+    one = ctypes.c_void_p(256)           # a non-null, 16-byte aligned pointer value: the checks below never dereference it
+
+    def refused(rc, needle):
+        msg = lib.txl_last_error().decode()
+        assert rc == EINVAL and needle in msg, (rc, msg)
+    refused(lib.txl_dec_linear(one, 64, one, 64, None, one, 64, 65, 8, 64, 0, 0, 1, None, 0, None), 'dec_linear')          # M > 64
+    refused(lib.txl_dec_linear(one, 64, one, 64, None, one, 64, 4, 8, 40, 0, 0, 1, None, 0, None), 'dec_linear')           # K % 32 != 0
+    refused(lib.txl_dec_linear(one, 64, one, 64, None, one, 64, 4, 8, 64, 1, 1, 2, None, 0, None), 'split-K')              # ReLU with split-K
+    refused(lib.txl_dec_linear(None, 64, one, 64, None, one, 64, 4, 8, 64, 0, 0, 1, None, 0, None), 'dec_linear')          # null operand
+    refused(lib.txl_dec_add_ln(one, None, 2, None, one, one, one, 4, 64, 1e-5, None, 0, None), 'dec_add_ln')               # planes missing
+    refused(lib.txl_dec_add_ln(one, one, 1, None, one, one, one, 4, 2048, 1e-5, None, 0, None), 'dec_add_ln')              # d > 1024
+    refused(lib.txl_decode_attn_pipe(one, one, one, one, one, one, one, 2, 2, 16, 48, 1, None, None, None), 'd_head')       # d_head not in {32,64,128}
+    refused(lib.txl_decode_attn_pipe(one, one, one, one, one, one, one, 2, 2, 16, 64, 2, None, None, None), 'splits')       # splits without workspace
+    refused(lib.txl_decode_tail(one, 8, None, 2, 16, 1, 0.0, 8, 1.0, 1, 0, one, one, one, 8, 0, one, one, 0, 0, 1, one, one, 8, 1.0, None), 'decode_tail')   # ldl < V / temperature 0
+    refused(lib.txl_ntp_acc(one, 3, one, 8, 2, 8, one, None), 'ntp_acc')                                                    # row pitch < T
+    refused(lib.txl_clm_labels(one, None, 8, 1, None), 'clm_labels')
+    refused(lib.txl_last_index_of(one, 4, 2, 8, 9, one, None), 'last_index_of')                                             # row pitch < T
+    refused(lib.txl_sample(one, 2, 16, 1, 0.0, 8, 1.0, one, one, None, None, None), 'sample')                               # temperature 0
+    assert lib.txl_decode_attn_pipe_ws_bytes(2, 3, 64, 1) == 0 and lib.txl_decode_attn_pipe_ws_bytes(2, 3, 64, 4) == 2 * 3 * 4 * 66 * 4
