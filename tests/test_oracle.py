@@ -162,3 +162,33 @@ def test_oracle_train_steps_schedule_and_groups():
     lrs = [l['learning_rate'] for l in logs]
     assert lrs[0] == 0.0 and abs(lrs[1] - 1.5e-4) < 1e-12 and abs(lrs[2] - 3e-4) < 1e-12 and lrs[3] < lrs[2] and lrs[4] < lrs[3]
     assert logs[-1]['loss'] < logs[1]['loss']
+
+
+@pytest.mark.parametrize('ML,clamp', [(8, 1024), (8, 3), (33, 16), (128, 1024), (5, 5)])
+def test_decode_ring_index_map_equals_literal_shift(ML, clamp):
+    """Integer indexing of the T=1 decode step, bit-exact on the CPU: the ring-slot -> r-row closed form of csrc/decode_stream.cu / decode.cu
+    (slot s <= cur: ML - cur + s, else s - cur; the bulk-copy split of a stage at the wrap point) addresses exactly the relative positions that
+    HF's pad/reshape `_rel_shift` + same_length mask give for qlen=1, mlen=mem_len=ML, and key 0 (the slot being overwritten) is the masked one."""
+    from oracle.txl_ref import literal_index_maps, literal_pos_seq
+    masked, ridx = literal_index_maps(1, ML, ML, clamp, True)
+    assert masked[0].tolist() == [1] + [0] * ML                   # cat(mems, cur): only the oldest memory is outside the band
+    table_pos = literal_pos_seq(ML + 1, clamp)                    # relative-position value of r row x (what posemb_table(ML+1) encodes)
+    for pos in list(range(0, 2 * ML + 3)):
+        cur = pos % ML
+        xs = []
+        for s in range(ML):
+            x = ML - cur + s if s <= cur else s - cur            # the kernels' closed form
+            dist = (cur - s) % ML
+            assert x == ML - dist
+            xs.append(x)
+            # ring slot s holds the token `dist` steps back = key j = ML - dist of cat(mems, cur) (slot cur = the new token = key ML)
+            j = ML - dist
+            assert masked[0, j] == 0 and int(ridx[0, j]) == int(table_pos[x])
+        assert sorted(xs) == list(range(1, ML + 1)) and xs[cur] == ML
+        # the producer's two bulk copies per stage reproduce the same rows (stage sizes of every geometry the kernel has)
+        for CKS in (32, 64, 128):
+            for s0 in range(0, ML, CKS):
+                n = min(CKS, ML - s0)
+                n1 = max(0, min(n, cur + 1 - s0))
+                rows = [ML - cur + s0 + i for i in range(n1)] + [s0 + n1 - cur + i for i in range(n - n1)]
+                assert rows == xs[s0:s0 + n]
