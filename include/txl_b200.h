@@ -173,6 +173,11 @@ int txl_ntp_acc(const int64_t* preds, int64_t ld_preds, const int64_t* labels, i
  * txl_last_index_of: out[b] = last t with ids[b, t] == token, -1 if none — the cut point of MusicGenerator._truncate_last_bar
  *   (musicnlp/trainer/eval.py:178-185: ids[:last start-of-bar]). */
 int txl_clm_labels(const int64_t* ids, int64_t* labels, int64_t n, int64_t pad_id, void* stream);
+/* labels [B, T] int64 (row stride ld) -> shift [B*T]: shift[b*T+t] = labels[b, t+1], -100 in the last column (HF crit's `labels[..., 1:]`,
+ * A.6), after the reference's all-pad first-row fix-up applied IN PLACE on the device with its own arithmetic
+ * (musicnlp/models/transformer_xl.py:176-182: sum(labels[0,1:]) == (T-1)*-100  =>  labels[0,1] = eos).  bad (optional, int32, accumulated):
+ * number of labels outside [0, V) that are not -100. */
+int txl_shift_labels(int64_t* labels, int64_t ld, int B, int T, int64_t eos, int V, int64_t* shift, int* bad, void* stream);
 int txl_last_index_of(const int64_t* ids, int64_t ld, int B, int T, int64_t token, int64_t* out, void* stream);
 
 /* ---- parameters --------------------------------------------------------------------------------- */
@@ -255,21 +260,6 @@ int txl_decode_tail(const float* logits, int64_t ldl, float* scores, int B, int 
                     int32_t* pos, int* arrive, int64_t eos, int64_t pad, int use_eos, const void* E, void* x0, int d, float emb_scale,
                     void* stream);
 int txl_set_pdl(int on);
-
-/* Fused decode step: embedding + all L layers (qkv, ring append + band attention, o_net, LN, FF1, FF2, LN) + LM-head GEMM as ONE persistent
- * cooperative kernel (grid barriers between stages; every Linear split over 16-column x 256-K work items with fp32 partials summed by the
- * consumer stage).  Per-layer pointers arrive as host arrays of L device pointers.  Call once with build_layer_table=1 (uploads the pointer
- * table into `ws`, synchronises the stream), then once per token with build_layer_table=0 (a single launch; capturable in a CUDA graph).
- * logits [B, Vp] fp32 = x E^T + out_bias (log-softmax / sampling / txl_decode_commit follow as separate calls).  B <= 64. */
-int64_t txl_decode_fused_workspace(int B, int d, int di, int V, int L, int dtype);
-/* profiling hook: device buffer (>= 7 L + 4 uint64) receiving %globaltimer stamps after every stage of the fused step; NULL disables */
-int txl_decode_fused_set_timestamps(unsigned long long* dev_buf);
-int txl_decode_fused_step(const void* const* wqkv, const void* const* wo, const void* const* w1, const void* const* w2, const void* const* rtab,
-                          const float* const* b1, const float* const* b2, const float* const* rwb, const float* const* rrb,
-                          const float* const* ln1w, const float* const* ln1b, const float* const* ln2w, const float* const* ln2b,
-                          void* const* kc, void* const* vc, const void* E, const float* out_bias, const int64_t* tok, const int32_t* pos,
-                          float* logits, void* ws, int build_layer_table, int B, int H, int dh, int d, int di, int ML, int L, int V, int Vp,
-                          float eps, int dtype, void* stream);
 
 /* ---- mems ring / layout helpers  [A.8' _update_mems] ----------------------------------------------
  * time-major (L?,rows,B,d) <-> batch-major copies used at the Python boundary */

@@ -17,23 +17,3 @@ prompt = torch.randint(1, 1190, (B, 16)).cuda()
 out = model.generate(input_ids=prompt, max_length=16 + NEW, do_sample=True, top_k=8, eos_token_id=None, seed=77, use_cuda_graph=False)
 torch.cuda.synchronize()
 print(out.shape)
-
-if os.environ.get('PROBE_STAGES'):
-    L_ = importlib.import_module('symbolic-music-generation_b200._lib')
-    lib = L_.load()
-    buf = torch.zeros(7 * 12 + 8, dtype=torch.int64, device='cuda')
-    lib.txl_decode_fused_set_timestamps(buf.data_ptr())
-    out = model.generate(input_ids=prompt, max_length=16 + 4, do_sample=True, top_k=8, eos_token_id=None, seed=77, use_cuda_graph=False, use_fused_step=True)
-    torch.cuda.synchronize()
-    lib.txl_decode_fused_set_timestamps(None)
-    t = buf.cpu().tolist()
-    # NOTE: the stamp after the embedding barrier is not emitted, so stage i is labelled with the name of stage i-1's successor:
-    # read 'qkv' as attn, 'attn' as o, 'o' as ln1, 'ln1' as ff1, 'ff1' as ff2, 'ff2' as ln2, 'ln2' as the next layer's qkv.
-    names = ['embed'] + [f'L{l}.{s}' for l in range(12) for s in ('qkv', 'attn', 'o', 'ln1', 'ff1', 'ff2', 'ln2')] + ['head', 'empty_sync']
-    d = [(t[i + 1] - t[i]) / 1e3 for i in range(len(names))]
-    agg = {}
-    for n, v in zip(names, d):
-        k = n.split('.')[-1]
-        agg[k] = agg.get(k, 0) + v
-    print('layer 5 stages:', {n: round(v, 1) for n, v in zip(names, d) if n.startswith('L5.')})
-    print('fused step stage times (us, summed over layers):', {k: round(v, 1) for k, v in agg.items()}, 'total', round(sum(d), 1))

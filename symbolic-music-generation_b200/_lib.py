@@ -61,6 +61,7 @@ SIGNATURES = {
     'txl_masked_mean': (_i, [_vp, _i64, _vp, _vp, _vp]),
     'txl_ntp_acc': (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp]),
     'txl_clm_labels': (_i, [_vp, _vp, _i64, _i64, _vp]),
+    'txl_shift_labels': (_i, [_vp, _i64, _i, _i, _i64, _i, _vp, _vp, _vp]),
     'txl_last_index_of': (_i, [_vp, _i64, _i, _i, _i64, _vp, _vp]),
     'txl_cast_f32_to_bf16': (_i, [_vp, _vp, _i64, _vp]),
     'txl_cast_bf16_to_f32': (_i, [_vp, _vp, _i64, _vp]),
@@ -82,9 +83,6 @@ SIGNATURES = {
     'txl_decode_tail': (_i, [_vp, _i64, _vp, _i, _i, _i, _f, _i, _f, _u64, _i64, _vp, _vp, _vp, _i64, _i, _vp, _vp, _i64, _i64, _i, _vp, _vp, _i, _f, _vp]),
     'txl_set_pdl': (_i, [_i]),
     'txl_decode_attn_pipe_config': (_i, [_i]),
-    'txl_decode_fused_workspace': (_i64, [_i, _i, _i, _i, _i, _i]),
-    'txl_decode_fused_set_timestamps': (_i, [_vp]),
-    'txl_decode_fused_step': (_i, [_vp] * 15 + [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     'txl_tm_to_bm': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'txl_bm_to_tm': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }

@@ -321,7 +321,9 @@ __global__ void decode_uniform_kernel(float* __restrict__ u, int B, uint64_t see
 extern "C" int txl_decode_cache_init(const void* kv_mem, int64_t ld, void* kc, void* vc, int B, int H, int ML, int dh, int dtype, void* stream) {
   TXL_CHECK_ARG(kv_mem && kc && vc && B > 0 && H > 0 && ML > 0 && dh > 0 && ld >= 2 * H * dh, "decode_cache_init: bad args");
   int grid = (int)imin64(cdiv64((int64_t)B * H * ML * dh, 256), (int64_t)txl_num_sms() * 16);
-  DEC_DISPATCH(dtype, (cache_init_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)kv_mem, ld, (T*)kc, (T*)vc, B, H, ML, dh)));
+  TXL_CHECK_ARG(dtype == TXL_F32, "decode_cache_init: fp32 parity mode only (bf16 decodes over the interleaved ring of txl_decode_cache_init_kv)");
+  typedef float T;
+  cache_init_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)kv_mem, ld, (T*)kc, (T*)vc, B, H, ML, dh);
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }
@@ -339,7 +341,9 @@ extern "C" int txl_decode_attn(const void* qkv, void* kc, void* vc, const void* 
     if (smem > 48 * 1024 && smem > attr_smem) { TXL_CUDA(cudaFuncSetAttribute(decode_attn_kernel<T, DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
     decode_attn_kernel<T, DHV><<<grid, DEC_THREADS, smem, st>>>((const T*)qkv, (T*)kc, (T*)vc, (const T*)r, rwb, rrb, (T*)out, pos, H, ML);  \
   }
-  DEC_DISPATCH(dtype, { if (dh == 32) DEC_LAUNCH(32) else if (dh == 64) DEC_LAUNCH(64) else DEC_LAUNCH(128) });
+  TXL_CHECK_ARG(dtype == TXL_F32, "decode_attn: fp32 parity mode only (bf16: txl_decode_attn_pipe)");
+  typedef float T;
+  if (dh == 32) DEC_LAUNCH(32) else if (dh == 64) DEC_LAUNCH(64) else DEC_LAUNCH(128)
 #undef DEC_LAUNCH
   TXL_LAUNCH_CHECK();
   return TXL_OK;

@@ -545,6 +545,48 @@ extern "C" int txl_clm_labels(const int64_t* ids, int64_t* labels, int64_t n, in
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }
+// labels [B, T] (row stride ld) -> shift[b*T + t] = labels[b, t+1] (t < T-1), -100 in the last column: what HF's crit sees as `labels[..., 1:]`.
+// Block 0 first applies the reference's fix-up (musicnlp/models/transformer_xl.py:176-182), with its own arithmetic: if
+// sum(labels[0, 1:]) == (T-1) * -100 then labels[0, 1] = eos, IN PLACE (the caller's tensor is mutated as in the reference), no host sync.
+// Also counts labels outside [0, V) that are not -100 into bad[0] (optional range check, HF raises on those).
+__global__ void shift_labels_kernel(int64_t* __restrict__ labels, int64_t ld, int B, int T, int64_t eos, int V, int64_t* __restrict__ shift,
+                                    int* __restrict__ bad) {
+  __shared__ long long s_sum[32];
+  __shared__ int s_fix;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int64_t* row = labels + (int64_t)b * ld;
+  if (b == 0) {
+    long long acc = 0;
+    for (int t = 1 + tid; t < T; t += blockDim.x) acc += row[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_sum[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      long long tot = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_sum[w];
+      s_fix = (T > 1 && tot == (long long)(T - 1) * -100) ? 1 : 0;
+      if (s_fix) row[1] = eos;
+    }
+    __syncthreads();
+  }
+  int nbad = 0;
+  for (int t = tid; t < T; t += blockDim.x) {
+    int64_t v = -100;
+    if (t + 1 < T) {
+      v = (b == 0 && t == 0 && s_fix) ? eos : row[t + 1];
+      if (v != -100 && (v < 0 || v >= V)) ++nbad;
+    }
+    shift[(int64_t)b * T + t] = v;
+  }
+  if (bad && nbad) atomicAdd(bad, nbad);
+}
+extern "C" int txl_shift_labels(int64_t* labels, int64_t ld, int B, int T, int64_t eos, int V, int64_t* shift, int* bad, void* stream) {
+  TXL_CHECK_ARG(labels && shift && B > 0 && T > 0 && ld >= T && V > 0, "shift_labels: bad args");
+  shift_labels_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(labels, ld, B, T, eos, V, shift, bad);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
 // last position of `token` in every row (-1 if absent): one warp per row, scanning from the end
 __global__ void last_index_kernel(const int64_t* __restrict__ ids, int64_t ld, int B, int T, int64_t token, int64_t* __restrict__ out) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;

@@ -8,8 +8,8 @@ Two generations of kernels share this file:
   * bf16 (the measured path): `txl_dec_linear` / `txl_dec_add_ln` / `txl_decode_attn_pipe` / `txl_decode_tail` (csrc/decode_stream.cu,
     csrc/sample.cu) over an interleaved k|v ring, launched with programmatic stream serialization; `GroupedDecoder` captures groups of 16
     sequences as parallel branches of one graph.  74 launches per step and group.
-  * fp32 parity mode (token-identical greedy decode against the oracle) and `TXL_DECODE_GEN1=1`: the first-generation kernels of csrc/decode.cu.
-Environment switches (A/B measurements, see profiles/r01_decode_ab.txt; defaults are the measured best): TXL_DECODE_GEN1, TXL_DECODE_PDL,
+  * fp32 parity mode (token-identical greedy decode against the oracle): the exact-FMA kernels of csrc/decode.cu.
+Environment switches (A/B measurements, see profiles/r01_decode_ab.txt; defaults are the measured best): TXL_DECODE_PDL,
 TXL_DECODE_TAIL, TXL_DECODE_GROUPS, TXL_DECODE_ATTN_SPLITS, TXL_DECODE_ATTN_CFG, TXL_DECODE_PREFETCH_MB, TXL_DEC_SPLIT_COLS,
 TXL_DEC_LINEAR_2STAGE, TXL_DECODE_ABL (timing ablation: results are garbage).
 """
@@ -28,11 +28,11 @@ SK_MAXM = 64
 
 
 def supported(model, B):
+    """Any batch size: more than SK_MAXM sequences are decoded as several sequence groups (`sequence_groups`)."""
     cfg = model.config
-    return B <= SK_MAXM and cfg.same_length and cfg.mem_len > 0 and cfg.d_head in (32, 64, 128) and cfg.d_model % 8 == 0 and cfg.d_inner % 8 == 0
+    return B >= 1 and cfg.same_length and cfg.mem_len > 0 and cfg.d_head in (32, 64, 128) and cfg.d_model % 8 == 0 and cfg.d_inner % 8 == 0
 
 
-_GEN1 = os.environ.get('TXL_DECODE_GEN1', '') == '1'      # A/B switch: first-generation kernels (tcgen05 transposed-store Linears, register-fed attention)
 _PDL = os.environ.get('TXL_DECODE_PDL', '1') != '0'       # programmatic dependent launch of the step's kernels
 _ATTN_SPLITS = int(os.environ.get('TXL_DECODE_ATTN_SPLITS', '0'))   # 0 = automatic
 # per layer: MB of the next attention kernel's ring that the six kernels before it ask into L2 (cp.async.bulk.prefetch.L2).  Measured at cfg4:
@@ -43,7 +43,7 @@ _ABL = int(os.environ.get('TXL_DECODE_ABL', '0'))       # timing ablations (resu
 
 
 def _dec_linear_ok(A, W):
-    return (A.dtype == torch.bfloat16 and not _GEN1 and A.shape[1] % 32 == 0 and A.stride(1) == 1 and W.stride(1) == 1 and A.stride(0) % 8 == 0
+    return (A.dtype == torch.bfloat16 and A.shape[1] % 32 == 0 and A.stride(1) == 1 and W.stride(1) == 1 and A.stride(0) % 8 == 0
             and W.stride(0) % 8 == 0)
 
 
@@ -98,10 +98,13 @@ def sequence_groups(model, B, requested=None):
     """How many independent sequence groups generate() decodes as parallel graph branches (GroupedDecoder).  bf16 second-generation path only."""
     if requested is None:
         requested = int(os.environ.get('TXL_DECODE_GROUPS', '0')) or None
-    if model._E.dtype != torch.bfloat16 or _GEN1 or os.environ.get('TXL_DECODE_TAIL', '1') == '0' or model.config.vocab_size > 8192:
-        return 1
+    need = (B + SK_MAXM - 1) // SK_MAXM              # a Decoder (one chain of kernels) takes at most SK_MAXM sequences
+    if model._E.dtype != torch.bfloat16 or os.environ.get('TXL_DECODE_TAIL', '1') == '0' or model.config.vocab_size > 8192:
+        return need
     if requested is not None:
-        return max(1, min(int(requested), B))
+        return max(need, min(int(requested), B))
+    if B > SK_MAXM:
+        return (B + 15) // 16
     # groups of 16 sequences: the Linears then work on ONE 16-row MMA tile, and 16 x 8 heads = 128 attention CTAs sit one per SM.  Measured at 64
     # sequences (us/step): 1 group 613, 2 groups 601, 3 groups 710, 4 groups 546, 5 groups 567, 8 groups 701.
     return min(4, B // 16) if B >= 32 else 1
@@ -111,7 +114,7 @@ class Decoder:
     """Device-resident generation state for `B` sequences.  Built from the mems the prompt forward returned."""
 
     def __init__(self, model, mems, out_ids, col0, *, do_sample, temperature, top_k, top_p, eos_token_id, pad_token_id, seed=0, seq_offset=0,
-                 use_graph=True, use_fused=False, attn_splits=None):
+                 use_graph=True, attn_splits=None):
         cfg = model.config
         self.model, self.cfg = model, cfg
         bm = mems._bm if hasattr(mems, '_bm') else model._mems_to_bm(mems, out_ids.shape[0])
@@ -126,7 +129,7 @@ class Decoder:
         # per-layer ring caches of projected keys / values + cached r tables (weights are frozen during generation)
         pos_tab = ops.posemb_table(ML + 1, cfg.clamp_len, d, dt, dev)
         self.kc, self.vc, self.kvc, self.r, self.r_hm = [], [], [], [], []
-        self.pipe_attn = dt == torch.bfloat16 and not _GEN1 and not use_fused
+        self.pipe_attn = dt == torch.bfloat16
         for li, w in enumerate(model._W):
             kv = ops.gemm(bm[li].reshape(B * ML, d).contiguous(), w.qkv[d:], transB=True)          # (B*ML, 2d)
             if self.pipe_attn:
@@ -179,42 +182,11 @@ class Decoder:
         self.graph = None
         self.use_graph = use_graph
         self.steps_done = 0
-        self.fused = None
-        if use_fused:
-            self._build_fused()
-
-    def _build_fused(self):
-        """Pointer tables + workspace of the persistent fused step kernel (csrc/decode_fused.cu)."""
-        m, cfg, lib = self.model, self.cfg, load()
-        L = cfg.n_layer
-
-        def arr(ts):
-            return (C.c_void_p * L)(*[t.data_ptr() for t in ts])
-        W = m._W
-        self._fused_keep = [[w.qkv for w in W], [w.o for w in W], [w.w1 for w in W], [w.w2 for w in W], self.r, [w.b1 for w in W], [w.b2 for w in W],
-                            [w.rwb for w in W], [w.rrb for w in W], [w.ln1_w for w in W], [w.ln1_b for w in W], [w.ln2_w for w in W], [w.ln2_b for w in W],
-                            self.kc, self.vc]
-        self._fused_arrays = [arr(ts) for ts in self._fused_keep]
-        nbytes = lib.txl_decode_fused_workspace(self.B, self.d, cfg.d_inner, self.V, L, dtype_code(self.dt))
-        self._fused_ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
-        self.logits32 = torch.zeros(self.B, self.Vp, dtype=torch.float32, device=self.dev)
-        self._fused_call(1)
-        self.fused = True
-
-    def _fused_call(self, build):
-        cfg = self.cfg
-        check(load().txl_decode_fused_step(*self._fused_arrays, ptr(self.model._E), ptr(self.model._out_bias), ptr(self.tok), ptr(self.pos),
-                                           ptr(self.logits32), ptr(self._fused_ws), int(build), self.B, cfg.n_head, cfg.d_head, self.d, cfg.d_inner,
-                                           self.ML, cfg.n_layer, self.V, self.Vp, float(cfg.layer_norm_epsilon), dtype_code(self.dt), stream_ptr()),
-              'decode_fused_step')
 
     # one decode step: every line is a kernel launch on the current stream
     def _step_kernels(self):
         m, cfg, lib = self.model, self.cfg, load()
         B, d, H, dh, ML = self.B, self.d, cfg.n_head, cfg.d_head, self.ML
-        if self.fused:
-            self._fused_call(0)
-            return self._finish_step(self.logits32)
         pdl_old = lib.txl_set_pdl(1) if (self.pipe_attn and _PDL) else None
         cfg_old = lib.txl_decode_attn_pipe_config(self.attn_cfg) if (self.pipe_attn and self.attn_cfg is not None) else None
         try:
@@ -367,7 +339,8 @@ class GroupedDecoder:
             return 0
         for d, (lo, hi) in zip(self.decs, self.bounds):
             d.tok.copy_(first_token[lo:hi])
-            d.x0.copy_(ops.embed_fwd(d.tok, d.model._E, math.sqrt(d.d)))
+            if d.gen2_tail:
+                d.x0.copy_(ops.embed_fwd(d.tok, d.model._E, math.sqrt(d.d)))
             d._step_kernels()                         # eager first step: warms caches, sets kernel attributes
         done = 1
         if self.use_graph and n_steps > 1:

@@ -3,6 +3,12 @@ modes `musicnlp/trainer/eval.py:277-333` drives, following HF 4.25 `GenerationMi
 (SURVEY.md Appendix A.7): one forward per new token fed through `prepare_inputs_for_generation(input_ids, past=mems)`,
 log-prob scores of the last position, warpers in HF order, eos/pad bookkeeping, stop at `max_length`.
 
+The device-resident decode step (ring cache, CUDA graph; decode.py) is the DEFAULT for every call the reference makes
+(`eval.py:333`: HF kwargs only).  Sampling draws are keyed (seed, global sequence index, step): when the caller passes no
+`seed`, one is drawn from torch's global generator, so `torch.manual_seed(s)` makes a run reproducible exactly as it does for
+HF's `torch.multinomial`, and consecutive calls differ.  Passing a `torch.Generator` (`generator=`) or asking for per-step
+scores selects the one-forward-per-token host loop.  Any batch size: more than 64 sequences are decoded as further sequence groups.
+
 Beam search, contrastive search, typical-p and repetition penalty are outside the measured path and raise.
 """
 from __future__ import annotations
@@ -19,7 +25,7 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
              typical_p: Optional[float] = None, repetition_penalty: Optional[float] = None, renormalize_logits: Optional[bool] = None,
              num_beams: Optional[int] = None, num_beam_groups: Optional[int] = None, diversity_penalty=None, penalty_alpha=None,
              num_return_sequences: Optional[int] = None, eos_token_id='config', pad_token_id='config', generator=None,
-             return_step_scores: bool = False, use_decode_cache: bool = True, seed: int = 0, seq_offset: int = 0, use_cuda_graph: bool = True, use_fused_step: bool = False,
+             return_step_scores: bool = False, use_decode_cache: bool = True, seed: Optional[int] = None, seq_offset: int = 0, use_cuda_graph: bool = True,
              decode_groups: Optional[int] = None, **unused):
     cfg = model.config
     if input_ids is None:
@@ -57,6 +63,11 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
     past = None
     fast = (use_decode_cache and not return_step_scores and generator is None and decode.supported(model, B)
             and max_length - cur >= 2)
+    if fast and do_sample and seed is None:
+        # the reference's call carries no seed (eval.py:277-333): key the draws on torch's global generator, as HF's multinomial is
+        seed = int(torch.randint(1, 2 ** 62, (1,)).item())
+    seed = int(seed or 0)
+    model.last_generate_path = 'decode_cache' if fast else 'forward_per_token'
     try:
         with torch.no_grad():
             while cur < max_length:
@@ -64,7 +75,7 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
                 out = model(**inputs, return_dict=True)
                 scores = out.logits[:, -1, :].contiguous()
                 past = out.mems
-                if fast and (seed or not do_sample):
+                if fast:
                     u = None
                     if do_sample:      # first draw uses the same keyed stream as the device loop (step index -1 -> pos 0 is the next one)
                         u = torch.empty(B, dtype=torch.float32, device=dev)
@@ -79,8 +90,8 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
                     cur += 1
                     if cur < max_length:
                         dkw = dict(do_sample=do_sample, temperature=temperature, top_k=top_k, top_p=top_p, eos_token_id=eos_token_id,
-                                   pad_token_id=pad_token_id, seed=seed, seq_offset=seq_offset, use_graph=use_cuda_graph, use_fused=use_fused_step)
-                        groups = decode.sequence_groups(model, B, decode_groups) if not use_fused_step else 1
+                                   pad_token_id=pad_token_id, seed=seed, seq_offset=seq_offset, use_graph=use_cuda_graph)
+                        groups = decode.sequence_groups(model, B, decode_groups)
                         if groups > 1:
                             dec = decode.GroupedDecoder(model, past, out_ids, cur, groups, **dkw)
                             dec.set_unfinished(unfinished)

@@ -219,6 +219,7 @@ class _TxlStep(torch.autograd.Function):
         if g_losses is not None:
             grow[:, :T - 1] += g_losses.to(torch.float32)
         gflat = model._fresh_grad_buffer()
+        model._backwards_since_step += 1
         hook = model._grad_hook
         engine.backward(model.config, model._W, model._G, model._E, model._gE, model._g_out_bias, sv, grow.view(-1),
                         on_layer_done=(lambda li: hook('layer', li)) if hook else None)
@@ -245,6 +246,9 @@ class MyTransfoXLLMHeadModel(nn.Module):
             raise NotImplementedError('n_head * d_head must equal d_model (reference presets guarantee it)')
         if config.same_length and config.mem_len <= 0:
             raise NotImplementedError('same_length with mem_len<=0 masks every key')
+        if getattr(config, 'dropatt', 0.0):
+            raise NotImplementedError('dropatt > 0 (dropout on the attention probabilities) is not implemented: the reference keeps the HF '
+                                      'default dropatt=0.0 (notebook/train/transformer-xl.ipynb:492-513)')
         self.config = config
         self._specs = _named_param_specs(config)
         self._slots, off = [], 0
@@ -267,6 +271,13 @@ class MyTransfoXLLMHeadModel(nn.Module):
         # `outputs.logits.argmax(-1)` (train_util_wrap.py:106) / `preprocess_logits_for_metrics` (train.py:248) needs no (B,T,V) tensor
         self.monitor_greedy = False
         self.last_greedy = None
+        # optional range check (HF raises an index error for ids / labels outside the vocabulary; the kernels here would embed zeros / score
+        # loss 0): with check_ranges the label-shift kernel counts offending labels on the device, `assert_ranges_ok()` reads the counter
+        self.check_ranges = False
+        self._bad_labels = None
+        self.last_generate_path = None
+        self._backwards_since_step = 0
+        self._grad_accum_base = None
         if device is not None:
             self.to(device)
 
@@ -447,9 +458,36 @@ class MyTransfoXLLMHeadModel(nn.Module):
         if reuse:
             self._gflat.zero_()
         else:
+            if self._gflat is not None and self._grad_accum_base is None:
+                self._grad_accum_base = self._gflat      # `.grad`s alias it: autograd accumulates the later backwards INTO this buffer
             self._gflat = torch.zeros(self._flat_numel, dtype=torch.float32, device=self._flat.device)
         self._bind_grad_views(self._gflat)
         return self._gflat
+
+    def zero_grad(self, set_to_none: bool = True):
+        super().zero_grad(set_to_none=set_to_none)
+        self._grad_accum_base = None
+        self._backwards_since_step = 0
+
+    def flat_grads(self):
+        """The flat fp32 gradient the optimiser must consume = what the parameters' `.grad` hold (HF Trainer semantics: gradient
+        accumulation over several backwards, external clipping / unscaling of `.grad`).  Normally the `.grad`s are views of one flat buffer
+        (the first backward's; later backwards are accumulated into it by autograd) and that buffer is returned as is; if any `.grad` was
+        replaced by the user, the gradients are gathered into a scratch buffer."""
+        params = list(self._param_by_name.values())
+        g0 = params[0].grad
+        if g0 is None:
+            raise RuntimeError('no gradients: call loss.backward() first')
+        base = g0.data_ptr() - 4 * self._slots[0][0]
+        for cand in (self._grad_accum_base, self._gflat):
+            if cand is not None and cand.data_ptr() == base and all(
+                    p.grad is not None and p.grad.data_ptr() == base + 4 * o for p, (o, n, s) in zip(params, self._slots)):
+                return cand
+        scratch = torch.zeros(self._flat_numel, dtype=torch.float32, device=self._flat.device)
+        for p, (o, n, shape) in zip(params, self._slots):
+            if p.grad is not None:
+                scratch[o:o + n].copy_(p.grad.reshape(-1))
+        return scratch
 
     def layer_param_ranges(self):
         """[(start, end)] element ranges of the flat buffers: index 0 = embedding + output bias, 1.. = layers (for gradient buckets)."""
@@ -541,14 +579,21 @@ class MyTransfoXLLMHeadModel(nn.Module):
         if labels is not None:
             if tuple(labels.shape) != (bsz, tgt_len):
                 raise RuntimeError('Input and labels should have the same size in the batch dimension.')
-            # reference :176-182 — in-place fix-up of an all-pad first row
-            miss_valid_label = labels[0, 1:].sum() == (labels.size(1) - 1) * -100
-            if miss_valid_label:
-                labels[0, 1] = self.config.eos_token_id
-            lab = labels.to(dev, non_blocking=True).long()
-            labels_shift = torch.full((bsz, tgt_len), PT_LOSS_PAD, dtype=torch.int64, device=dev)
-            labels_shift[:, :tgt_len - 1] = lab[:, 1:]
-            labels_shift = labels_shift.view(-1)
+            # reference :176-182 — in-place fix-up of an all-pad first row.  Host labels: checked on the host (no device sync);
+            # device labels: checked and patched by the label-shift kernel itself, so the training loop never waits for the GPU here.
+            if not labels.is_cuda:
+                miss_valid_label = labels[0, 1:].sum() == (labels.size(1) - 1) * -100
+                if miss_valid_label:
+                    labels[0, 1] = self.config.eos_token_id
+            lab = labels.to(dev, non_blocking=True)
+            direct = lab.dtype == torch.int64 and lab.stride(1) == 1
+            lab_k = lab if direct else lab.long().contiguous()
+            if self.check_ranges and self._bad_labels is None:
+                self._bad_labels = torch.zeros(1, dtype=torch.int32, device=dev)
+            labels_shift = ops.shift_labels(lab_k, self.config.eos_token_id if self.config.eos_token_id is not None else 0,
+                                            self.config.vocab_size, self._bad_labels if self.check_ranges else None)
+            if labels.is_cuda and not direct:
+                labels[0, 1] = lab_k[0, 1]          # carry the in-place side effect back to the caller's tensor (device-side copy)
         mems_bm = self._mems_to_bm(mems, bsz)
         in_eval = not self.training
         want_logprobs = labels is None or in_eval
@@ -585,6 +630,16 @@ class MyTransfoXLLMHeadModel(nn.Module):
             return (output + (loss,)) if loss is not None else output
         return TransfoXLLMHeadModelOutput(loss=loss, prediction_scores=prediction_scores, losses=losses, mems=new_mems,
                                           hidden_states=None, attentions=None)
+
+    def assert_ranges_ok(self):
+        """One host read: raises if any label seen since `check_ranges = True` was outside [0, vocab_size) (and not -100)."""
+        if self._bad_labels is not None and int(self._bad_labels.item()) != 0:
+            raise IndexError(f'{int(self._bad_labels.item())} label(s) outside [0, {self.config.vocab_size}) were passed to forward')
+
+    def mark_params_dirty(self):
+        """Call after writing parameters through raw storage (`model._flat`, `.data`, a broadcast): such writes do not bump the autograd
+        version counters `_refresh_shadow` keys on, so the bf16 shadow would silently go stale."""
+        self._shadow_version = None
 
     def ntp_acc_counts(self, labels, out=None):
         """int64[2] device tensor (matches, non-pad positions) of next-token prediction for the last forward (needs monitor_greedy=True):

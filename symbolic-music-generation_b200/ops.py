@@ -201,6 +201,16 @@ def ntp_acc(preds, labels, out=None):
     return out
 
 
+def shift_labels(labels, eos, V, bad=None):
+    """labels (B, T) int64 CUDA, last dim dense -> (B*T,) shifted labels for the LM-head kernels; applies the reference's all-pad first-row
+    fix-up to `labels` in place on the device (transformer_xl.py:176-182) — no host round trip."""
+    assert labels.dtype == torch.int64 and labels.dim() == 2 and labels.stride(1) == 1
+    B, T = labels.shape
+    out = torch.empty(B * T, dtype=torch.int64, device=labels.device)
+    check(_lib().txl_shift_labels(ptr(labels), labels.stride(0), B, T, int(eos), int(V), ptr(out), ptr(bad), stream_ptr()), 'shift_labels')
+    return out
+
+
 def masked_mean(losses):
     out = torch.empty(2, dtype=torch.float32, device=losses.device)
     check(_lib().txl_masked_mean(ptr(losses), losses.numel(), ptr(out[0:1]), ptr(out[1:2]), stream_ptr()), 'masked_mean')

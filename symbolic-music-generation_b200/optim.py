@@ -38,11 +38,11 @@ class FusedAdamW:
         self.last_grad_norm = None
 
     def step(self, lr=None):
-        """Uses the gradients of the last backward (model._gflat).  Single backward per step (no accumulation) is assumed."""
+        """Consumes the parameters' `.grad` (`model.flat_grads()`): with gradient accumulation (several backwards before one step, as HF
+        Trainer's `gradient_accumulation_steps` does) autograd has summed the micro-batches into the first backward's flat buffer, which is
+        what is read here — not the buffer of the last backward alone."""
         model = self.model
-        g = model._gflat
-        if g is None:
-            raise RuntimeError('no gradients: call loss.backward() first')
+        g = model.flat_grads()
         self.t += 1
         scale = None
         if self.max_grad_norm and self.max_grad_norm > 0:
@@ -56,5 +56,4 @@ class FusedAdamW:
         # parameters were updated through raw pointers: autograd version counters did not move and the shadow is already fresh
 
     def zero_grad(self, set_to_none=True):
-        for p in self.model.parameters():
-            p.grad = None
+        self.model.zero_grad(set_to_none=True)

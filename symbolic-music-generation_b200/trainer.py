@@ -33,6 +33,12 @@ class TxlTrainer:
         self.warmup = warmup_steps(self.total_steps, warmup_ratio)
         self.opt = optim.FusedAdamW(model, lr=learning_rate, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
         self.bucketer = GradBucketer(model, bucket_mb=bucket_mb) if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1 else None
+        if self.bucketer is not None:
+            # DDP's construction-time contract: every replica starts from rank 0's parameters (replicas built under different seeds or from
+            # different checkpoints would otherwise diverge silently while their averaged gradients look healthy)
+            model._ensure_engine()
+            torch.distributed.broadcast(model._flat, 0)
+            model.mark_params_dirty()
         self.monitor_ntp_acc = bool(monitor_ntp_acc)
         self.step = 0                                          # optimizer steps taken == scheduler steps taken
         self._acc = torch.zeros(2, dtype=torch.int64, device=model._flat.device) if model._flat is not None and model._flat.is_cuda else None
@@ -66,8 +72,9 @@ class TxlTrainer:
         return loss.detach()
 
     def log(self, loss: torch.Tensor) -> Dict[str, float]:
-        """One host read per call: loss, lr of the step just taken, gradient norm before clipping, ntp_acc since the last log."""
-        entry = dict(step=self.step, loss=float(loss.item()), learning_rate=self.lr_at(self.step - 1),
+        """One host read per call: loss, lr of the step just taken, gradient norm before clipping, ntp_acc since the last log.
+        (HF Trainer logs `lr_scheduler.get_last_lr()` AFTER the scheduler stepped, i.e. the NEXT step's rate: `learning_rate_next` holds that.)"""
+        entry = dict(step=self.step, loss=float(loss.item()), learning_rate=self.lr_at(self.step - 1), learning_rate_next=self.lr_at(self.step),
                      grad_norm=float(self.opt.last_grad_norm.item()) if self.opt.last_grad_norm is not None else float('nan'))
         if self.monitor_ntp_acc and self._acc is not None:
             hit, cnt = self._acc.tolist()

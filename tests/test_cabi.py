@@ -103,8 +103,8 @@ def test_prepare_inputs_for_generation(pkg):
 
 
 def test_decode_sequence_groups_rule(pkg):
-    """Host logic of the grouped decode (no GPU): groups of 16 sequences from 32 up, capped at 4; explicit requests are clamped to [1, B];
-    fp32 models and large vocabularies stay on the single-branch path."""
+    """Host logic of the grouped decode (no GPU): groups of 16 sequences from 32 up; explicit requests are clamped to [1, B]; fp32 models
+    and large vocabularies stay on one chain of kernels per 64 sequences; any batch size is accepted (a chain takes at most 64 sequences)."""
     import importlib
     import types
     import torch
@@ -113,9 +113,10 @@ def test_decode_sequence_groups_rule(pkg):
     def fake(dtype, V=1190):
         return types.SimpleNamespace(_E=torch.empty(1, dtype=dtype), config=types.SimpleNamespace(vocab_size=V))
     m = fake(torch.bfloat16)
-    assert [decode.sequence_groups(m, B) for B in (1, 8, 16, 31, 32, 47, 48, 64, 100)] == [1, 1, 1, 1, 2, 2, 3, 4, 4]
+    assert [decode.sequence_groups(m, B) for B in (1, 8, 16, 31, 32, 47, 48, 64, 100, 256)] == [1, 1, 1, 1, 2, 2, 3, 4, 7, 16]
     assert decode.sequence_groups(m, 7, requested=3) == 3 and decode.sequence_groups(m, 2, requested=5) == 2 and decode.sequence_groups(m, 9, requested=0) == 1
     assert decode.sequence_groups(fake(torch.float32), 64) == 1 and decode.sequence_groups(fake(torch.bfloat16, V=40000), 64) == 1
+    assert decode.sequence_groups(fake(torch.float32), 65) == 2 and decode.sequence_groups(fake(torch.float32), 200) == 4 and decode.sequence_groups(m, 100, requested=1) == 2
     bounds = []
     per, rem = divmod(7, 3)
     lo = 0
