@@ -145,7 +145,10 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'TXL train tokens/s', 'value': r['value'], 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': r['steps'],
         'warmup': min(args.warmup, 1), 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'cfg2: Transformer-XL 12L d512 H8 di2048 T1024 mem1024 V1190 training step (CPU reference arm, bounded sample B=1)'},
+        'config': {'workload': 'cfg2: Transformer-XL 12L d512 H8 di2048 T1024 mem1024 V1190 training step (CPU reference arm, bounded sample B=1)',
+                   'same_config_as_ours': False,
+                   'bounded_sample': f"B=1 sequence x {r['steps']} timed steps on {r['cores']} host threads in fp32 (ours: B=32 per GPU, bf16); a CPU baseline, "
+                                     'reported beside the GPU number, not a like-for-like speed-up'},
         'cpu_baseline': {'value': r['value'], 'unit': 'tokens/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
         'e2e': {'value': r['value'], 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': 'reference dependency transformers==4.25.1 is not installable here; this is the oracle restatement (kind=port)',
@@ -190,6 +193,7 @@ def run_ours(args):
     model._ensure_engine()
     if world > 1:       # identical replicas: broadcast rank 0's flat parameters
         dist.broadcast(model._flat, 0)
+        model.mark_params_dirty()
     opt = optim.FusedAdamW(model, lr=3e-4, weight_decay=0.01, max_grad_norm=1.0)
     bucketer = pdist.GradBucketer(model, bucket_mb=25.0) if world > 1 else None
 
@@ -285,6 +289,18 @@ def run_ours(args):
         'roofline_step': {'bound': 'tensor', 'achieved': step_tf, 'peak': peaks['tf'], 'unit': 'TFLOP/s', 'frac': step_tf / peaks['tf'],
                           'note': f'whole step, algorithmic FLOP/token {fpt:.4e} (SURVEY §8d) / per-GPU tokens/s; peak = sustained bf16, {peaks["src"]}'},
     }
+    if world > 1:
+        line['dp_check'] = dp_check(torch, dist, model, bucketer, dev_ids[0], dev_lab[0], state['mems'], world)
+    # free the cfg2 training state before the other workloads
+    del opt, bucketer
+    state['mems'] = None
+    model._grad_hook = None
+    model.zero_grad()
+    model._gflat = None
+    del model
+    torch.cuda.empty_cache()
+    if not args.no_cfg5:
+        line['cfg5'] = cfg5_probe(torch, dist, pkg, optim, pdist, args, dev, rank, world)
     if not args.no_decode:
         line['decode'] = decode_probe(torch, pkg, pdist, cfg, args, dev, rank, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -294,6 +310,100 @@ def run_ours(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dp_check(torch, dist, model, bucketer, ids, labels, mems, world):
+    """the data-parallel step must equal the single-GPU step on the same global batch.  One extra (untimed) step, run twice on
+    every rank with identical dropout seeds: (1) without the bucketer -> this rank's own gradients; all-gather two layers' slices and average
+    them on the device = what one GPU holding the global batch would compute (per-replica `losses[losses != 0].mean()`, then the mean of
+    replicas: DDP's arithmetic); (2) with the bucketed NCCL all-reduce fired from inside the backward.  Reports the largest
+    absolute difference between (2) and the average of (1), and the scale of the gradients."""
+    ranges = model.layer_param_ranges()
+    picks = {'layer0': ranges[1], f'layer{len(ranges) - 2}': ranges[-1], 'embedding': ranges[0]}
+    seed0 = model._step_seed
+
+    def one_pass(hook):
+        model._grad_hook = hook
+        model._step_seed = seed0
+        model.zero_grad()
+        model(input_ids=ids, mems=mems, labels=labels).loss.backward()
+        return model.flat_grads()
+    g_local = one_pass(None)
+    want = {}
+    for k, (s, e) in picks.items():
+        mine = g_local[s:e].clone()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        want[k] = torch.stack(parts).mean(0)
+    g_red = one_pass(bucketer)
+    out = {'what': 'max |bucketed all-reduce gradient - mean over ranks of the un-reduced gradients| (fp32), same batch and dropout seed', 'world': world}
+    worst = 0.0
+    for k, (s, e) in picks.items():
+        err = float((g_red[s:e] - want[k]).abs().max().item())
+        out[k] = {'max_abs_err': err, 'max_abs_grad': float(want[k].abs().max().item())}
+        worst = max(worst, err / max(out[k]['max_abs_grad'], 1e-30))
+    out['max_rel_err'] = worst
+    model.zero_grad()
+    return out
+
+
+def cfg5_probe(torch, dist, pkg, optim, pdist, args, dev, rank, world):
+    """BASELINE configs[4]: longer-seq Transformer-XL (seq 2048, mem_len 2048, clamp_len 1024 = the `small` preset's), bf16 training step,
+    16 sequences per GPU, data-parallel over the ranks with the same bucketed all-reduce; carried non-zero mems, dropout 0.1."""
+    T = M = 2048
+    B = args.cfg5_batch
+    cfg = pkg.MyTransfoXLConfig(compute_dtype=args.dtype, dropout=args.dropout, **dict(CFG2, max_length=T, mem_len=M))
+    torch.manual_seed(77)
+    model = pkg.MyTransfoXLLMHeadModel(cfg).to(dev).train()
+    model._ensure_engine()
+    if world > 1:
+        dist.broadcast(model._flat, 0)
+        model.mark_params_dirty()
+    opt = optim.FusedAdamW(model, lr=3e-4, weight_decay=0.01, max_grad_norm=1.0)
+    bucketer = pdist.GradBucketer(model, bucket_mb=25.0) if world > 1 else None
+    g = torch.Generator().manual_seed(770 + rank)
+    ids = [torch.randint(0, cfg.vocab_size, (B, T), generator=g).to(dev) for _ in range(2)]
+    state = {'mems': None}
+
+    def step(i):
+        out = model(input_ids=ids[i % 2], mems=state['mems'], labels=ids[i % 2])
+        out.loss.backward()
+        opt.step()
+        opt.zero_grad()
+        state['mems'] = out.mems
+    steps, warm = max(3, args.steps // 2), 3
+    for i in range(warm):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warm + i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    fpt, _ = flop_per_token(cfg.n_layer, cfg.d_model, cfg.d_inner, T, M, cfg.vocab_size, M)
+    peaks = measured_peaks()
+    value = B * T * world / (ms / 1e3)
+    tf = value / world * fpt / 1e12
+    model._grad_hook = None
+    del opt, bucketer, model
+    state['mems'] = None
+    torch.cuda.empty_cache()
+    return {'metric': 'TXL train tokens/s', 'value': value, 'unit': 'tokens/s', 'ms_per_step': ms, 'steps': steps, 'warmup': warm, 'n_gpus': world,
+            'config': {'workload': f'cfg5: Transformer-XL 12L d512 H8 dh64 di2048 T{T} mem{M} clamp_len {cfg.clamp_len} V{cfg.vocab_size} bf16 training step '
+                                   f'(fwd+bwd+clip+AdamW, carried non-zero mems, dropout {args.dropout})', 'batch_per_gpu': B, 'global_batch': B * world,
+                       'parallelism': f'dp{world}', 'flop_per_token': fpt},
+            'roofline_step': {'bound': 'tensor', 'achieved': tf, 'peak': peaks['tf'], 'unit': 'TFLOP/s', 'frac': tf / peaks['tf'],
+                              'note': 'algorithmic FLOP/token (SURVEY 8d, band-aware) x per-GPU tokens/s; peak = sustained bf16, ' + peaks['src']}}
 
 
 def decode_probe(torch, pkg, pdist, cfg_train, args, dev, rank, world):
@@ -308,7 +418,7 @@ def decode_probe(torch, pkg, pdist, cfg_train, args, dev, rank, world):
     model = pkg.MyTransfoXLLMHeadModel(cfg).to(dev).eval()
     g = torch.Generator().manual_seed(77)
     prompt = torch.randint(1, cfg.vocab_size, (args.decode_seqs, 16), generator=g)[lo:hi].to(dev)
-    kw = dict(do_sample=True, top_k=8, temperature=1.0, renormalize_logits=True, eos_token_id=None, seed=77, seq_offset=lo)
+    kw = dict(do_sample=True, top_k=8, temperature=1.0, renormalize_logits=True, eos_token_id=None, seed=77, seq_offset=lo)    # seed: same tokens under any sharding
     model.generate(input_ids=prompt, max_length=16 + 8, **kw)          # warm-up (kernel attributes, allocator)
     torch.cuda.synchronize()
     if world > 1:
@@ -385,11 +495,12 @@ def dominant_kernel_probe(torch, ops, model, cfg, B, T, M, dev):
         return e0.elapsed_time(e1) / n
     ms_fwd = timeit(fwd)
     ms_bwd_all = timeit(bwd)
-    os.environ['TXL_DBG'] = '48'          # dQ pass alone (prep kernel and lite passes skipped; operands in the workspace are stale but valid)
+    lib = importlib.import_module(PKG + '._lib').load()
+    lib.txl_relattn_bwd_probe(48, 0)      # dQ pass alone (prep kernel and lite passes skipped; operands in the workspace are stale but valid)
     try:
         ms_dq = timeit(bwd)
     finally:
-        os.environ.pop('TXL_DBG', None)
+        lib.txl_relattn_bwd_probe(0, 0)
     Kb = min(M, T + M)
     unit = 2.0 * T * Kb * d * B                      # one score-sized contraction over the live band, per launch
     tf = lambda units, ms: units * unit / (ms / 1e3) / 1e12
@@ -423,6 +534,8 @@ def main():
     ap.add_argument('--dropout', type=float, default=0.1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-decode', action='store_true')
+    ap.add_argument('--no-cfg5', action='store_true')
+    ap.add_argument('--cfg5-batch', type=int, default=16)
     ap.add_argument('--decode-only', action='store_true')
     ap.add_argument('--decode-seqs', type=int, default=64)
     ap.add_argument('--decode-new', type=int, default=2048)

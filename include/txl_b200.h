@@ -143,6 +143,9 @@ int txl_relattn_fwd(const void* q, const void* k_mem, const void* v_mem, const v
  * slices of one [B,T,3d] buffer); dk_mem/dv_mem may be NULL (mems detached and all-zero => no wgrad term).
  * dr [klen,H*dh], drwb/drrb [H*dh] are fp32 and ACCUMULATED into.  ws: workspace of txl_relattn_bwd_workspace bytes.
  * saved: NULL, or the buffer the forward call with the same inputs and dims filled (read-only here). */
+/* profiling aid (bench.py's dominant-kernel probe): dbg 16 = the tensor-core backward runs its dQ pass alone, 32 = skips the prep kernel;
+ * abl = ablation bits of the dQ pass.  0, 0 = normal operation.  Returns the previous dbg.  Never set on the product path. */
+int txl_relattn_bwd_probe(int dbg, int abl);
 int64_t txl_relattn_bwd_workspace(const TxlAttnDims* dims);
 int txl_relattn_bwd(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur,
                     const void* r, const float* rwb, const float* rrb, const void* out, const float* lse,
@@ -160,6 +163,20 @@ int txl_logsoftmax_nll_fwd(const void* logits, int64_t ldl, const int64_t* label
 int txl_logsoftmax_nll_bwd(const void* logits, int64_t ldl, int dtype, void* dlogits, int64_t ldd, int dtype_out, const int64_t* labels,
                            const float* lse, const float* grow, int64_t N, int V, void* stream);
 /* loss = mean(losses[losses != 0]) and grow[n] = g_loss/cnt * (losses[n]!=0) + g_losses[n]  (transformer_xl.py:197-200) */
+/* Adaptive softmax, cluster path (HF ProjectedAdaptiveLogSoftmax with n_clusters > 0, div_val 1: the reference's DEFAULT criterion for
+ * vocabularies >= 1000, musicnlp/models/transformer_xl.py:56-66).  A logits row = V token logits followed by the n_clusters cluster logits
+ * (one GEMM over [embedding ; crit.cluster_weight]); cutoffs = HF's `cutoffs` (increasing, inside (0, V)), n_clusters <= 4.
+ * fwd: lse [N, 1 + n_clusters] (head, tails); losses[n] = -log p(labels[n]) (0 where the label is -100); logprobs [N, V] (optional) =
+ *      head log-softmax for v < cutoffs[0], else head log-prob of the tail's cluster + tail log-softmax; argmax (optional) of those.
+ * bwd: dlogits [N, ldd >= V + n_clusters] = grow[n] * d losses[n] / d logits.
+ * txl_pack_losses: HF's keep_order=False ordering of the returned loss vector (positions of cluster 0 first, then cluster 1, ..., ignored
+ *      labels as trailing zeros): pos_losses [B, T] -> packed [B*(T-1)], perm[k] = b*T + t of packed entry k (-1: none). */
+int txl_adaptive_lsm_nll_fwd(const void* logits, int64_t ldl, const int64_t* labels, float* losses, float* lse, float* logprobs,
+                             int64_t* argmax, int64_t N, int V, int n_clusters, const int* cutoffs, int dtype, void* stream);
+int txl_adaptive_lsm_nll_bwd(const void* logits, int64_t ldl, int dtype, void* dlogits, int64_t ldd, int dtype_out, const int64_t* labels,
+                             const float* lse, const float* grow, int64_t N, int V, int n_clusters, const int* cutoffs, void* stream);
+int txl_pack_losses(const float* pos_losses, const int64_t* labels_shift, int B, int T, int V, int n_clusters, const int* cutoffs,
+                    float* packed, int64_t* perm, void* stream);
 int txl_masked_mean(const float* losses, int64_t N, float* loss_out, float* count_out, void* stream);
 /* Next-token-prediction accuracy counts  [reference train_util_wrap.py:113-120, train.py:279-284; SURVEY §8f-2]
  * preds  [B, T] int64: greedy prediction made AT each position (the fused argmax of txl_logsoftmax_nll_fwd), row stride ld_preds

@@ -225,13 +225,28 @@ class _AdaptiveEmb(nn.Module):
 
 
 class _Crit(nn.Module):
-    """ProjectedAdaptiveLogSoftmax, n_clusters == 0 path only (Appendix A.6)."""
+    """HF 4.25.1 `ProjectedAdaptiveLogSoftmax` at div_val == 1, d_proj == d_embed (Appendix A.6): the n_clusters == 0 path the reference
+    trains with (`cutoffs=[]`, musicnlp/trainer/train.py:521-527) AND the cluster path its config derivation selects by default for
+    vocabularies >= 1000 (`cutoffs=[1000]` ..., musicnlp/models/transformer_xl.py:56-66), restated construct by construct:
+    `cutoffs + [n_token]`, head = shortlist rows + `cluster_weight`, `cluster_prob_idx = cutoffs[0] + i - 1`, per-cluster
+    `index_select`, and - because TransfoXLLMHeadModel builds the criterion with keep_order=False - the PACKED loss vector
+    (`out[offset : offset + n_i]`, clusters in order, ignored labels left as trailing zeros)."""
 
-    def __init__(self, V, d):
+    def __init__(self, V, d, cutoffs=(), keep_order=False):
         super().__init__()
+        self.n_token = V
+        self.cutoffs = list(cutoffs) + [V]
+        self.cutoff_ends = [0] + self.cutoffs
+        self.shortlist_size = self.cutoffs[0]
+        self.n_clusters = len(self.cutoffs) - 1
+        self.head_size = self.shortlist_size + self.n_clusters
+        if self.n_clusters > 0:
+            self.cluster_weight = nn.Parameter(torch.zeros(self.n_clusters, d))
+            self.cluster_bias = nn.Parameter(torch.zeros(self.n_clusters))
         self.out_layers = nn.ModuleList([nn.Linear(d, V)])
+        self.keep_order = keep_order
 
-    def forward(self, hidden, labels=None):
+    def forward(self, hidden, labels=None, keep_order=False):
         if labels is not None:
             hidden = hidden[..., :-1, :].contiguous()
             labels = labels[..., 1:].contiguous()
@@ -241,13 +256,67 @@ class _Crit(nn.Module):
                 raise RuntimeError('Input and labels should have the same size in the batch dimension.')
         else:
             hidden = hidden.view(-1, hidden.size(-1))
-        logit = F.linear(hidden, self.out_layers[0].weight, self.out_layers[0].bias)
-        if labels is not None:
-            mask = labels != PT_LOSS_PAD
+        if self.n_clusters == 0:
+            logit = F.linear(hidden, self.out_layers[0].weight, self.out_layers[0].bias)
+            if labels is not None:
+                mask = labels != PT_LOSS_PAD
+                out = torch.zeros_like(labels, dtype=hidden.dtype)
+                out[mask] = -F.log_softmax(logit, dim=-1)[mask].gather(1, labels[mask].unsqueeze(1)).squeeze(1)
+                return out
+            return F.log_softmax(logit, dim=-1)
+        # ---- cluster path
+        weights, biases = [], []
+        for i in range(len(self.cutoffs)):
+            l_idx, r_idx = self.cutoff_ends[i], self.cutoff_ends[i + 1]
+            weight_i = self.out_layers[0].weight[l_idx:r_idx]
+            bias_i = self.out_layers[0].bias[l_idx:r_idx]
+            if i == 0:
+                weight_i = torch.cat([weight_i, self.cluster_weight], dim=0)
+                bias_i = torch.cat([bias_i, self.cluster_bias], dim=0)
+            weights.append(weight_i)
+            biases.append(bias_i)
+        head_logit = F.linear(hidden, weights[0], biases[0])
+        head_logprob = F.log_softmax(head_logit, dim=1)
+        if labels is None:
+            out = hidden.new_empty((head_logit.size(0), self.n_token))
+        else:
             out = torch.zeros_like(labels, dtype=hidden.dtype)
-            out[mask] = -F.log_softmax(logit, dim=-1)[mask].gather(1, labels[mask].unsqueeze(1)).squeeze(1)
-            return out
-        return F.log_softmax(logit, dim=-1)
+        offset = 0
+        cutoff_values = [0] + self.cutoffs
+        for i in range(len(cutoff_values) - 1):
+            l_idx, r_idx = cutoff_values[i], cutoff_values[i + 1]
+            if labels is not None:
+                mask_i = (labels >= l_idx) & (labels < r_idx)
+                indices_i = mask_i.nonzero().squeeze()
+                if indices_i.numel() == 0:
+                    continue
+                indices_i = indices_i.view(-1)          # (.squeeze() of a single hit is 0-d; index_select wants 1-d - same values)
+                target_i = labels.index_select(0, indices_i) - l_idx
+                head_logprob_i = head_logprob.index_select(0, indices_i)
+                hidden_i = hidden.index_select(0, indices_i)
+            else:
+                hidden_i = hidden
+            if i == 0:
+                if labels is not None:
+                    logprob_i = head_logprob_i.gather(1, target_i[:, None]).squeeze(1)
+                else:
+                    out[:, :self.cutoffs[0]] = head_logprob[:, :self.cutoffs[0]]
+            else:
+                tail_logit_i = F.linear(hidden_i, weights[i], biases[i])
+                tail_logprob_i = F.log_softmax(tail_logit_i, dim=1)
+                cluster_prob_idx = self.cutoffs[0] + i - 1          # no probability for the head cluster
+                if labels is not None:
+                    logprob_i = head_logprob_i[:, cluster_prob_idx] + tail_logprob_i.gather(1, target_i[:, None]).squeeze(1)
+                else:
+                    logprob_i = head_logprob[:, cluster_prob_idx, None] + tail_logprob_i
+                    out[:, l_idx:r_idx] = logprob_i
+            if labels is not None:
+                if self.keep_order or keep_order:
+                    out.index_copy_(0, indices_i, -logprob_i)
+                else:
+                    out[offset:offset + logprob_i.size(0)].copy_(-logprob_i)
+                offset += logprob_i.size(0)
+        return out
 
 
 class _Transformer(nn.Module):
@@ -316,11 +385,9 @@ class RefTransfoXLLMHeadModel(nn.Module):
 
     def __init__(self, cfg: RefConfig):
         super().__init__()
-        if cfg.cutoffs:
-            raise NotImplementedError('adaptive-softmax clusters are out of scope (SURVEY §8f-3); pass cutoffs=[]')
         self.config = cfg
         self.transformer = _Transformer(cfg)
-        self.crit = _Crit(cfg.vocab_size, cfg.d_model)
+        self.crit = _Crit(cfg.vocab_size, cfg.d_model, cfg.cutoffs)      # HF builds it with keep_order=False
         self.apply(self._init_weights)
         self.crit.out_layers[0].weight = self.transformer.word_emb.emb_layers[0].weight   # tie_word_embeddings
 
@@ -339,6 +406,9 @@ class RefTransfoXLLMHeadModel(nn.Module):
         elif isinstance(m, _RelAttn):
             nn.init.normal_(m.r_w_bias, 0.0, std)
             nn.init.normal_(m.r_r_bias, 0.0, std)
+        elif isinstance(m, _Crit) and m.n_clusters > 0:
+            nn.init.normal_(m.cluster_weight, 0.0, std)
+            nn.init.constant_(m.cluster_bias, 0.0)
 
     def num_parameters(self):
         return sum(p.numel() for p in self.parameters())    # tied weight counted once by .parameters()
@@ -431,9 +501,9 @@ class RefTransfoXLLMHeadModel(nn.Module):
         return (ids, step_scores) if return_step_scores else ids
 
 
-def expected_param_count(L, d, di, V):
+def expected_param_count(L, d, di, V, n_clusters=0):
     """Appendix A.8 closed form; KAT: (12, 768, 3072, 418) -> 92,435,362 (log says 92.4M)."""
-    return L * (3 * d * d + 2 * d * d + 2 * d + 2 * d + d * di + di + di * d + d + 2 * d) + V * d + V
+    return L * (3 * d * d + 2 * d * d + 2 * d + 2 * d + d * di + di + di * d + d + 2 * d) + V * d + V + n_clusters * (d + 1)
 
 
 def ntp_acc_counts(preds, labels, pad=-100):

@@ -54,10 +54,14 @@ SIGNATURES = {
     'txl_dropout': (_i, [_vp, _vp, _i64, _i, _f, _u64, _u32, _vp]),
     'txl_relattn_saved_bytes': (_i64, [C.POINTER(TxlAttnDims)]),
     'txl_relattn_fwd': (_i, [_vp] * 11 + [C.POINTER(TxlAttnDims), _vp]),
+    'txl_relattn_bwd_probe': (_i, [_i, _i]),
     'txl_relattn_bwd_workspace': (_i64, [C.POINTER(TxlAttnDims)]),
     'txl_relattn_bwd': (_i, [_vp] * 21 + [C.POINTER(TxlAttnDims), _vp]),
     'txl_logsoftmax_nll_fwd': (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     'txl_logsoftmax_nll_bwd': (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp]),
+    'txl_adaptive_lsm_nll_fwd': (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp]),
+    'txl_adaptive_lsm_nll_bwd': (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp]),
+    'txl_pack_losses': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'txl_masked_mean': (_i, [_vp, _i64, _vp, _vp, _vp]),
     'txl_ntp_acc': (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp]),
     'txl_clm_labels': (_i, [_vp, _vp, _i64, _i64, _vp]),

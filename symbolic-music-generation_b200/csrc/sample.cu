@@ -273,8 +273,10 @@ extern "C" int txl_sample(const float* scores, int B, int V, int do_sample, floa
   while (NP < V) NP <<= 1;
   TXL_CHECK_ARG(NP <= 16384, "sample: vocab %d too large for the shared-memory sampler", V);
   size_t smem = (size_t)NP * 12;
-  static size_t attr_smem = 0;
-  if (smem > 48 * 1024 && smem > attr_smem) { TXL_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
+  static size_t attr_smem[64] = {0};      // per device: the attribute belongs to the (function, device) pair
+  int dev = 0;
+  TXL_CUDA(cudaGetDevice(&dev));
+  if (smem > 48 * 1024 && smem > attr_smem[dev & 63]) { TXL_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem[dev & 63] = smem; }
   sample_kernel<<<B, NT, smem, (cudaStream_t)stream>>>(scores, V, NP, do_sample, temperature, top_k, top_p, u, next, keep, warped);
   TXL_LAUNCH_CHECK();
   return TXL_OK;
@@ -290,8 +292,10 @@ extern "C" int txl_decode_tail(const float* logits, int64_t ldl, float* scores, 
   while (NP < V) NP <<= 1;
   TXL_CHECK_ARG(NP <= 8192, "decode_tail: vocab %d too large for the shared-memory sampler", V);
   const size_t smem = (size_t)NP * 16;
-  static size_t attr_smem = 0;
-  if (smem > 48 * 1024 && smem > attr_smem) { TXL_CUDA(cudaFuncSetAttribute(decode_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
+  static size_t attr_smem[64] = {0};
+  int dev = 0;
+  TXL_CUDA(cudaGetDevice(&dev));
+  if (smem > 48 * 1024 && smem > attr_smem[dev & 63]) { TXL_CUDA(cudaFuncSetAttribute(decode_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem[dev & 63] = smem; }
   TXL_CUDA(txl_launch_pdl(decode_tail_kernel, dim3(B), dim3(NT), smem, (cudaStream_t)stream, logits, ldl, scores, V, NP, do_sample, temperature, top_k, top_p,
                           seed, seq_offset, tok, unfinished, out_ids, ld_out, col0, pos, arrive, eos, pad, use_eos, (const bf16*)E, (bf16*)x0, d, emb_scale));
   TXL_LAUNCH_CHECK();

@@ -480,6 +480,189 @@ extern "C" int txl_logsoftmax_nll_bwd(const void* logits, int64_t ldl, int dtype
   return TXL_OK;
 }
 
+// ------------------------------------------------------------------ adaptive softmax, cluster path (HF ProjectedAdaptiveLogSoftmax, n_clusters > 0)
+// A logits row holds the V token logits (columns 0..V-1, over the tied embedding) followed by the n_clusters cluster logits (columns V..V+nc-1,
+// over crit.cluster_weight): ONE GEMM over the [V+nc, d] extended matrix produces it.  Head = tokens [0, c0) + the cluster columns (HF's head
+// index of tail i is c0 + i - 1 = column V + i - 1 here); tail i = tokens [c_{i-1}, c_i).  log p(v) = head log-softmax for v < c0, else
+// head log-prob of the tail's cluster column + tail log-softmax.  One warp per row; lse[row][0] = head, lse[row][i] = tail i.
+struct Cuts { int nc; int c[5]; };   // c[0] = shortlist size, ..., c[nc] = V
+
+__device__ __forceinline__ int cluster_of(const Cuts& q, int v) {
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) k += (i < q.nc && v >= q.c[i]) ? 1 : 0;
+  return k;
+}
+
+template <typename T>
+__global__ void adaptive_lsm_fwd_kernel(const T* __restrict__ logits, int64_t ldl, const int64_t* __restrict__ labels, float* __restrict__ losses,
+                                        float* __restrict__ lse_out, float* __restrict__ logprobs, int64_t* __restrict__ argmax, int64_t N, int V,
+                                        const Cuts q) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, nc = q.nc;
+  const int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
+  for (int64_t row = warp; row < N; row += (int64_t)gridDim.x * wpb) {
+    const T* l = logits + row * ldl;
+    float lse[5], clp[5];     // clp[i] = head log-prob of tail i's cluster column (clp[0] = 0)
+    {
+      float m = -INFINITY;
+      for (int v = lane; v < q.c[0]; v += 32) m = fmaxf(m, to_f32(l[v]));
+      if (lane < nc) m = fmaxf(m, to_f32(l[V + lane]));
+      m = warp_max(m);
+      float s = 0.f;
+      for (int v = lane; v < q.c[0]; v += 32) s += expf(to_f32(l[v]) - m);
+      if (lane < nc) s += expf(to_f32(l[V + lane]) - m);
+      lse[0] = m + logf(warp_sum(s));
+      clp[0] = 0.f;
+    }
+    for (int i = 1; i <= nc; ++i) {
+      float m = -INFINITY;
+      for (int v = q.c[i - 1] + lane; v < q.c[i]; v += 32) m = fmaxf(m, to_f32(l[v]));
+      m = warp_max(m);
+      float s = 0.f;
+      for (int v = q.c[i - 1] + lane; v < q.c[i]; v += 32) s += expf(to_f32(l[v]) - m);
+      lse[i] = m + logf(warp_sum(s));
+      clp[i] = to_f32(l[V + i - 1]) - lse[0];
+    }
+    if (logprobs || argmax) {
+      float best = -INFINITY; int am = 0x7fffffff;
+      for (int v = lane; v < V; v += 32) {
+        const int k = cluster_of(q, v);
+        const float lp = clp[k] + (to_f32(l[v]) - lse[k]);
+        if (logprobs) logprobs[row * V + v] = lp;
+        if (lp > best) { best = lp; am = v; }
+      }
+      if (argmax) {
+        const float bb = warp_max(best);
+        int cand = (best == bb) ? am : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        if (lane == 0) argmax[row] = cand;
+      }
+    }
+    if (lane == 0) {
+      if (lse_out)
+        for (int i = 0; i <= nc; ++i) lse_out[row * (nc + 1) + i] = lse[i];
+      if (losses) {
+        const int64_t lab = labels ? labels[row] : -100;
+        float out = 0.f;
+        if (lab >= 0 && lab < V) {
+          const int k = cluster_of(q, (int)lab);
+          out = -(clp[k] + (to_f32(l[lab]) - lse[k]));
+        }
+        losses[row] = out;
+      }
+    }
+  }
+}
+
+// d(-log p(label)) / d logits, times grow[row]:  head columns softmax_head - [v == label or v == label's cluster column];
+// the label's tail: softmax_tail - [v == label]; other tails 0.
+template <typename T, typename TO>
+__global__ void adaptive_lsm_bwd_kernel(const T* __restrict__ logits, int64_t ldl, TO* __restrict__ dlogits, int64_t ldd, const int64_t* __restrict__ labels,
+                                        const float* __restrict__ lse, const float* __restrict__ grow, int64_t N, int V, const Cuts q) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, nc = q.nc;
+  const int64_t warp = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5);
+  for (int64_t row = warp; row < N; row += (int64_t)gridDim.x * wpb) {
+    const T* l = logits + row * ldl;
+    TO* o = dlogits + row * ldd;
+    const int64_t lab = labels[row];
+    const bool valid = lab >= 0 && lab < V;
+    const float g = valid ? grow[row] : 0.f;
+    const int kl = valid ? cluster_of(q, (int)lab) : 0;
+    const float lse_h = lse[row * (nc + 1)], lse_t = lse[row * (nc + 1) + kl];
+    const int hot_head = kl == 0 ? (int)lab : V + kl - 1;
+    for (int v = lane; v < ldd; v += 32) {
+      float out = 0.f;
+      if (g != 0.f && v < V + nc) {
+        if (v < q.c[0] || v >= V) out = (expf(to_f32(l[v]) - lse_h) - (v == hot_head ? 1.f : 0.f)) * g;
+        else if (kl > 0 && v >= q.c[kl - 1] && v < q.c[kl]) out = (expf(to_f32(l[v]) - lse_t) - (v == lab ? 1.f : 0.f)) * g;
+      }
+      o[v] = from_f32<TO>(out);
+    }
+  }
+}
+
+// HF builds the criterion with keep_order=False: the loss vector it returns is PACKED - the (b, t < T-1) positions whose label falls in
+// cluster 0 first (in position order), then cluster 1, ..., ignored labels as trailing zeros (`out[offset : offset + n_i]`).  Stable
+// partition by one CTA: per cluster, chunks of blockDim positions, ballot + prefix counts.  perm[k] = b*T + t of packed entry k (-1: none).
+__global__ void pack_losses_kernel(const float* __restrict__ pos_losses, const int64_t* __restrict__ labels_shift, int B, int T, int V, const Cuts q,
+                                   float* __restrict__ packed, int64_t* __restrict__ perm) {
+  __shared__ int wcnt[32];
+  __shared__ int base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int64_t n = (int64_t)B * (T - 1);
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (int k = 0; k <= q.nc; ++k) {
+    for (int64_t i0 = 0; i0 < n; i0 += blockDim.x) {
+      const int64_t i = i0 + tid;
+      bool hit = false; int64_t src = 0;
+      if (i < n) {
+        src = (i / (T - 1)) * T + (i % (T - 1));
+        const int64_t lab = labels_shift[src];
+        hit = lab >= 0 && lab < V && cluster_of(q, (int)lab) == k;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) wcnt[warp] = __popc(m);
+      __syncthreads();
+      int before = 0, total = 0;
+      for (int w = 0; w < nw; ++w) { if (w < warp) before += wcnt[w]; total += wcnt[w]; }
+      if (hit) {
+        const int dst = base + before + __popc(m & ((1u << lane) - 1u));
+        packed[dst] = pos_losses[src];
+        if (perm) perm[dst] = src;
+      }
+      __syncthreads();
+      if (tid == 0) base += total;
+      __syncthreads();
+    }
+  }
+  for (int64_t i = base + tid; i < n; i += blockDim.x) { packed[i] = 0.f; if (perm) perm[i] = -1; }
+}
+
+static int make_cuts(Cuts& q, int V, int nc, const int* cutoffs, const char* who) {
+  if (!(nc >= 1 && nc <= 4 && cutoffs)) { txl_set_error("%s: 1 <= n_clusters <= 4 and cutoffs required", who); return TXL_EINVAL; }
+  q.nc = nc;
+  int prev = 0;
+  for (int i = 0; i < nc; ++i) {
+    if (!(cutoffs[i] > prev && cutoffs[i] < V)) { txl_set_error("%s: cutoffs must be increasing inside (0, V)", who); return TXL_EINVAL; }
+    q.c[i] = prev = cutoffs[i];
+  }
+  for (int i = nc; i < 5; ++i) q.c[i] = V;
+  return TXL_OK;
+}
+
+extern "C" int txl_adaptive_lsm_nll_fwd(const void* logits, int64_t ldl, const int64_t* labels, float* losses, float* lse, float* logprobs,
+                                        int64_t* argmax, int64_t N, int V, int n_clusters, const int* cutoffs, int dtype, void* stream) {
+  TXL_CHECK_ARG(logits && N > 0 && V > 0 && ldl >= V + n_clusters, "adaptive_lsm_nll_fwd: bad sizes");
+  Cuts q; int rc = make_cuts(q, V, n_clusters, cutoffs, "adaptive_lsm_nll_fwd"); if (rc) return rc;
+  const int grid = (int)imin64(cdiv64(N, 8), (int64_t)txl_num_sms() * 8);
+  DISPATCH_DTYPE(dtype, (adaptive_lsm_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)logits, ldl, labels, losses, lse, logprobs, argmax, N, V, q)));
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+extern "C" int txl_adaptive_lsm_nll_bwd(const void* logits, int64_t ldl, int dtype, void* dlogits, int64_t ldd, int dtype_out, const int64_t* labels,
+                                        const float* lse, const float* grow, int64_t N, int V, int n_clusters, const int* cutoffs, void* stream) {
+  TXL_CHECK_ARG(logits && dlogits && labels && lse && grow && N > 0 && V > 0 && ldl >= V + n_clusters && ldd >= V + n_clusters, "adaptive_lsm_nll_bwd: bad sizes");
+  TXL_CHECK_ARG(logits != dlogits || (dtype == dtype_out && ldl == ldd), "adaptive_lsm_nll_bwd: in-place needs identical dtype and pitch");
+  Cuts q; int rc = make_cuts(q, V, n_clusters, cutoffs, "adaptive_lsm_nll_bwd"); if (rc) return rc;
+  const int grid = (int)imin64(cdiv64(N, 8), (int64_t)txl_num_sms() * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TXL_F32 && dtype_out == TXL_F32) adaptive_lsm_bwd_kernel<float, float><<<grid, 256, 0, st>>>((const float*)logits, ldl, (float*)dlogits, ldd, labels, lse, grow, N, V, q);
+  else if (dtype == TXL_F32 && dtype_out == TXL_BF16) adaptive_lsm_bwd_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)logits, ldl, (bf16*)dlogits, ldd, labels, lse, grow, N, V, q);
+  else { txl_set_error("adaptive_lsm_nll_bwd: unsupported dtype pair"); return TXL_EINVAL; }
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+extern "C" int txl_pack_losses(const float* pos_losses, const int64_t* labels_shift, int B, int T, int V, int n_clusters, const int* cutoffs,
+                               float* packed, int64_t* perm, void* stream) {
+  TXL_CHECK_ARG(pos_losses && labels_shift && packed && B > 0 && T > 1 && V > 0, "pack_losses: bad args");
+  Cuts q; int rc = make_cuts(q, V, n_clusters, cutoffs, "pack_losses"); if (rc) return rc;
+  pack_losses_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos_losses, labels_shift, B, T, V, q, packed, perm);
+  TXL_LAUNCH_CHECK();
+  return TXL_OK;
+}
+
 // loss = mean(losses[losses != 0])  — single block, deterministic tree order
 __global__ void masked_mean_kernel(const float* __restrict__ losses, int64_t N, float* loss_out, float* count_out) {
   __shared__ double ssum[32];

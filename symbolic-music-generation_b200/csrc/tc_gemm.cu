@@ -22,7 +22,41 @@ static EncodeTiledFn get_encode() {
   });
   return fn;
 }
+// Encoded maps are cached per (base, shape, pitch, box): a training step re-encodes the same few hundred descriptors (weights, activation
+// buffers the caching allocator hands back at the same address) every step, 5-12 per attention call.  A map is a pure function of the key
+// (no device state), so entries never go stale; the table is dropped when it reaches 8192 entries.
+#include <unordered_map>
+namespace {
+struct TmapKey {
+  uint64_t v[7];
+  bool operator==(const TmapKey& o) const { for (int i = 0; i < 7; ++i) if (v[i] != o.v[i]) return false; return true; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < 7; ++i) { h ^= k.v[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); }
+    return (size_t)h;
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+bool tmap_lookup(const TmapKey& k, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmap_cache.find(k);
+  if (it == g_tmap_cache.end()) return false;
+  *out = it->second;
+  return true;
+}
+void tmap_store(const TmapKey& k, const CUtensorMap& m) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();
+  g_tmap_cache.emplace(k, m);
+}
+}  // namespace
+
 int txl_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  const TmapKey key = {{(uint64_t)(uintptr_t)base, rows, cols, ld, ((uint64_t)box_rows << 32) | box_cols, 0, 2}};
+  if (tmap_lookup(key, out)) return TXL_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) { txl_set_error("cuTensorMapEncodeTiled not available from the driver"); return TXL_ECUDA; }
   cuuint64_t dims[2] = {cols, rows};
@@ -32,10 +66,13 @@ int txl_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { txl_set_error("cuTensorMapEncodeTiled(2d rows=%llu cols=%llu ld=%llu box=%ux%u) failed: %d", (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols, (int)r); return TXL_ECUDA; }
+  tmap_store(key, *out);
   return TXL_OK;
 }
 int txl_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld2, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols) {
+  const TmapKey key = {{(uint64_t)(uintptr_t)base, rows, cols, ld, ((uint64_t)box_rows << 32) | box_cols, (d2 << 32) ^ ld2, 3}};
+  if (tmap_lookup(key, out)) return TXL_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) { txl_set_error("cuTensorMapEncodeTiled not available from the driver"); return TXL_ECUDA; }
   cuuint64_t dims[3] = {cols, rows, d2};
@@ -45,6 +82,7 @@ int txl_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t r
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { txl_set_error("cuTensorMapEncodeTiled(3d) failed: %d", (int)r); return TXL_ECUDA; }
+  tmap_store(key, *out);
   return TXL_OK;
 }
 

@@ -1288,6 +1288,18 @@ int64_t txl_relattn_bwd_tc_workspace(const TxlAttnDims* D) {
   return base + 2 * bwd_tile_rows(D) * BKV * 2 + 2048;     // + bf16 P and dS tile stores
 }
 
+// Probe switches of the backward (profiling only; never set on the product path): read from TXL_DBG / TXL_ABL ONCE at load time, changed
+// afterwards only through txl_relattn_bwd_probe — no getenv on the per-call path.
+static int env_int_once(const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; }
+static int g_bwd_probe_dbg = env_int_once("TXL_DBG");
+static int g_bwd_probe_abl = env_int_once("TXL_ABL");
+extern "C" int txl_relattn_bwd_probe(int dbg, int abl) {
+  const int old = g_bwd_probe_dbg;
+  g_bwd_probe_dbg = dbg;
+  g_bwd_probe_abl = abl;
+  return old;
+}
+
 int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, const void* k_cur, const void* v_cur, const void* r, const float* rwb,
                        const float* rrb, const void* out, const float* lse, const void* dout, void* dq, void* dk_mem, void* dv_mem, void* dk_cur,
                        void* dv_cur, float* dr, float* drwb, float* drrb, void* ws, const void* saved, const TxlAttnDims* D, void* stream, int* handled) {
@@ -1304,8 +1316,7 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
       !al16(dv_cur) || !al16(ws) || (dk_mem && (!al16(dk_mem) || !al16(dv_mem))))
     return TXL_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int dbg = 0;   // TXL_DBG (timing probes only): 16 = run the dQ pass alone, 32 = skip the prep kernel (operands from a previous call)
-  { const char* e = getenv("TXL_DBG"); dbg = e ? atoi(e) : 0; }
+  const int dbg = g_bwd_probe_dbg;   // timing probes only (txl_relattn_bwd_probe): 16 = run the dQ pass alone, 32 = skip the prep kernel
   const int64_t n = (int64_t)D->B * T * HD;
   bf16* qw = (bf16*)ws; bf16* qr = qw + n; float* delta = (float*)(qr + n);
   if (!(dbg & 32)) {
@@ -1353,7 +1364,7 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
     if ((rc = txl_make_tmap_2d(&M.dst, dstore, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
   } else { M.pst = M.qw; M.dst = M.qw; }
   a.m_tiles = nullptr; M.psv = M.qw; M.r64 = M.r; M.pst2 = M.qw; M.dst2 = M.qw;
-  { const char* e = getenv("TXL_ABL"); a.abl = e ? atoi(e) : 0; }
+  a.abl = g_bwd_probe_abl;
   if (saved && a.store_tiles && txl_relattn_saved_bytes_tc(D) > 0 && al16(saved)) {
     a.m_tiles = reinterpret_cast<const float*>(reinterpret_cast<const bf16*>(saved) + trows * BKV);
     if ((rc = txl_make_tmap_2d(&M.psv, saved, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;

@@ -99,7 +99,7 @@ def sequence_groups(model, B, requested=None):
     if requested is None:
         requested = int(os.environ.get('TXL_DECODE_GROUPS', '0')) or None
     need = (B + SK_MAXM - 1) // SK_MAXM              # a Decoder (one chain of kernels) takes at most SK_MAXM sequences
-    if model._E.dtype != torch.bfloat16 or os.environ.get('TXL_DECODE_TAIL', '1') == '0' or model.config.vocab_size > 8192:
+    if model._E.dtype != torch.bfloat16 or os.environ.get('TXL_DECODE_TAIL', '1') == '0' or model.config.vocab_size > 8192 or getattr(model.config, 'cutoffs', None):
         return need
     if requested is not None:
         return max(need, min(int(requested), B))
@@ -163,7 +163,7 @@ class Decoder:
             self.attn_ws = torch.empty(lib.txl_decode_attn_pipe_ws_bytes(B, H, dh, self.attn_splits), dtype=torch.uint8, device=dev)
             self.attn_cnt = torch.zeros(B * H, dtype=torch.int32, device=dev)
         # fused step tail (log-softmax + keyed uniform + sampler + eos/pad bookkeeping + next embedding + step counter in one kernel)
-        self.gen2_tail = self.pipe_attn and os.environ.get('TXL_DECODE_TAIL', '1') != '0' and cfg.vocab_size <= 8192
+        self.gen2_tail = self.pipe_attn and os.environ.get('TXL_DECODE_TAIL', '1') != '0' and cfg.vocab_size <= 8192 and not cfg.cutoffs
         self.x0 = torch.empty(B, d, dtype=dt, device=dev) if self.gen2_tail else None
         self.tail_arrive = torch.zeros(1, dtype=torch.int32, device=dev) if self.gen2_tail else None
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -176,7 +176,8 @@ class Decoder:
         self.eos, self.pad = eos_token_id, pad_token_id
         self.seed, self.seq_offset = int(seed), int(seq_offset)
         self.V = cfg.vocab_size
-        self.Vp = (self.V + 7) // 8 * 8
+        self.Vx = self.V + len(cfg.cutoffs)                # LM-head columns: token logits + one per adaptive-softmax cluster
+        self.Vp = (self.Vx + 7) // 8 * 8
         self.logits = torch.zeros(B, self.Vp, dtype=torch.float32 if dt == torch.bfloat16 else dt, device=dev)
         self.scores = torch.zeros(B, cfg.vocab_size, dtype=torch.float32, device=dev) if self.gen2_tail else None      # log-probs of the last step
         self.graph = None
@@ -225,7 +226,7 @@ class Decoder:
                 hdn = _skinny(y1, w.w1, bias=w.b1, relu=True)
                 f = _skinny(hdn, w.w2, bias=w.b2)
                 x, _, _, _ = ops.add_ln_fwd(y1, f, w.ln2_w, w.ln2_b, cfg.layer_norm_epsilon, save=False)
-            _skinny(x, m._E, bias=m._out_bias, out=self.logits[:, :self.V], pf=pf(0, 5))      # the next step's first attention kernel
+            _skinny(x, m._E_ext, bias=m._out_bias_ext, out=self.logits[:, :self.Vx], pf=pf(0, 5))      # the next step's first attention kernel
         finally:
             if pdl_old is not None:
                 lib.txl_set_pdl(pdl_old)
@@ -248,7 +249,10 @@ class Decoder:
                 if pdl_old is not None:
                     lib.txl_set_pdl(pdl_old)
             return
-        _, _, logprobs, _ = ops.logsoftmax_nll_fwd(logits, self.V, None, want_logprobs=True)
+        if self.cfg.cutoffs:
+            _, _, logprobs, _ = ops.adaptive_lsm_nll_fwd(logits, self.V, self.cfg.cutoffs, None, want_logprobs=True)
+        else:
+            _, _, logprobs, _ = ops.logsoftmax_nll_fwd(logits, self.V, None, want_logprobs=True)
         self.scores = logprobs
         if self.do_sample:
             check(lib.txl_decode_uniform(ptr(self.u), B, self.seed, self.seq_offset, ptr(self.pos), stream_ptr()), 'decode_uniform')
@@ -257,6 +261,13 @@ class Decoder:
         use_eos = self.eos is not None
         check(lib.txl_decode_commit(ptr(self.next), ptr(self.tok), ptr(self.unfinished), ptr(self.out_ids), self.out_ids.stride(0), self.col0, ptr(self.pos), B,
                                     int(self.eos if use_eos else 0), int(self.pad if self.pad is not None else 0), int(use_eos), stream_ptr()), 'decode_commit')
+
+    def set_unfinished(self, unfinished):
+        self.unfinished.copy_(unfinished)
+
+    def last_scores(self):
+        """(B, V) fp32 log-probs the last step sampled from (what HF's `scores` holds before the warpers)."""
+        return self.scores
 
     def run(self, first_token, n_steps, poll_every=64):
         """Feed `first_token` (B,) and generate `n_steps` tokens into out_ids[:, col0:col0+n_steps].  Returns steps actually run."""
@@ -296,6 +307,16 @@ class Decoder:
         return done
 
 
+def make_decoder(model, mems, out_ids, col0, groups=None, **kw):
+    """The decode engine generate() uses for `out_ids.shape[0]` sequences: one chain of kernels (Decoder) or several sequence groups as
+    parallel graph branches (GroupedDecoder).  Both expose run(first_token, n_steps), set_unfinished(mask) and last_scores()."""
+    B = out_ids.shape[0]
+    g = sequence_groups(model, B, groups)
+    if g > 1:
+        return GroupedDecoder(model, mems, out_ids, col0, g, **kw)
+    return Decoder(model, mems, out_ids, col0, **kw)
+
+
 class _BmSlice:
     """Batch slice of the batch-major mems (what Decoder reads through `._bm`)."""
 
@@ -330,6 +351,9 @@ class GroupedDecoder:
     def set_unfinished(self, unfinished):
         for d, (lo, hi) in zip(self.decs, self.bounds):
             d.unfinished.copy_(unfinished[lo:hi])
+
+    def last_scores(self):
+        return torch.cat([d.scores for d in self.decs], 0)
 
     def _all_unfinished_max(self):
         return max(int(d.unfinished.max().item()) for d in self.decs)

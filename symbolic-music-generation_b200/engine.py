@@ -68,7 +68,9 @@ class Geometry:
         self.N = B * T
         self.band = ops.make_band(T, mlen, cfg.mem_len, cfg.clamp_len, cfg.same_length)
         self.P = ops.num_r(T, mlen, cfg.clamp_len)
-        self.Vp = (self.V + 7) // 8 * 8
+        self.cutoffs = list(getattr(cfg, 'cutoffs', []) or [])
+        self.Vx = self.V + len(self.cutoffs)          # LM-head columns: token logits, then one logit per adaptive-softmax cluster
+        self.Vp = (self.Vx + 7) // 8 * 8
 
 
 def forward(cfg, W: List[LayerW], E, out_bias, ids, mems_bm, labels_shift, *, drop_p, seed, save: bool,
@@ -84,7 +86,7 @@ def forward(cfg, W: List[LayerW], E, out_bias, ids, mems_bm, labels_shift, *, dr
     dt, dev = E.dtype, E.device
     sv = Saved(ids=ids, labels=labels_shift, seed=seed, drop_p=drop_p, mems_real=mems_real, B=B, T=T, mlen=mlen) if save else None
 
-    x = ops.embed_fwd(ids.reshape(-1), E, math.sqrt(d), drop_p, seed, SITE_EMB)
+    x = ops.embed_fwd(ids.reshape(-1), E[:g.V], math.sqrt(d), drop_p, seed, SITE_EMB)     # E = [embedding ; cluster_weight] (V + n_clusters, d)
     pos = ops.posemb_table(g.P, cfg.clamp_len, d, dt, dev, drop_p, seed, SITE_POS)
     if save:
         sv.pos = pos
@@ -121,10 +123,13 @@ def forward(cfg, W: List[LayerW], E, out_bias, ids, mems_bm, labels_shift, *, dr
     # LM head: logits for every position; label shifting is done by the caller (labels_shift)
     # logits stay fp32 (the log-softmax / NLL reads them once; bf16 logits would cost ~1.5e-2 absolute on every log-prob)
     logits = torch.empty(N, g.Vp, dtype=torch.float32, device=dev)
-    if g.Vp != g.V:
-        logits[:, g.V:].zero_()
-    ops.gemm(core, E, transB=True, bias=out_bias, out=logits, N=g.V)
-    losses, lse_v, logprobs, argmax = ops.logsoftmax_nll_fwd(logits, g.V, labels_shift, want_logprobs, want_argmax)
+    if g.Vp != g.Vx:
+        logits[:, g.Vx:].zero_()
+    ops.gemm(core, E, transB=True, bias=out_bias, out=logits, N=g.Vx)
+    if g.cutoffs:      # adaptive softmax: head over the shortlist + cluster logits, one tail per cluster (A.6, cluster path)
+        losses, lse_v, logprobs, argmax = ops.adaptive_lsm_nll_fwd(logits, g.V, g.cutoffs, labels_shift, want_logprobs, want_argmax)
+    else:
+        losses, lse_v, logprobs, argmax = ops.logsoftmax_nll_fwd(logits, g.V, labels_shift, want_logprobs, want_argmax)
     loss = count = None
     if labels_shift is not None:
         loss, count = ops.masked_mean(losses)
@@ -143,9 +148,12 @@ def backward(cfg, W: List[LayerW], G: List[LayerW], E, gE, g_out_bias, sv: Saved
     dt = E.dtype
     p, seed = sv.drop_p, sv.seed
     # ---- LM head
-    dlogits = ops.logsoftmax_nll_bwd(sv.logits, g.V, sv.labels, sv.lse, grow, out_dtype=dt)           # (N, Vp) in the compute dtype
-    ops.colsum(dlogits[:, :g.V], g_out_bias)
-    dl = dlogits[:, :g.V]
+    if g.cutoffs:
+        dlogits = ops.adaptive_lsm_nll_bwd(sv.logits, g.V, g.cutoffs, sv.labels, sv.lse, grow, out_dtype=dt)
+    else:
+        dlogits = ops.logsoftmax_nll_bwd(sv.logits, g.V, sv.labels, sv.lse, grow, out_dtype=dt)       # (N, Vp) in the compute dtype
+    ops.colsum(dlogits[:, :g.Vx], g_out_bias)
+    dl = dlogits[:, :g.Vx]
     ops.gemm(dl, sv.core, transA=True, out=gE, accumulate=True)                                       # dE += dlogits^T core
     dcore = ops.gemm(dl, E)                                                                           # (N, d)
     sv.logits = None
@@ -188,4 +196,4 @@ def backward(cfg, W: List[LayerW], G: List[LayerW], E, gE, g_out_bias, sv: Saved
         sv.layers[li] = None
         if on_layer_done is not None:
             on_layer_done(li)
-    ops.embed_bwd(sv.ids.reshape(-1), dx, gE, math.sqrt(d), p, seed, SITE_EMB, dOut2=dx2)
+    ops.embed_bwd(sv.ids.reshape(-1), dx, gE[:g.V], math.sqrt(d), p, seed, SITE_EMB, dOut2=dx2)

@@ -91,13 +91,8 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
                     if cur < max_length:
                         dkw = dict(do_sample=do_sample, temperature=temperature, top_k=top_k, top_p=top_p, eos_token_id=eos_token_id,
                                    pad_token_id=pad_token_id, seed=seed, seq_offset=seq_offset, use_graph=use_cuda_graph)
-                        groups = decode.sequence_groups(model, B, decode_groups)
-                        if groups > 1:
-                            dec = decode.GroupedDecoder(model, past, out_ids, cur, groups, **dkw)
-                            dec.set_unfinished(unfinished)
-                        else:
-                            dec = decode.Decoder(model, past, out_ids, cur, **dkw)
-                            dec.unfinished.copy_(unfinished)
+                        dec = decode.make_decoder(model, past, out_ids, cur, groups=decode_groups, **dkw)
+                        dec.set_unfinished(unfinished)
                         cur += dec.run(nxt, max_length - cur)
                     break
                 u = torch.rand(B, device=dev, generator=generator) if do_sample else None

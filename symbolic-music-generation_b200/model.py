@@ -174,7 +174,13 @@ class _Holder(nn.Module):
 def _named_param_specs(cfg):
     """(state_dict name, shape, kind) in flat-buffer order.  kind: 'mat' (cast to compute dtype) or 'vec' (kept fp32)."""
     d, di, V, H, dh = cfg.d_model, cfg.d_inner, cfg.vocab_size, cfg.n_head, cfg.d_head
-    specs = [('transformer.word_emb.emb_layers.0.weight', (V, d), 'mat'), ('crit.out_layers.0.bias', (V,), 'vec')]
+    nc = len(cfg.cutoffs)
+    specs = [('transformer.word_emb.emb_layers.0.weight', (V, d), 'mat')]
+    if nc:      # adaptive-softmax clusters: packed right behind the embedding / output bias, so that [embedding ; cluster_weight] is ONE (V+nc, d)
+        specs += [('crit.cluster_weight', (nc, d), 'mat+')]          # matrix and [out bias ; cluster_bias] one vector ('+' = no alignment gap)
+    specs += [('crit.out_layers.0.bias', (V,), 'vec')]
+    if nc:
+        specs += [('crit.cluster_bias', (nc,), 'vec+')]
     for i in range(cfg.n_layer):
         a, f = f'transformer.layers.{i}.dec_attn.', f'transformer.layers.{i}.pos_ff.'
         specs += [
@@ -196,12 +202,13 @@ class _TxlStep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, ids, labels_shift, mems_bm, seed, drop_p, want_logprobs, *params):
-        out = engine.forward(model.config, model._W, model._E, model._out_bias, ids, mems_bm, labels_shift, drop_p=drop_p, seed=seed,
+        out = engine.forward(model.config, model._W, model._E_ext, model._out_bias_ext, ids, mems_bm, labels_shift, drop_p=drop_p, seed=seed,
                              save=True, want_logprobs=want_logprobs, want_argmax=model.monitor_greedy, zero_kvm=model._zero_kvm)
         ctx.model, ctx.sv = model, out['saved']
+        ctx.set_materialize_grads(False)
         model._last = out
         B, T = ids.shape
-        losses = out['losses'].view(B, T)[:, :T - 1]
+        losses, ctx.perm = model._returned_losses(out['losses'], labels_shift, B, T)
         ctx.mark_non_differentiable(*[t for t in (out['logprobs'],) if t is not None])
         lp = out['logprobs'] if out['logprobs'] is not None else torch.empty(0, device=ids.device)
         return out['loss'], losses, lp
@@ -217,11 +224,14 @@ class _TxlStep(torch.autograd.Function):
         if g_loss is not None:
             grow += (losses.view(B, T) != 0).to(torch.float32) * (g_loss.to(torch.float32) / sv.count)
         if g_losses is not None:
-            grow[:, :T - 1] += g_losses.to(torch.float32)
+            if ctx.perm is None:
+                grow[:, :T - 1] += g_losses.to(torch.float32)
+            else:       # packed loss order (adaptive softmax, HF keep_order=False): route each entry back to its position; no host sync
+                grow.view(-1).index_add_(0, ctx.perm.clamp(min=0), g_losses.reshape(-1).to(torch.float32) * (ctx.perm >= 0))
         gflat = model._fresh_grad_buffer()
         model._backwards_since_step += 1
         hook = model._grad_hook
-        engine.backward(model.config, model._W, model._G, model._E, model._gE, model._g_out_bias, sv, grow.view(-1),
+        engine.backward(model.config, model._W, model._G, model._E_ext, model._gE, model._g_out_bias, sv, grow.view(-1),
                         on_layer_done=(lambda li: hook('layer', li)) if hook else None)
         if hook:
             hook('embed', -1)
@@ -237,9 +247,8 @@ class MyTransfoXLLMHeadModel(nn.Module):
 
     def __init__(self, config: MyTransfoXLConfig, device=None):
         super().__init__()
-        if config.cutoffs:
-            raise NotImplementedError('adaptive-softmax clusters (cutoffs != []) are outside this path (SURVEY §8f-3); '
-                                      'the reference trains with model_config=dict(cutoffs=[]) (musicnlp/trainer/train.py:521-527)')
+        if len(config.cutoffs) > 4 or any(not (0 < c < config.vocab_size) for c in config.cutoffs) or sorted(set(config.cutoffs)) != list(config.cutoffs):
+            raise NotImplementedError('cutoffs must be at most 4 increasing values inside (0, vocab_size)')
         if config.div_val != 1 or config.d_embed != config.d_model or config.pre_lnorm or not config.untie_r or config.attn_type != 0:
             raise NotImplementedError('only div_val=1, d_embed=d_model, post-LN, untie_r=True, attn_type=0 are on the reference path')
         if config.n_head * config.d_head != config.d_model:
@@ -251,14 +260,18 @@ class MyTransfoXLLMHeadModel(nn.Module):
                                       'default dropatt=0.0 (notebook/train/transformer-xl.ipynb:492-513)')
         self.config = config
         self._specs = _named_param_specs(config)
-        self._slots, off = [], 0
-        for _, shape, _k in self._specs:
+        self._slots, off, end = [], 0, 0
+        for _, shape, kind in self._specs:
             n = 1
             for s in shape:
                 n *= s
+            if kind.endswith('+'):
+                off = end                     # glued to the previous tensor
             self._slots.append((off, n, shape))
-            off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
+            end = off + n
+            off = (end + _ALIGN - 1) // _ALIGN * _ALIGN
         self._flat_numel = off
+        self._n_head_slots = 2 + 2 * (1 if config.cutoffs else 0)       # slots before the first layer's
         flat = torch.zeros(off, dtype=torch.float32)
         self._build_modules(flat)
         self._init_weights()
@@ -323,6 +336,9 @@ class MyTransfoXLLMHeadModel(nn.Module):
         out0.weight = params['transformer.word_emb.emb_layers.0.weight']     # tie_word_embeddings
         out0.bias = params['crit.out_layers.0.bias']
         crit.out_layers = nn.ModuleList([out0])
+        if cfg.cutoffs:
+            crit.cluster_weight = params['crit.cluster_weight']
+            crit.cluster_bias = params['crit.cluster_bias']
         self.crit = crit
         self._param_by_name = params
 
@@ -333,7 +349,7 @@ class MyTransfoXLLMHeadModel(nn.Module):
             for name, p in self._param_by_name.items():
                 if name.endswith('layer_norm.weight'):
                     p.normal_(1.0, std)
-                elif name.endswith('.bias') and 'r_' not in name.rsplit('.', 1)[-1]:
+                elif (name.endswith('.bias') and 'r_' not in name.rsplit('.', 1)[-1]) or name == 'crit.cluster_bias':
                     p.zero_()
                 else:
                     p.normal_(0.0, std)
@@ -417,6 +433,11 @@ class MyTransfoXLLMHeadModel(nn.Module):
 
         self._E = mat('transformer.word_emb.emb_layers.0.weight')
         self._out_bias = vec('crit.out_layers.0.bias')
+        # LM-head operands: with adaptive-softmax clusters the cluster rows / biases sit right behind, so one GEMM yields token + cluster logits
+        V, d, nc = self.config.vocab_size, self.config.d_model, len(self.config.cutoffs)
+        o_e, o_b = self._slots[idx['transformer.word_emb.emb_layers.0.weight']][0], self._slots[idx['crit.out_layers.0.bias']][0]
+        self._E_ext = mat_src[o_e:o_e + (V + nc) * d].view(V + nc, d)
+        self._out_bias_ext = self._flat[o_b:o_b + V + nc]
         self._W = []
         for i in range(self.config.n_layer):
             a, f = f'transformer.layers.{i}.dec_attn.', f'transformer.layers.{i}.pos_ff.'
@@ -433,8 +454,10 @@ class MyTransfoXLLMHeadModel(nn.Module):
         def gv(n):
             return self._view(gflat, idx[n])
 
-        self._gE = gv('transformer.word_emb.emb_layers.0.weight')
-        self._g_out_bias = gv('crit.out_layers.0.bias').reshape(-1)
+        V, d, nc = self.config.vocab_size, self.config.d_model, len(self.config.cutoffs)
+        o_e, o_b = self._slots[idx['transformer.word_emb.emb_layers.0.weight']][0], self._slots[idx['crit.out_layers.0.bias']][0]
+        self._gE = gflat[o_e:o_e + (V + nc) * d].view(V + nc, d)          # [embedding ; cluster_weight] gradients
+        self._g_out_bias = gflat[o_b:o_b + V + nc]
         self._G = []
         for i in range(self.config.n_layer):
             a, f = f'transformer.layers.{i}.dec_attn.', f'transformer.layers.{i}.pos_ff.'
@@ -491,11 +514,11 @@ class MyTransfoXLLMHeadModel(nn.Module):
 
     def layer_param_ranges(self):
         """[(start, end)] element ranges of the flat buffers: index 0 = embedding + output bias, 1.. = layers (for gradient buckets)."""
-        per = 13
-        out = [(self._slots[0][0], self._slots[2][0] if len(self._slots) > 2 else self._flat_numel)]
+        per, h0 = 13, self._n_head_slots
+        out = [(self._slots[0][0], self._slots[h0][0] if len(self._slots) > h0 else self._flat_numel)]
         for i in range(self.config.n_layer):
-            s = self._slots[2 + per * i][0]
-            e = self._slots[2 + per * (i + 1)][0] if i + 1 < self.config.n_layer else self._flat_numel
+            s = self._slots[h0 + per * i][0]
+            e = self._slots[h0 + per * (i + 1)][0] if i + 1 < self.config.n_layer else self._flat_numel
             out.append((s, e))
         return out
 
@@ -607,10 +630,10 @@ class MyTransfoXLLMHeadModel(nn.Module):
             logprobs = lp if want_logprobs else None
         else:
             with torch.no_grad():
-                out = engine.forward(self.config, self._W, self._E, self._out_bias, ids, mems_bm, labels_shift, drop_p=drop_p, seed=seed,
+                out = engine.forward(self.config, self._W, self._E_ext, self._out_bias_ext, ids, mems_bm, labels_shift, drop_p=drop_p, seed=seed,
                                      save=False, want_logprobs=want_logprobs, want_argmax=self.monitor_greedy, zero_kvm=self._zero_kvm)
             loss = out['loss']
-            losses = out['losses'].view(bsz, tgt_len)[:, :tgt_len - 1] if labels is not None else None
+            losses = self._returned_losses(out['losses'], labels_shift, bsz, tgt_len)[0] if labels is not None else None
             logprobs = out['logprobs']
         new_mems = self._new_mems(mems_bm, out['hid_in'], bsz, tgt_len)
         # greedy ids of every position, straight from the LM-head kernel (what `logits.argmax(-1)` is in train_util_wrap.py:106 / train.py:248)
@@ -640,6 +663,14 @@ class MyTransfoXLLMHeadModel(nn.Module):
         """Call after writing parameters through raw storage (`model._flat`, `.data`, a broadcast): such writes do not bump the autograd
         version counters `_refresh_shadow` keys on, so the bf16 shadow would silently go stale."""
         self._shadow_version = None
+
+    def _returned_losses(self, pos_losses, labels_shift, B, T):
+        """`losses` as the reference returns them: (B, T-1) in position order without clusters; with adaptive-softmax clusters HF's criterion
+        (built with keep_order=False) returns them PACKED cluster by cluster with the ignored labels as trailing zeros (Appendix A.6) — same
+        multiset, so `losses[losses != 0].mean()` is unchanged.  Returns (losses, perm or None)."""
+        if not self.config.cutoffs:
+            return pos_losses.view(B, T)[:, :T - 1], None
+        return ops.pack_losses(pos_losses, labels_shift, B, T, self.config.vocab_size, self.config.cutoffs)
 
     def ntp_acc_counts(self, labels, out=None):
         """int64[2] device tensor (matches, non-pad positions) of next-token prediction for the last forward (needs monitor_greedy=True):

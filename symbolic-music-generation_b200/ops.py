@@ -191,6 +191,40 @@ def logsoftmax_nll_bwd(logits, V, labels, lse, grow, out_dtype=None):
     return out
 
 
+def _cuts(cutoffs):
+    arr = (C.c_int * len(cutoffs))(*[int(c) for c in cutoffs])
+    return arr
+
+
+def adaptive_lsm_nll_fwd(logits, V, cutoffs, labels=None, want_logprobs=False, want_argmax=False):
+    """Cluster path of HF's ProjectedAdaptiveLogSoftmax: logits (N, >= V + n_clusters) = token logits then cluster logits."""
+    N, nc, dev = logits.shape[0], len(cutoffs), logits.device
+    losses = torch.empty(N, dtype=torch.float32, device=dev) if labels is not None else None
+    lse = torch.empty(N, nc + 1, dtype=torch.float32, device=dev)
+    logprobs = torch.empty(N, V, dtype=torch.float32, device=dev) if want_logprobs else None
+    argmax = torch.empty(N, dtype=torch.int64, device=dev) if want_argmax else None
+    check(_lib().txl_adaptive_lsm_nll_fwd(ptr(logits), logits.stride(0), ptr(labels), ptr(losses), ptr(lse), ptr(logprobs), ptr(argmax), N, V, nc,
+                                          _cuts(cutoffs), dtype_code(logits.dtype), stream_ptr()), 'adaptive_lsm_nll_fwd')
+    return losses, lse, logprobs, argmax
+
+
+def adaptive_lsm_nll_bwd(logits, V, cutoffs, labels, lse, grow, out_dtype=None):
+    out = logits if out_dtype in (None, logits.dtype) else torch.empty(logits.shape[0], logits.stride(0), dtype=out_dtype, device=logits.device)
+    check(_lib().txl_adaptive_lsm_nll_bwd(ptr(logits), logits.stride(0), dtype_code(logits.dtype), ptr(out), out.stride(0), dtype_code(out.dtype),
+                                          ptr(labels), ptr(lse), ptr(grow), logits.shape[0], V, len(cutoffs), _cuts(cutoffs), stream_ptr()),
+          'adaptive_lsm_nll_bwd')
+    return out
+
+
+def pack_losses(pos_losses, labels_shift, B, T, V, cutoffs):
+    """HF keep_order=False ordering of the returned loss vector: (packed (B, T-1) fp32, perm (B*(T-1),) int64 of source rows b*T+t / -1)."""
+    packed = torch.empty(B, T - 1, dtype=torch.float32, device=pos_losses.device)
+    perm = torch.empty(B * (T - 1), dtype=torch.int64, device=pos_losses.device)
+    check(_lib().txl_pack_losses(ptr(pos_losses), ptr(labels_shift), B, T, V, len(cutoffs), _cuts(cutoffs), ptr(packed), ptr(perm), stream_ptr()),
+          'pack_losses')
+    return packed, perm
+
+
 def ntp_acc(preds, labels, out=None):
     """(matches, non-pad count) of next-token prediction, accumulated into the int64[2] device tensor `out` (created zeroed if None)."""
     assert preds.dtype == torch.int64 and labels.dtype == torch.int64 and preds.shape == labels.shape and preds.dim() == 2

@@ -53,8 +53,9 @@ def make_pair(pkg, mode, seed=77, **kw):
     torch.manual_seed(seed)
     base = dict(vocab_size=422, d_model=128, n_head=4, n_layer=2, d_head=32, d_inner=256, mem_len=32, clamp_len=1024, dropout=0.0)
     base.update(kw)
+    base.setdefault('cutoffs', [])
     ref = RefTransfoXLLMHeadModel(RefConfig(d_embed=base['d_model'], **base))
-    cfg = pkg.MyTransfoXLConfig('debug', cutoffs=[], compute_dtype=mode, d_embed=base['d_model'], **base)
+    cfg = pkg.MyTransfoXLConfig('debug', compute_dtype=mode, d_embed=base['d_model'], **base)
     model = pkg.MyTransfoXLLMHeadModel(cfg)
     missing = model.load_state_dict(ref.state_dict(), strict=True)
     model.to('cuda')

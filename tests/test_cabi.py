@@ -66,15 +66,23 @@ def test_config_mirrors_reference_presets(pkg):
     assert pkg.MyTransfoXLConfig('small', tokenizer=Tok()).cutoffs == [1000]
     Tok.vocab_size = 422
     assert pkg.MyTransfoXLConfig('small', tokenizer=Tok()).cutoffs == []
+    # the reference's default criterion for V >= 1000: adaptive-softmax cluster path, HF state_dict names, cluster rows glued behind the embedding
+    m = pkg.MyTransfoXLLMHeadModel(pkg.MyTransfoXLConfig('debug', vocab_size=1190, cutoffs=[1000]))
+    sd = m.state_dict()
+    assert sd['crit.cluster_weight'].shape == (1, 128) and sd['crit.cluster_bias'].shape == (1,)
+    emb, cw = m.transformer.word_emb.emb_layers[0].weight, m.crit.cluster_weight
+    assert cw.data_ptr() == emb.data_ptr() + emb.numel() * 4 and m.crit.cluster_bias.data_ptr() == m.crit.out_layers[0].bias.data_ptr() + 1190 * 4
+    assert float(m.crit.cluster_bias.abs().sum()) == 0 and float(cw.abs().sum()) > 0
     with pytest.raises(NotImplementedError):
-        pkg.MyTransfoXLLMHeadModel(pkg.MyTransfoXLConfig('debug', vocab_size=1190, cutoffs=[1000]))
+        pkg.MyTransfoXLLMHeadModel(pkg.MyTransfoXLConfig('debug', vocab_size=1190, cutoffs=[1000, 500]))
 
 
-def test_state_dict_roundtrip_with_oracle(pkg, tmp_path):
+@pytest.mark.parametrize('cutoffs', [[], [20], [10, 25]])
+def test_state_dict_roundtrip_with_oracle(pkg, tmp_path, cutoffs):
     from oracle.txl_ref import RefConfig, RefTransfoXLLMHeadModel
     kw = dict(vocab_size=37, d_model=32, n_head=4, n_layer=2, d_head=8, d_inner=48, mem_len=4, clamp_len=8)
-    ref = RefTransfoXLLMHeadModel(RefConfig(d_embed=32, **kw))
-    m = pkg.MyTransfoXLLMHeadModel(pkg.MyTransfoXLConfig('debug', cutoffs=[], d_embed=32, **kw))
+    ref = RefTransfoXLLMHeadModel(RefConfig(d_embed=32, cutoffs=cutoffs, **kw))
+    m = pkg.MyTransfoXLLMHeadModel(pkg.MyTransfoXLConfig('debug', cutoffs=cutoffs, d_embed=32, **kw))
     assert set(m.state_dict()) == set(ref.state_dict())
     assert m.num_parameters() == ref.num_parameters()
     m.load_state_dict(ref.state_dict())

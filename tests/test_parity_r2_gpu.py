@@ -1,0 +1,289 @@
+"""Round-2 parity cases on the configurations BASELINE.json names ("do this" item 1) and on the rows added this round:
+full-depth cfg2, the cfg5 geometry (T = mem_len = 2048, clamp_len 1024), the bf16 decode step against the ORACLE's own
+`forward(input_ids[:, -1:], mems)` (not against the repo's forward), a cfg4-shaped decode, the reference's literal `generate` call, the
+adaptive-softmax criterion, gradient accumulation, and batches beyond 64 sequences."""
+import importlib
+import os
+
+import pytest
+import torch
+
+from conftest import make_pair
+
+pytestmark = pytest.mark.gpu
+FAST = os.environ.get('TXL_TEST_FAST', '') == '1'
+
+
+def _batch(V, B, T, seed=77, pad=True):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    labels = ids.clone()
+    if pad and B > 1:
+        labels[1, T - T // 4:] = -100
+    return ids, labels
+
+
+def _fro(a, b):
+    return ((a - b).norm() / b.norm().clamp(min=1e-12)).item()
+
+
+# ----------------------------------------------------------------------------------------------------------------- cfg2, full depth
+def test_cfg2_full_depth_bf16_carried_mems(pkg):
+    """BASELINE configs[1] at full depth: 12 layers, d_model 512, 8 heads, seq 1024, mem_len 1024, V 1190, bf16, two segments (the second one
+    attends the first one's real mems).  Per-token losses and eval log-probs of the SECOND segment within 1e-2 of the fp32 oracle."""
+    ref, model = make_pair(pkg, 'bf16', vocab_size=1190, d_model=512, n_head=8, d_head=64, d_inner=2048, n_layer=12, mem_len=1024, clamp_len=1024)
+    ids1, _ = _batch(1190, 2, 1024, seed=77, pad=False)
+    ids2, labels2 = _batch(1190, 2, 1024, seed=78)
+    ref.eval(); model.eval()
+    with torch.no_grad():
+        r1 = ref(input_ids=ids1)
+        o1 = model(input_ids=ids1.cuda())
+        r2 = ref(input_ids=ids2, mems=r1.mems, labels=labels2.clone())
+        o2 = model(input_ids=ids2.cuda(), mems=o1.mems, labels=labels2.cuda())
+    valid = r2.losses != 0
+    assert torch.equal(o2.losses.cpu() != 0, valid)
+    # relative to max(|loss|, 1): an easy token has a loss of ~0.1 where a pure ratio is meaningless
+    rel = ((o2.losses.cpu() - r2.losses).abs() / r2.losses.abs().clamp(min=1.0))[valid].max().item()
+    assert rel < 1e-2, rel
+    assert abs(o2.loss.item() - r2.loss.item()) / r2.loss.item() < 2e-3
+    lrel = ((o2.logits.float().cpu() - r2.logits).abs() / r2.logits.abs()).max().item()      # log-probs ~ -7
+    assert lrel < 1e-2, lrel
+    mrel = _fro(o2.mems[11].float().cpu(), r2.mems[11])
+    assert mrel < 1e-2, mrel
+
+
+# ----------------------------------------------------------------------------------------------------------------- cfg5 geometry
+@pytest.mark.parametrize('mode,tol', [('fp32', 2e-4), ('bf16', 1e-2)])
+def test_cfg5_geometry_one_layer(pkg, mode, tol):
+    """BASELINE configs[4] geometry: T = mem_len = 2048 with clamp_len 1024 (distances 1025..2047 share the clamped position row), one layer,
+    d_model 512, 8 heads: losses, eval log-probs and every gradient against the oracle's literal pad/view `_rel_shift` + uint8 mask."""
+    ref, model = make_pair(pkg, mode, vocab_size=1190, d_model=512, n_head=8, d_head=64, d_inner=2048, n_layer=1, mem_len=2048, clamp_len=1024)
+    ids, labels = _batch(1190, 1, 2048, pad=False)
+    labels[0, 1900:] = -100
+    torch.manual_seed(3)
+    mems = [0.5 * torch.randn(2048, 1, 512)]
+    ref.train(); model.train()
+    ro = ref(input_ids=ids, mems=mems, labels=labels.clone())
+    ro.loss.backward()
+    out = model(input_ids=ids.cuda(), mems=[m.cuda() for m in mems], labels=labels.cuda())
+    out.loss.backward()
+    valid = ro.losses != 0
+    rel = ((out.losses.detach().cpu() - ro.losses.detach()).abs() / ro.losses.detach().abs().clamp(min=1.0))[valid].max().item()
+    assert rel < tol, rel
+    got = dict(model.named_parameters())
+    for name, p in ref.named_parameters():
+        g = got[name].grad.float().cpu()
+        if mode == 'fp32':
+            assert ((g - p.grad).abs().max() / p.grad.abs().max()).item() < 1e-3, name
+        else:
+            cos = torch.nn.functional.cosine_similarity(g.flatten(), p.grad.flatten(), dim=0).item()
+            assert cos > 0.99 and _fro(g, p.grad) < 0.12, (name, cos, _fro(g, p.grad))
+    model.eval(); ref.eval()
+    with torch.no_grad():
+        lg = model(input_ids=ids.cuda(), mems=[m.cuda() for m in mems]).logits.float().cpu()
+        lr = ref(input_ids=ids, mems=mems).logits
+    assert ((lg - lr).abs() / lr.abs()).max().item() < tol
+
+
+# ----------------------------------------------------------------------------------------------------------------- decode vs the oracle
+def _decode_vs_oracle(pkg, ref, model, B, prompt_len, n_steps, V, tol, groups=None):
+    """Drives the device-resident decode step (ring cache, no CUDA graph so that every step's scores can be read) greedily and feeds the
+    ORACLE the same tokens through its own `forward(input_ids[:, -1:], mems)`; returns the worst relative log-prob error over all steps."""
+    decode = importlib.import_module('symbolic-music-generation_b200.decode')
+    model.eval(); ref.eval()
+    ids, _ = _batch(V, B, prompt_len, pad=False)
+    with torch.no_grad():
+        ro = ref(input_ids=ids)
+        out = model(input_ids=ids.cuda())
+        r_past, past = ro.mems, out.mems
+        tok = ro.logits[:, -1].argmax(-1)                  # both sides are fed the oracle's greedy token
+        out_ids = torch.zeros(B, n_steps + 1, dtype=torch.int64, device='cuda')
+        dec = decode.make_decoder(model, past, out_ids, 0, groups=groups, do_sample=False, temperature=1.0, top_k=0, top_p=1.0, eos_token_id=None,
+                                  pad_token_id=None, use_graph=False)
+        worst = 0.0
+        for step in range(n_steps):
+            r = ref(input_ids=tok[:, None], mems=r_past)
+            r_past = r.mems
+            dec.run(tok.cuda(), 1)
+            got, want = dec.last_scores().float().cpu(), r.logits[:, -1]
+            worst = max(worst, ((got - want).abs() / want.abs()).max().item())
+            tok = want.argmax(-1)
+    return worst
+
+
+@pytest.mark.parametrize('mem_len,dh,H', [(32, 32, 4), (48, 64, 2), (64, 64, 8)])
+def test_decode_step_bf16_vs_oracle(pkg, mem_len, dh, H):
+    """bf16 decode step log-probs vs the oracle's `forward(input_ids[:, -1:], mems)` at <= 1e-2 relative, over mem_len + 8 steps (the ring wraps)."""
+    ref, model = make_pair(pkg, 'bf16', mem_len=mem_len, n_layer=2, d_head=dh, n_head=H, d_model=dh * H)
+    worst = _decode_vs_oracle(pkg, ref, model, 3, mem_len + 5, mem_len + 8, 422, 1e-2)
+    assert worst < 1e-2, worst
+
+
+def test_decode_cfg4_shape_bf16_vs_oracle(pkg):
+    """BASELINE configs[3] shape: 64 sequences, 12 layers, d_model 512, mem_len 1024, bf16; 32 decode steps vs the oracle (TXL_TEST_FAST=1: 6)."""
+    ref, model = make_pair(pkg, 'bf16', vocab_size=1190, d_model=512, n_head=8, d_head=64, d_inner=2048, n_layer=12, mem_len=1024, clamp_len=1024)
+    worst = _decode_vs_oracle(pkg, ref, model, 64, 16, 6 if FAST else 32, 1190, 1e-2)
+    assert worst < 1e-2, worst
+
+
+# ----------------------------------------------------------------------------------------------------------------- the reference's generate call
+def test_reference_generate_call_takes_the_device_decode_path(pkg):
+    """The call `MusicGenerator.__call__` makes (musicnlp/trainer/eval.py:277,325-333: HF kwargs only, no seed) must run the device-resident
+    decode step, not one full forward per token: the attention kernel of the decode step is launched once per layer and token."""
+    L = importlib.import_module('symbolic-music-generation_b200._lib')
+    lib = L.load()
+    _, model = make_pair(pkg, 'bf16', mem_len=32, n_layer=2)
+    ids, _ = _batch(422, 4, 6, pad=False)
+    torch.manual_seed(11)
+    n0 = lib.txl_launch_count()
+    out = model.generate(input_ids=ids.cuda(), max_length=6 + 40, do_sample=True, top_k=8, renormalize_logits=True, early_stopping=True)
+    n1 = lib.txl_launch_count()
+    assert model.last_generate_path == 'decode_cache'
+    assert out.shape[0] == 4 and out.shape[1] <= 46 and torch.equal(out[:, :6].cpu(), ids)
+    # prompt forward + ONE eager step + graph capture (launch calls are counted while capturing, replays are not): far fewer host-side launch
+    # calls than 40 per-token forwards would make (> 40 * 2 layers * 10 kernels)
+    assert n1 - n0 < 400, n1 - n0
+    # torch.manual_seed makes the un-seeded call reproducible (as it does HF's multinomial); consecutive calls differ
+    torch.manual_seed(11)
+    again = model.generate(input_ids=ids.cuda(), max_length=6 + 40, do_sample=True, top_k=8, renormalize_logits=True, early_stopping=True)
+    other = model.generate(input_ids=ids.cuda(), max_length=6 + 40, do_sample=True, top_k=8, renormalize_logits=True, early_stopping=True)
+    assert torch.equal(out, again)
+    assert out.shape != other.shape or not torch.equal(out, other)
+    # a torch.Generator selects the host loop
+    g = torch.Generator(device='cuda').manual_seed(3)
+    model.generate(input_ids=ids.cuda(), max_length=12, do_sample=True, top_k=8, generator=g)
+    assert model.last_generate_path == 'forward_per_token'
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_generate_more_than_64_sequences(pkg, mode):
+    """Any batch size: 70 sequences are decoded as further sequence groups and give the tokens of the same sequences decoded in two calls."""
+    _, model = make_pair(pkg, mode, mem_len=16, n_layer=1)
+    ids, _ = _batch(422, 70, 4, pad=False)
+    kw = dict(max_length=4 + 24, do_sample=True, top_k=8, temperature=1.0, renormalize_logits=True, eos_token_id=None, seed=5)
+    full = model.generate(input_ids=ids.cuda(), **kw)
+    lo = model.generate(input_ids=ids[:40].cuda(), seq_offset=0, **kw)
+    hi = model.generate(input_ids=ids[40:].cuda(), seq_offset=40, **kw)
+    assert model.last_generate_path == 'decode_cache'
+    assert full.shape == (70, 28) and torch.equal(full, torch.cat([lo, hi], 0))
+
+
+# ----------------------------------------------------------------------------------------------------------------- adaptive softmax (8f-3)
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('bf16', 1e-2)])
+@pytest.mark.parametrize('V,cutoffs', [(1190, [1000]), (60, [20, 45])])
+def test_adaptive_softmax_model_parity(pkg, mode, tol, V, cutoffs):
+    """The reference's default criterion for V >= 1000 (`cutoffs=[1000]`, transformer_xl.py:56-66): HF ProjectedAdaptiveLogSoftmax cluster
+    path.  Packed `losses` (keep_order=False), loss, eval log-probs over the full vocabulary, and gradients incl. crit.cluster_*."""
+    ref, model = make_pair(pkg, mode, vocab_size=V, cutoffs=cutoffs)
+    ids, labels = _batch(V, 3, 40)
+    ids[0, :10] = torch.arange(V - 10, V)                  # make sure the last tail is exercised
+    labels[0, :10] = ids[0, :10]
+    ref.train(); model.train()
+    ro = ref(input_ids=ids, labels=labels.clone())
+    ro.loss.backward()
+    out = model(input_ids=ids.cuda(), labels=labels.cuda())
+    out.loss.backward()
+    assert out.losses.shape == (3, 39) and torch.equal(out.losses.detach().cpu() != 0, ro.losses.detach() != 0)
+    valid = ro.losses != 0
+    rel = ((out.losses.detach().cpu() - ro.losses.detach()).abs() / ro.losses.detach().abs().clamp(min=1e-2 if mode == 'fp32' else 1.0))[valid].max().item()
+    assert rel < tol, rel
+    assert abs(out.loss.item() - ro.loss.item()) / ro.loss.item() < tol
+    got = dict(model.named_parameters())
+    assert 'crit.cluster_weight' in got and 'crit.cluster_bias' in got
+    for name, p in ref.named_parameters():
+        g = got[name].grad.float().cpu()
+        if mode == 'fp32':
+            assert ((g - p.grad).abs().max() / p.grad.abs().max().clamp(min=1e-12)).item() < 5e-4, name
+        else:
+            assert _fro(g, p.grad) < 0.1, (name, _fro(g, p.grad))
+    model.eval(); ref.eval()
+    with torch.no_grad():
+        eo = model(input_ids=ids.cuda(), labels=labels.cuda())
+        er = ref(input_ids=ids, labels=labels.clone())
+    assert eo.logits.shape == (3, 40, V)
+    assert ((eo.logits.float().cpu() - er.logits).abs() / er.logits.abs().clamp(min=1e-2)).max().item() < tol
+    assert torch.allclose(eo.logits.float().exp().sum(-1).cpu(), torch.ones(3, 40), atol=1e-3)
+    assert torch.equal(eo.losses.cpu() != 0, er.losses != 0)
+
+
+def test_adaptive_softmax_losses_gradient_and_generate(pkg):
+    """Gradients routed through the packed `losses` vector; greedy generate over the cluster path == oracle (fp32)."""
+    ref, model = make_pair(pkg, 'fp32', vocab_size=60, cutoffs=[20, 45], n_layer=1)
+    ids, labels = _batch(60, 2, 24)
+    ref.train(); model.train()
+    w = torch.rand(2, 23)
+    (ref(input_ids=ids, labels=labels.clone()).losses * w).sum().backward()
+    (model(input_ids=ids.cuda(), labels=labels.cuda()).losses * w.cuda()).sum().backward()
+    got = dict(model.named_parameters())
+    for name, p in ref.named_parameters():
+        assert ((got[name].grad.cpu() - p.grad).abs().max() / p.grad.abs().max().clamp(min=1e-12)).item() < 5e-4, name
+    prompt = torch.randint(1, 60, (3, 5))
+    want = ref.generate(prompt, max_length=5 + 60, do_sample=False, eos_token_id=None)
+    have = model.generate(input_ids=prompt.cuda(), max_length=5 + 60, do_sample=False, eos_token_id=None)
+    assert torch.equal(have.cpu(), want)
+    bf = make_pair(pkg, 'bf16', vocab_size=60, cutoffs=[20, 45], n_layer=1)[1]
+    s = bf.generate(input_ids=prompt.cuda(), max_length=5 + 30, do_sample=True, top_k=8, eos_token_id=None, seed=3)
+    assert s.shape == (3, 35) and int(s.max()) < 60 and bf.last_generate_path == 'decode_cache'
+
+
+# ----------------------------------------------------------------------------------------------------------------- optimiser / labels
+def test_gradient_accumulation_reaches_the_fused_optimizer(pkg):
+    """Two backwards before one step (HF `gradient_accumulation_steps`): FusedAdamW must consume the SUM the `.grad`s hold, not the last
+    micro-batch's buffer.  Checked against torch.optim.AdamW on the oracle fed the same two micro-batches."""
+    optim = importlib.import_module('symbolic-music-generation_b200.optim')
+    from oracle.txl_ref import hf_param_groups
+    ref, model = make_pair(pkg, 'fp32', n_layer=1)
+    ref.train(); model.train()
+    a, la = _batch(422, 2, 16, seed=1)
+    b, lb = _batch(422, 2, 16, seed=2)
+    opt = optim.FusedAdamW(model, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
+    ropt = torch.optim.AdamW(hf_param_groups(ref, 0.01), lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    for ids, lab in ((a, la), (b, lb)):
+        model(input_ids=ids.cuda(), labels=lab.cuda()).loss.backward()
+        ref(input_ids=ids, labels=lab.clone()).loss.backward()
+    torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+    ropt.step()
+    opt.step()
+    opt.zero_grad()
+    got = dict(model.named_parameters())
+    for name, p in ref.named_parameters():
+        assert torch.allclose(got[name].detach().cpu(), p.detach(), rtol=1e-4, atol=2e-6), name
+    # and an edited .grad (external unscaling) is honoured
+    model(input_ids=a.cuda(), labels=la.cuda()).loss.backward()
+    for p in model.parameters():
+        p.grad = p.grad * 0.0
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    opt2 = optim.FusedAdamW(model, lr=1e-3, weight_decay=0.0, max_grad_norm=0.0)
+    opt2.step()
+    for n, p in model.named_parameters():
+        assert torch.equal(p.detach(), before[n]), n
+
+
+def test_device_label_fixup_and_range_check(pkg):
+    """All-pad first row: device labels are patched in place by the label-shift kernel (no host sync), host labels on the host; with
+    `check_ranges` out-of-vocabulary labels are counted on the device and reported by assert_ranges_ok()."""
+    ref, model = make_pair(pkg, 'fp32', n_layer=1)
+    ids, labels = _batch(422, 2, 12, pad=False)
+    labels[0, 1:] = -100
+    host = labels.clone()
+    model.train(); ref.train()
+    out_h = model(input_ids=ids.cuda(), labels=host)                    # CPU labels
+    assert host[0, 1].item() == model.config.eos_token_id
+    dev = labels.clone().cuda()
+    out_d = model(input_ids=ids.cuda(), labels=dev)
+    assert dev[0, 1].item() == model.config.eos_token_id
+    i32 = labels.clone().int().cuda()                                   # not int64: converted copy, side effect carried back
+    model(input_ids=ids.cuda(), labels=i32)
+    assert i32[0, 1].item() == model.config.eos_token_id
+    ro = ref(input_ids=ids, labels=labels.clone())
+    for o in (out_h, out_d):
+        assert abs(o.loss.item() - ro.loss.item()) < 1e-4 * ro.loss.item()
+    model.check_ranges = True
+    ok = ids.clone()
+    model(input_ids=ids.cuda(), labels=ok.cuda())
+    model.assert_ranges_ok()
+    bad = ids.clone()
+    bad[1, 3] = 422
+    model(input_ids=ids.cuda(), labels=bad.cuda())
+    with pytest.raises(IndexError):
+        model.assert_ranges_ok()
