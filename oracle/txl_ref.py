@@ -368,12 +368,18 @@ class _Transformer(nn.Module):
         return core_out.transpose(0, 1).contiguous(), new_mems
 
 
-@dataclass
-class RefOutput:
-    loss: Optional[torch.Tensor] = None
-    losses: Optional[torch.Tensor] = None
-    prediction_scores: object = None
-    mems: Optional[List[torch.Tensor]] = None
+class RefOutput(dict):
+    """reference musicnlp/models/transformer_xl.py:81-124 (`TransfoXLLMHeadModelOutput`, an HF `ModelOutput`): dict-like over the non-None
+    fields in the order `losses, prediction_scores, mems, hidden_states, attentions, loss`, with attribute access and `.logits`."""
+    _fields = ('losses', 'prediction_scores', 'mems', 'hidden_states', 'attentions', 'loss')
+
+    def __init__(self, loss=None, losses=None, prediction_scores=None, mems=None, hidden_states=None, attentions=None):
+        super().__init__()
+        vals = dict(losses=losses, prediction_scores=prediction_scores, mems=mems, hidden_states=hidden_states, attentions=attentions, loss=loss)
+        for k in self._fields:
+            object.__setattr__(self, k, vals[k])
+            if vals[k] is not None:
+                self[k] = vals[k]
 
     @property
     def logits(self):

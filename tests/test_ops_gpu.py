@@ -429,7 +429,7 @@ def test_dec_linear_vs_fp32_matmul(pkg, M, N, K):
 @pytest.mark.gpu
 @pytest.mark.parametrize('B,H,dh,ML', [(3, 2, 64, 128), (2, 3, 32, 40), (2, 2, 128, 100), (64, 8, 64, 1024), (1, 1, 64, 7)])
 def test_decode_attn_pipe_vs_first_generation(pkg, B, H, dh, ML):
-    """The bulk-copy-pipelined decode attention == the register-fed kernel on the same ring, at ring positions before, at and after the wrap
+    """The bulk-copy-pipelined bf16 decode attention == the register-fed fp32 kernel on the same ring, at ring positions before, at and after the wrap
     point (incl. mem_len that is not a multiple of the 32-key stage); the ring append is bit-identical."""
     import importlib
     L_ = importlib.import_module('symbolic-music-generation_b200._lib')
@@ -455,11 +455,13 @@ def test_decode_attn_pipe_vs_first_generation(pkg, B, H, dh, ML):
     for p in list(range(0, 12)) + [31, 32, ML - 1, ML, ML + 5] + list(range(3 * ML + 33, 3 * ML + 39)):
         qkv = torch.randn(B, 3 * HD, generator=g).cuda().to(bf)
         pos = torch.tensor([p], dtype=torch.int32, device='cuda')
-        k1, v1 = kc0.clone(), vc0.clone()
-        o1 = torch.zeros(B, HD, dtype=bf, device='cuda')
+        # the exact-FMA kernel of the fp32 parity mode on fp32 copies of the same operands (its bf16 instantiation left the library in round 2)
+        k1, v1 = kc0.float(), vc0.float()
+        o1 = torch.zeros(B, HD, dtype=torch.float32, device='cuda')
         o2 = torch.zeros(B, HD, dtype=bf, device='cuda')
-        L_.check(lib.txl_decode_attn(qkv.data_ptr(), k1.data_ptr(), v1.data_ptr(), r.data_ptr(), rwb.data_ptr(), rrb.data_ptr(), o1.data_ptr(),
-                                     pos.data_ptr(), B, H, ML, dh, L_.BF16, st), 'decode_attn')
+        qkv32, r32 = qkv.float(), r.float()
+        L_.check(lib.txl_decode_attn(qkv32.data_ptr(), k1.data_ptr(), v1.data_ptr(), r32.data_ptr(), rwb.data_ptr(), rrb.data_ptr(), o1.data_ptr(),
+                                     pos.data_ptr(), B, H, ML, dh, L_.F32, st), 'decode_attn')
         splits = [1, 2, 3][p % 3]
         ws = torch.empty(max(1, lib.txl_decode_attn_pipe_ws_bytes(B, H, dh, splits)), dtype=torch.uint8, device='cuda')
         kv2 = torch.cat([kc0, vc0], dim=-1).contiguous()                                   # interleaved ring [B, H, ML, 2*dh]
@@ -470,7 +472,7 @@ def test_decode_attn_pipe_vs_first_generation(pkg, B, H, dh, ML):
         k2, v2 = kv2[..., :dh].contiguous(), kv2[..., dh:].contiguous()
         assert int(cnt.abs().sum().item()) == 0          # the merge counters are left zeroed for the next launch
         torch.cuda.synchronize()
-        assert torch.equal(k1, k2) and torch.equal(v1, v2)
+        assert torch.equal(k1, k2.float()) and torch.equal(v1, v2.float())
         assert torch.equal(k2[:, :, p % ML].reshape(B, HD), qkv[:, HD:2 * HD]) and torch.equal(v2[:, :, p % ML].reshape(B, HD), qkv[:, 2 * HD:])
         # exact fp32 softmax over the ring as the arbiter for both kernels
         q = qkv[:, :HD].float().view(B, H, dh)
