@@ -278,6 +278,26 @@ int txl_decode_tail(const float* logits, int64_t ldl, float* scores, int B, int 
                     void* stream);
 int txl_set_pdl(int on);
 
+/* Third-generation bf16 decode step (csrc/decode_persist.cu): embedding row in x -> all L layers -> LM-head GEMM as ONE persistent cooperative
+ * kernel (one CTA per SM, the stages of a layer separated by grid barriers) over a ring of cached HIDDEN states: ring[l] [B, mem_len, d] is
+ * HF's mems[l] (Appendix A.8'), slot pos % mem_len is overwritten with the layer input each step, and the per-head key / value projections
+ * are absorbed into the query / output side (AC = (W_k,h^T (q_h + r_w_bias_h)) . hid_s, out_h = W_v,h sum_s p hid_s), so a cached token costs
+ * d*2 bytes per layer instead of the 2*d*2 of a projected k|v cache; BD comes from one [B, H, mem_len+1] table per layer.  Replaces the T=1
+ * forward of HF `sample` / `greedy_search` (A.3-A.6, A.7).  Geometry: B <= 64, d_head 64, d_model 128 or 512, H <= 8, d_inner <= 512 or a
+ * multiple of 512 (txl_decode_persist_supported).  Per-layer pointers arrive as host arrays of L device pointers: wqkv (qkv_net.weight),
+ * wkT ([H, d, 64]: wkT[h, c, e] = W_k[h*64+e, c]), wo, w1, w2, rtab ([mem_len+1, d] = r_net(pos_emb), row x <-> distance mem_len - x), biases
+ * and LayerNorm vectors (fp32), ring.  Call once with build_table = 1 (uploads the table into ws, zeroes the barrier counter, synchronises
+ * the stream), then once per token with build_table = 0: x [B, d] bf16 holds E[token]*sqrt(d) on entry and the final hidden state on exit,
+ * logits [B, ldl] fp32 = x [E ; cluster_weight]^T + bias (Vx columns).  *pos must advance by one between steps (txl_decode_tail does). */
+int txl_decode_persist_supported(int B, int H, int dh, int d, int di, int mem_len, int L, int Vx);
+int64_t txl_decode_persist_ws_bytes(int B, int H, int dh, int d, int di, int mem_len, int L, int Vx);
+int txl_decode_persist_step(const void* const* wqkv, const void* const* wkT, const void* const* wo, const void* const* w1, const void* const* w2,
+                            const void* const* rtab, const float* const* b1, const float* const* b2, const float* const* rwb,
+                            const float* const* rrb, const float* const* ln1w, const float* const* ln1b, const float* const* ln2w,
+                            const float* const* ln2b, void* const* ring, const void* E, const float* out_bias, void* x, const int32_t* pos,
+                            float* logits, int64_t ldl, void* ws, int build_table, int B, int H, int dh, int d, int di, int mem_len, int L, int Vx,
+                            float eps, void* stream);
+
 /* ---- mems ring / layout helpers  [A.8' _update_mems] ----------------------------------------------
  * time-major (L?,rows,B,d) <-> batch-major copies used at the Python boundary */
 int txl_tm_to_bm(const void* src, void* dst, int rows, int B, int d, int dtype_src, int dtype_dst, void* stream);

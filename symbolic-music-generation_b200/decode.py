@@ -4,7 +4,11 @@ kernel, the whole step replayed as a CUDA graph (no host round trip between toke
 Follows HF 4.25 `sample` / `greedy_search` step for step: embed last token -> L x (qkv, relative-position attention
 over [mems ; current] with the same_length band, o_net + LN, FF + LN) -> log-softmax -> warpers -> draw -> eos/pad bookkeeping -> append.
 
-Two generations of kernels share this file:
+Three engines share this file:
+  * bf16, persistent (the default where its geometry applies: d_head 64, d_model 128 / 512, at most 64 sequences per chain): ONE cooperative
+    kernel per step for all layers + the LM-head GEMM (`txl_decode_persist_step`, csrc/decode_persist.cu) over a ring of cached HIDDEN
+    states - HF's `mems` themselves, half the bytes of a projected k|v cache - with the key / value projections absorbed into the query /
+    output side; grid barriers instead of 84 kernel boundaries.  Then `txl_decode_tail`.  `TXL_DECODE_PERSIST=0` selects the next one.
   * bf16 (the measured path): `txl_dec_linear` / `txl_dec_add_ln` / `txl_decode_attn_pipe` / `txl_decode_tail` (csrc/decode_stream.cu,
     csrc/sample.cu) over an interleaved k|v ring, launched with programmatic stream serialization; `GroupedDecoder` captures groups of 16
     sequences as parallel branches of one graph.  74 launches per step and group.
@@ -40,6 +44,18 @@ _ATTN_SPLITS = int(os.environ.get('TXL_DECODE_ATTN_SPLITS', '0'))   # 0 = automa
 _PREFETCH_MB = float(os.environ.get('TXL_DECODE_PREFETCH_MB', '0'))
 _SPLIT_COLS = int(os.environ.get('TXL_DEC_SPLIT_COLS', '1000000'))   # A/B switch: 512 makes every Linear fit two ring stages (see TXL_DEC_LINEAR_2STAGE)
 _ABL = int(os.environ.get('TXL_DECODE_ABL', '0'))       # timing ablations (results are garbage): 1 = no attention launch, 2 = no Linear / LayerNorm launches
+
+
+_PERSIST = os.environ.get('TXL_DECODE_PERSIST', '1') != '0'
+
+
+def persist_supported(model, B):
+    """The persistent one-kernel step (csrc/decode_persist.cu) takes this model and `B` sequences per chain."""
+    cfg = model.config
+    if not _PERSIST or model._E.dtype != torch.bfloat16 or not cfg.same_length or cfg.mem_len <= 0:
+        return False
+    Vx = cfg.vocab_size + len(getattr(cfg, 'cutoffs', []) or [])
+    return bool(load().txl_decode_persist_supported(int(B), cfg.n_head, cfg.d_head, cfg.d_model, cfg.d_inner, cfg.mem_len, cfg.n_layer, Vx))
 
 
 def _dec_linear_ok(A, W):
@@ -99,6 +115,9 @@ def sequence_groups(model, B, requested=None):
     if requested is None:
         requested = int(os.environ.get('TXL_DECODE_GROUPS', '0')) or None
     need = (B + SK_MAXM - 1) // SK_MAXM              # a Decoder (one chain of kernels) takes at most SK_MAXM sequences
+    if hasattr(model, '_W') and persist_supported(model, (B + need - 1) // need):
+        # the persistent step occupies every SM: sequence groups would only serialise, so as few chains as the 64-row limit allows
+        return max(need, min(int(requested), B)) if requested is not None else need
     if model._E.dtype != torch.bfloat16 or os.environ.get('TXL_DECODE_TAIL', '1') == '0' or model.config.vocab_size > 8192 or getattr(model.config, 'cutoffs', None):
         return need
     if requested is not None:
@@ -114,7 +133,7 @@ class Decoder:
     """Device-resident generation state for `B` sequences.  Built from the mems the prompt forward returned."""
 
     def __init__(self, model, mems, out_ids, col0, *, do_sample, temperature, top_k, top_p, eos_token_id, pad_token_id, seed=0, seq_offset=0,
-                 use_graph=True, attn_splits=None):
+                 use_graph=True, attn_splits=None, persist=True):
         cfg = model.config
         self.model, self.cfg = model, cfg
         bm = mems._bm if hasattr(mems, '_bm') else model._mems_to_bm(mems, out_ids.shape[0])
@@ -130,7 +149,14 @@ class Decoder:
         pos_tab = ops.posemb_table(ML + 1, cfg.clamp_len, d, dt, dev)
         self.kc, self.vc, self.kvc, self.r, self.r_hm = [], [], [], [], []
         self.pipe_attn = dt == torch.bfloat16
-        for li, w in enumerate(model._W):
+        self.persist = persist and persist_supported(model, B)
+        if self.persist:
+            # the cache IS the hidden-state mems (chronological rows: slot 0 = oldest = the first one to be overwritten); private copies,
+            # the step writes into them.  K projection transposed per head once: wkT[h, c, e] = W_k[h*64 + e, c].
+            self.ring = [t.contiguous().clone() for t in bm]
+            self.wkT = [w.qkv[d:2 * d].view(H, dh, d).transpose(1, 2).contiguous() for w in model._W]
+            self.r = [ops.gemm(pos_tab, w.r, transB=True) for w in model._W]                          # (ML+1, d): row x <-> distance ML - x
+        for li, w in enumerate(model._W if not self.persist else []):
             kv = ops.gemm(bm[li].reshape(B * ML, d).contiguous(), w.qkv[d:], transB=True)          # (B*ML, 2d)
             if self.pipe_attn:
                 kvc = torch.empty(B, H, ML, 2 * dh, dtype=dt, device=dev)      # a key's k row then its v row: one contiguous run per stage of keys
@@ -179,15 +205,49 @@ class Decoder:
         self.Vx = self.V + len(cfg.cutoffs)                # LM-head columns: token logits + one per adaptive-softmax cluster
         self.Vp = (self.Vx + 7) // 8 * 8
         self.logits = torch.zeros(B, self.Vp, dtype=torch.float32 if dt == torch.bfloat16 else dt, device=dev)
+        if self.persist:
+            self._build_persist()
         self.scores = torch.zeros(B, cfg.vocab_size, dtype=torch.float32, device=dev) if self.gen2_tail else None      # log-probs of the last step
         self.graph = None
         self.use_graph = use_graph
         self.steps_done = 0
 
+    def _build_persist(self):
+        """Per-layer pointer tables + workspace of the persistent step kernel; uploads the table (one synchronising call)."""
+        m, cfg, lib = self.model, self.cfg, load()
+        L = cfg.n_layer
+
+        def arr(ts):
+            return (C.c_void_p * L)(*[t.data_ptr() for t in ts])
+        W = m._W
+        self._persist_keep = [[w.qkv for w in W], self.wkT, [w.o for w in W], [w.w1 for w in W], [w.w2 for w in W], self.r, [w.b1 for w in W],
+                              [w.b2 for w in W], [w.rwb for w in W], [w.rrb for w in W], [w.ln1_w for w in W], [w.ln1_b for w in W],
+                              [w.ln2_w for w in W], [w.ln2_b for w in W], self.ring]
+        self._persist_arrays = [arr(ts) for ts in self._persist_keep]
+        nbytes = lib.txl_decode_persist_ws_bytes(self.B, cfg.n_head, cfg.d_head, self.d, cfg.d_inner, self.ML, L, self.Vx)
+        self._persist_ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.dev)
+        off = (-self._persist_ws.data_ptr()) % 256
+        self._persist_ws_ptr = self._persist_ws.data_ptr() + off
+        if self.x0 is None:
+            self.x0 = torch.empty(self.B, self.d, dtype=self.dt, device=self.dev)
+        self._persist_call(1)
+
+    def _persist_call(self, build):
+        cfg = self.cfg
+        check(load().txl_decode_persist_step(*self._persist_arrays, ptr(self.model._E_ext), ptr(self.model._out_bias_ext), ptr(self.x0), ptr(self.pos),
+                                             ptr(self.logits), self.logits.stride(0), self._persist_ws_ptr, int(build), self.B, cfg.n_head, cfg.d_head,
+                                             self.d, cfg.d_inner, self.ML, cfg.n_layer, self.Vx, float(cfg.layer_norm_epsilon), stream_ptr()),
+              'decode_persist_step')
+
     # one decode step: every line is a kernel launch on the current stream
     def _step_kernels(self):
         m, cfg, lib = self.model, self.cfg, load()
         B, d, H, dh, ML = self.B, self.d, cfg.n_head, cfg.d_head, self.ML
+        if self.persist:
+            if not self.gen2_tail:                     # (adaptive-softmax / large vocabularies: the embedding is a separate launch)
+                self.x0.copy_(ops.embed_fwd(self.tok, m._E, math.sqrt(d)))
+            self._persist_call(0)
+            return self._finish_step(self.logits)
         pdl_old = lib.txl_set_pdl(1) if (self.pipe_attn and _PDL) else None
         cfg_old = lib.txl_decode_attn_pipe_config(self.attn_cfg) if (self.pipe_attn and self.attn_cfg is not None) else None
         try:
