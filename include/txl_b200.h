@@ -289,6 +289,8 @@ int txl_set_pdl(int on);
  * and LayerNorm vectors (fp32), ring.  Call once with build_table = 1 (uploads the table into ws, zeroes the barrier counter, synchronises
  * the stream), then once per token with build_table = 0: x [B, d] bf16 holds E[token]*sqrt(d) on entry and the final hidden state on exit,
  * logits [B, ldl] fp32 = x [E ; cluster_weight]^T + bias (Vx columns).  *pos must advance by one between steps (txl_decode_tail does). */
+/* profiling hook: device buffer (>= 7 L + 2 uint64) receiving CTA 0's %globaltimer at the start of a step and after every grid barrier; NULL disables */
+int txl_decode_persist_set_timestamps(unsigned long long* dev_buf);
 int txl_decode_persist_supported(int B, int H, int dh, int d, int di, int mem_len, int L, int Vx);
 int64_t txl_decode_persist_ws_bytes(int B, int H, int dh, int d, int di, int mem_len, int L, int Vx);
 int txl_decode_persist_step(const void* const* wqkv, const void* const* wkT, const void* const* wo, const void* const* w1, const void* const* w2,

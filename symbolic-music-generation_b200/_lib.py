@@ -84,6 +84,7 @@ SIGNATURES = {
     'txl_decode_attn_pipe_ws_bytes': (_i64, [_i, _i, _i, _i]),
     'txl_decode_cache_init_kv': (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _vp]),
     'txl_decode_attn_pipe': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'txl_decode_persist_set_timestamps': (_i, [_vp]),
     'txl_decode_persist_supported': (_i, [_i] * 8),
     'txl_decode_persist_ws_bytes': (_i64, [_i] * 8),
     'txl_decode_persist_step': (_i, [_vp] * 15 + [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i] + [_i] * 8 + [_f, _vp]),

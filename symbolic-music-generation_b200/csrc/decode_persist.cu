@@ -46,6 +46,7 @@ struct DpLayer {
 
 struct DpArgs {
   const DpLayer* layers;
+  const CUtensorMap* tmaps;   // per layer: the ring as a [B*ML, d] bf16 tensor, box 64 rows x 64 columns, SWIZZLE_128B
   const bf16* E;              // [Vx, d]  (token rows, then adaptive-softmax cluster rows)
   const float* out_bias;      // [Vx]
   bf16* x;                    // [B, d]   layer input / output (in: embedding of the current token)
@@ -59,6 +60,7 @@ struct DpArgs {
   float* logits;              // [B, ldl]
   unsigned long long* bar;    // grid barrier counter (monotonic)
   const int32_t* pos;
+  unsigned long long* tstamp;   // profiling only: %globaltimer of CTA 0 at the step's start and after every grid barrier (NULL: off)
   int64_t ldl;
   int B, H, d, di, ML, MLP, L, Vx, S, per, KW, KSL;   // per = keys per split; KW = K-slice width of FF2, KSL = number of slices
   float eps, scale_log2;
@@ -95,9 +97,9 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 __device__ __forceinline__ void cbar() { __syncthreads(); }
 
 // Grid barrier number `k` (0-based, counted over the whole generation): every CTA adds 1, all wait for (k+1)*G.  Writes made before it by
-// any CTA are visible after it to L1-bypassing loads and (after the proxy fence) to bulk copies.
+// any CTA are visible after it to L1-bypassing loads.  (Data handed to the async proxy - ring rows read by TMA - is fenced where it is
+// written and where the copies are issued, not here: fence.proxy.async on every barrier is not free.)
 __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long k) {
-  fence_proxy_async_all();
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -110,10 +112,8 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
       if (v >= target) break;
       if (clock64() - t0 > 6000000000ll) __trap();       // ~3 s: a protocol bug becomes a CUDA error, not a hung GPU
     }
-    __threadfence();
   }
   __syncthreads();
-  fence_proxy_async_all();
 }
 
 // rows [0, nrows) x cols [0, ncols) of a bf16 matrix (row pitch ld elements) -> shared memory with row pitch `pitch` bytes, 16-byte cp.async
@@ -165,52 +165,97 @@ struct Smem {
 // item = (head h, chunk c).  GEMM1: t_h [B, 64] = A1 [B, d] W1[h*64.., d]^T (+ bias1) -> bf16 (shared memory) ; GEMM2: out [B, N2] = t_h W2c^T.
 // KIND 0 = QT (A1 = x, W1 = W_q, bias rwb, W2c = W_kT[h][c*64.., 64], out -> qt bf16), KIND 1 = BD (bias rrb, W2c = r[c*128.., h*64..], out -> bd),
 // KIND 2 = VAON (A1 = merged context of head h, W1 = W_v, W2c = W_o[c*64.., h*64..], out -> planes[h]).
+// the weight slices of a chained item (they do not depend on other CTAs: issued BEFORE the grid barrier that precedes the stage)
+template <int KIND>
+__device__ __forceinline__ void chain_weights(const DpArgs& a, const DpLayer& ly, const Smem& sm, int h, int c) {
+  constexpr int P2 = DP_DH * 2 + 64;
+  const int tid = threadIdx.x, d = a.d;
+  const bf16* w1 = (KIND == 2 ? ly.wv : ly.wq) + (int64_t)h * DP_DH * d;
+  load_tile(sm.W, sm.pitchA, w1, d, DP_DH, DP_DH, d, tid, DP_THREADS);
+  if (KIND == 0) load_tile(sm.W2, P2, ly.wkT + ((int64_t)h * d + c * 64) * DP_DH, DP_DH, 64, 64, DP_DH, tid, DP_THREADS);
+  if (KIND == 1) load_tile(sm.W2, P2, ly.r + (int64_t)c * 128 * d + h * DP_DH, d, 128, a.ML + 1 - c * 128, DP_DH, tid, DP_THREADS);
+  if (KIND == 2) load_tile(sm.W2, P2, ly.wo + (int64_t)c * 64 * d + h * DP_DH, d, 64, 64, DP_DH, tid, DP_THREADS);
+  cpa_commit();
+}
+
 template <int MT, int KIND>
-__device__ void chain_item(const DpArgs& a, const DpLayer& ly, const Smem& sm, int h, int c) {
+__device__ void chain_item(const DpArgs& a, const DpLayer& ly, const Smem& sm, int h, int c, bool w_ready) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int d = a.d, B = a.B, H = a.H;
   constexpr int P2 = DP_DH * 2 + 64;              // pitch of the K = 64 operands
   constexpr int N2 = KIND == 1 ? 128 : 64, NTW2 = N2 / 64;
+  // every global load of the item is issued up front (a dependent L2 round trip costs ~0.8 us here)
+  float bias0 = 0.f, bias1 = 0.f;
+  if (KIND != 2) {
+    const float* bias = KIND == 0 ? ly.rwb : ly.rrb;
+    bias0 = bias[h * DP_DH + warp * 8 + 2 * t]; bias1 = bias[h * DP_DH + warp * 8 + 2 * t + 1];
+  }
   if (tid < DP_CWARPS * 32) {
-    // ---- operand loads (all cp.async, one group)
+    if (!w_ready) chain_weights<KIND>(a, ly, sm, h, c);
     if (KIND == 2) {
-      // A1 = merge of the ring splits of head h:  ctx = sum_z coef_z pctx[b, z, h, :],  coef_z = exp2(m_z - M) l_z / sum(...)
-      for (int b = warp; b < MT * 16; b += DP_CWARPS) {
+      // A1 = merge of the ring splits of head h:  ctx = sum_z coef_z pctx[b, z, h, :],  coef_z = exp2(m_z - M) l_z / sum(...).
+      // Dependent L2 round trips are what this costs, so: (1) one row per thread builds the coefficients with all its (m, l) loads in flight,
+      // (2) the vectors are merged 4 at a time with the loads of up to 4 splits each in flight.
+      float* coef = sm.red;                             // [MT*16][DP_MAXS]
+      for (int b = tid; b < MT * 16; b += DP_THREADS) {
         const int bb = min(b, B - 1);
-        float coef[DP_MAXS];
+        float2 ml[DP_MAXS];
+#pragma unroll
+        for (int z = 0; z < DP_MAXS; ++z)
+          ml[z] = z < a.S ? __ldcg(reinterpret_cast<const float2*>(a.pml + (((int64_t)bb * a.S + z) * H + h) * 2)) : make_float2(-INFINITY, 0.f);
         float M = -INFINITY;
-        for (int z = 0; z < a.S; ++z) M = fmaxf(M, __ldcg(a.pml + (((int64_t)bb * a.S + z) * H + h) * 2));
-        float Lsum = 0.f;
-        for (int z = 0; z < a.S; ++z) {
-          const float mz = __ldcg(a.pml + (((int64_t)bb * a.S + z) * H + h) * 2), lz = __ldcg(a.pml + (((int64_t)bb * a.S + z) * H + h) * 2 + 1);
-          coef[z] = (mz == -INFINITY) ? 0.f : exp2f(mz - M) * lz;
-          Lsum += coef[z];
-        }
+#pragma unroll
+        for (int z = 0; z < DP_MAXS; ++z) M = fmaxf(M, ml[z].x);
+        float cz[DP_MAXS], Lsum = 0.f;
+#pragma unroll
+        for (int z = 0; z < DP_MAXS; ++z) { cz[z] = (ml[z].x == -INFINITY) ? 0.f : exp2f(ml[z].x - M) * ml[z].y; Lsum += cz[z]; }
         const float inv = Lsum > 0.f ? 1.f / Lsum : 0.f;
-        for (int c0 = lane * 8; c0 < d; c0 += 256) {
-          float acc8[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc8[k] = 0.f;
-          for (int z = 0; z < a.S; ++z) {
-            const uint4 u = __ldcg(reinterpret_cast<const uint4*>(a.pctx + (((int64_t)bb * a.S + z) * H + h) * d + c0));
-            const bf16* e = reinterpret_cast<const bf16*>(&u);
-            const float cz = coef[z] * inv;
+        for (int z = 0; z < DP_MAXS; ++z) coef[b * DP_MAXS + z] = cz[z] * inv;
+      }
+      __syncthreads();
+      const int vpr = d / 8, nvec = MT * 16 * vpr;
+      for (int v0 = tid; v0 < nvec; v0 += 4 * DP_THREADS) {
+        float acc8[4][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc8[k] = fmaf(cz, __bfloat162float(e[k]), acc8[k]);
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc8[q][k] = 0.f;
+        for (int z0 = 0; z0 < a.S; z0 += 4) {
+          uint4 u[4][4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int v = v0 + q * DP_THREADS, b = min(v / vpr, MT * 16 - 1), bb = min(b, B - 1), c0 = (v % vpr) * 8;
+#pragma unroll
+            for (int zz = 0; zz < 4; ++zz)
+              u[q][zz] = (v < nvec && z0 + zz < a.S) ? __ldcg(reinterpret_cast<const uint4*>(a.pctx + (((int64_t)bb * a.S + z0 + zz) * H + h) * d + c0))
+                                                    : make_uint4(0, 0, 0, 0);
           }
-          uint4 o;
-          o.x = pack2(acc8[0], acc8[1]); o.y = pack2(acc8[2], acc8[3]); o.z = pack2(acc8[4], acc8[5]); o.w = pack2(acc8[6], acc8[7]);
-          *reinterpret_cast<uint4*>(sm.A + (size_t)b * sm.pitchA + c0 * 2) = o;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int v = v0 + q * DP_THREADS, b = min(v / vpr, MT * 16 - 1);
+#pragma unroll
+            for (int zz = 0; zz < 4; ++zz) {
+              const float cf = z0 + zz < a.S ? coef[b * DP_MAXS + z0 + zz] : 0.f;
+              const bf16* e = reinterpret_cast<const bf16*>(&u[q][zz]);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc8[q][k] = fmaf(cf, __bfloat162float(e[k]), acc8[q][k]);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int v = v0 + q * DP_THREADS;
+          if (v < nvec) {
+            uint4 o;
+            o.x = pack2(acc8[q][0], acc8[q][1]); o.y = pack2(acc8[q][2], acc8[q][3]); o.z = pack2(acc8[q][4], acc8[q][5]); o.w = pack2(acc8[q][6], acc8[q][7]);
+            *reinterpret_cast<uint4*>(sm.A + (size_t)(v / vpr) * sm.pitchA + (v % vpr) * 16) = o;
+          }
         }
       }
     } else {
       load_tile(sm.A, sm.pitchA, a.x, d, MT * 16, B, d, tid, DP_CWARPS * 32);
     }
-    const bf16* w1 = (KIND == 2 ? ly.wv : ly.wq) + (int64_t)h * DP_DH * d;
-    load_tile(sm.W, sm.pitchA, w1, d, DP_DH, DP_DH, d, tid, DP_CWARPS * 32);
-    if (KIND == 0) load_tile(sm.W2, P2, ly.wkT + ((int64_t)h * d + c * 64) * DP_DH, DP_DH, 64, 64, DP_DH, tid, DP_CWARPS * 32);
-    if (KIND == 1) load_tile(sm.W2, P2, ly.r + (int64_t)c * 128 * d + h * DP_DH, d, 128, a.ML + 1 - c * 128, DP_DH, tid, DP_CWARPS * 32);
-    if (KIND == 2) load_tile(sm.W2, P2, ly.wo + (int64_t)c * 64 * d + h * DP_DH, d, 64, 64, DP_DH, tid, DP_CWARPS * 32);
     cpa_commit();
     cpa_wait_all();
   }
@@ -224,11 +269,7 @@ __device__ void chain_item(const DpArgs& a, const DpLayer& ly, const Smem& sm, i
       for (int q = 0; q < 4; ++q) acc[i][0][q] = 0.f;
     gemm_nsplit<MT, 1>(acc, sm.A, sm.pitchA, sm.W, sm.pitchA, d, warp, lane);
     const int n = warp * 8 + 2 * t;
-    float b0 = 0.f, b1 = 0.f;
-    if (KIND != 2) {
-      const float* bias = KIND == 0 ? ly.rwb : ly.rrb;
-      b0 = bias[h * DP_DH + n]; b1 = bias[h * DP_DH + n + 1];
-    }
+    const float b0 = bias0, b1 = bias1;
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
       *reinterpret_cast<uint32_t*>(sm.A2 + (size_t)(i * 16 + g) * P2 + n * 2) = pack2(acc[i][0][0] + b0, acc[i][0][1] + b1);
@@ -274,18 +315,23 @@ __device__ void chain_item(const DpArgs& a, const DpLayer& ly, const Smem& sm, i
 // ------------------------------------------------------------------------------------------------------------------------------ linear stage
 // out[B, 16] = A[B, K] (row pitch lda, columns [k0, k0+K)) W[n0.., k0..]^T: the 8 warps split K in 32-wide blocks (warp w takes block w of every
 // 256-column chunk) and meet in shared memory.  MODE 0: + bias, ReLU, bf16 -> h1 ; MODE 1: fp32 plane ; MODE 2: + bias, fp32 -> logits
+__device__ __forceinline__ void lin_weights(const Smem& sm, const bf16* W, int64_t ldw, int N, int K, int n0, int k0) {
+  load_tile(sm.W, K * 2 + 64, W + (int64_t)n0 * ldw + k0, ldw, 16, N - n0, K, threadIdx.x, DP_THREADS);
+  cpa_commit();
+}
+
 template <int MT, int MODE>
 __device__ void lin_item(const DpArgs& a, const Smem& sm, const bf16* A, int64_t lda, const bf16* W, int64_t ldw, const float* bias, int N, int K, int n0,
-                         int k0, void* out, int64_t ldo) {
+                         int k0, void* out, int64_t ldo, bool w_ready) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int B = a.B;
   const int pitch = K * 2 + 64;
-  if (tid < DP_CWARPS * 32) {
-    load_tile(sm.A, pitch, A + k0, lda, MT * 16, B, K, tid, DP_CWARPS * 32);
-    load_tile(sm.W, pitch, W + (int64_t)n0 * ldw + k0, ldw, 16, N - n0, K, tid, DP_CWARPS * 32);
-    cpa_commit();
-    cpa_wait_all();
-  }
+  // epilogue bias of this thread's output column (e = tid + 256 i: column tid & 15 for every i), loaded before anything else
+  const float bias_e = (MODE != 1 && n0 + (tid & 15) < N) ? bias[n0 + (tid & 15)] : 0.f;
+  if (!w_ready) lin_weights(sm, W, ldw, N, K, n0, k0);
+  load_tile(sm.A, pitch, A + k0, lda, MT * 16, B, K, tid, DP_THREADS);
+  cpa_commit();
+  cpa_wait_all();
   __syncthreads();
   float (*red)[MT * 16][17] = reinterpret_cast<float (*)[MT * 16][17]>(sm.red);
   if (tid < DP_CWARPS * 32) {
@@ -332,12 +378,12 @@ __device__ void lin_item(const DpArgs& a, const Smem& sm, const bf16* A, int64_t
 #pragma unroll
       for (int w = 0; w < DP_CWARPS; ++w) v += red[w][m][nl];
       if (MODE == 0) {
-        v = fmaxf(v + bias[n], 0.f);
+        v = fmaxf(v + bias_e, 0.f);
         reinterpret_cast<bf16*>(out)[(int64_t)m * ldo + n] = __float2bfloat16_rn(v);
       } else if (MODE == 1) {
         reinterpret_cast<float*>(out)[(int64_t)m * ldo + n] = v;
       } else {
-        reinterpret_cast<float*>(out)[(int64_t)m * ldo + n] = v + bias[n];
+        reinterpret_cast<float*>(out)[(int64_t)m * ldo + n] = v + bias_e;
       }
     }
   }
@@ -345,92 +391,118 @@ __device__ void lin_item(const DpArgs& a, const Smem& sm, const bf16* A, int64_t
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------ LayerNorm rows
-// y[b] = LayerNorm(res[b] + sum_p planes[p][b] (+ bias)) * gamma + beta ; one warp per row, fp32 statistics (two-pass variance).  Optionally
-// also stored to `ring_row(b)` (the next layer's cache slot of this step).
+// y[b] = LayerNorm(res[b] + sum_p planes[p][b] (+ bias)) * gamma + beta, fp32 statistics (two-pass variance).  One 8-column vector per thread
+// (D/8 threads per row, 2048/D rows per CTA) so that EVERY load of the stage - residual, up to 8 planes, bias, gamma, beta - is in flight
+// at once: one L2 round trip instead of five.  Optionally also stored to the next layer's ring slot of this step (then fenced for the TMA).
+template <int D>
 __device__ void ln_rows(const DpArgs& a, const bf16* res, int nplanes, const float* bias, const float* gamma, const float* beta, bf16* y, bf16* ring,
-                        int cur) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int d = a.d, B = a.B;
-  for (int b = blockIdx.x * DP_CWARPS + warp; b < B; b += gridDim.x * DP_CWARPS) {
-    float v[4][8];      // d <= 1024: lane owns columns 8 (32 e + lane) ..
-    float s = 0.f;
+                        int cur, float* lnred) {
+  constexpr int LPR = D / 8;                        // threads per row
+  constexpr int RPC = DP_THREADS / LPR;             // rows per CTA and pass
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int B = a.B;
+  const int rl = tid / LPR, c = (tid % LPR) * 8;
+  for (int b0 = blockIdx.x * RPC; b0 < B; b0 += gridDim.x * RPC) {          // (uniform per CTA: the barriers below are safe)
+    const int b = b0 + rl;
+    const bool on = b < B;
+    const int bb = on ? b : B - 1;
+    const uint4 u = __ldcg(reinterpret_cast<const uint4*>(res + (int64_t)bb * D + c));
+    float4 pl[8][2];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = (e * 32 + lane) * 8;
-      if (c < d) {
-        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(res + (int64_t)b * d + c));
-        const bf16* eb = reinterpret_cast<const bf16*>(&u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[e][k] = __bfloat162float(eb[k]);
-        for (int p = 0; p < nplanes; ++p) {
-          const float4 p0 = __ldcg(reinterpret_cast<const float4*>(a.planes + ((int64_t)p * B + b) * d + c));
-          const float4 p1 = __ldcg(reinterpret_cast<const float4*>(a.planes + ((int64_t)p * B + b) * d + c + 4));
-          v[e][0] += p0.x; v[e][1] += p0.y; v[e][2] += p0.z; v[e][3] += p0.w; v[e][4] += p1.x; v[e][5] += p1.y; v[e][6] += p1.z; v[e][7] += p1.w;
-        }
-        if (bias) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[e][k] += bias[c + k];
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s += v[e][k];
-      }
+    for (int p = 0; p < 8; ++p) {
+      pl[p][0] = p < nplanes ? __ldcg(reinterpret_cast<const float4*>(a.planes + ((int64_t)p * B + bb) * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      pl[p][1] = p < nplanes ? __ldcg(reinterpret_cast<const float4*>(a.planes + ((int64_t)p * B + bb) * D + c + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float mu = warp_sum(s) / d;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 e0 = *reinterpret_cast<const float4*>(beta + c), e1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    if (bias) { s0 = *reinterpret_cast<const float4*>(bias + c); s1 = *reinterpret_cast<const float4*>(bias + c + 4); }
+    float v[8];
+    {
+      const bf16* eb = reinterpret_cast<const bf16*>(&u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __bfloat162float(eb[k]);
+    }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      v[0] += pl[p][0].x; v[1] += pl[p][0].y; v[2] += pl[p][0].z; v[3] += pl[p][0].w;
+      v[4] += pl[p][1].x; v[5] += pl[p][1].y; v[6] += pl[p][1].z; v[7] += pl[p][1].w;
+    }
+    v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+    // row sums over the LPR threads of the row: inside a warp by shuffles; rows wider than a warp meet in shared memory
+    auto rowsum = [&](float x) {
+      if (LPR >= 32) {
+        x = warp_sum(x);
+        if (LPR > 32) {
+          constexpr int WPR = LPR / 32 > 0 ? LPR / 32 : 1;
+          __syncthreads();
+          if (lane == 0) lnred[warp] = x;
+          __syncthreads();
+          float tt = 0.f;
+#pragma unroll
+          for (int w = 0; w < WPR; ++w) tt += lnred[(warp / WPR) * WPR + w];
+          x = tt;
+        }
+      } else {
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      }
+      return x;
+    };
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += v[k];
+    const float mu = rowsum(sum) / D;
     float q = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if ((e * 32 + lane) * 8 < d) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { const float tt = v[e][k] - mu; q += tt * tt; }
-      }
-    const float rs = rsqrtf(warp_sum(q) / d + a.eps);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = (e * 32 + lane) * 8;
-      if (c < d) {
-        uint4 o;
-        o.x = pack2((v[e][0] - mu) * rs * gamma[c] + beta[c], (v[e][1] - mu) * rs * gamma[c + 1] + beta[c + 1]);
-        o.y = pack2((v[e][2] - mu) * rs * gamma[c + 2] + beta[c + 2], (v[e][3] - mu) * rs * gamma[c + 3] + beta[c + 3]);
-        o.z = pack2((v[e][4] - mu) * rs * gamma[c + 4] + beta[c + 4], (v[e][5] - mu) * rs * gamma[c + 5] + beta[c + 5]);
-        o.w = pack2((v[e][6] - mu) * rs * gamma[c + 6] + beta[c + 6], (v[e][7] - mu) * rs * gamma[c + 7] + beta[c + 7]);
-        *reinterpret_cast<uint4*>(y + (int64_t)b * d + c) = o;
-        if (ring) *reinterpret_cast<uint4*>(ring + ((int64_t)b * a.ML + cur) * d + c) = o;
-      }
+    for (int k = 0; k < 8; ++k) { const float tt = v[k] - mu; q += tt * tt; }
+    const float rs = rsqrtf(rowsum(q) / D + a.eps);
+    if (on) {
+      uint4 o;
+      o.x = pack2((v[0] - mu) * rs * g0.x + e0.x, (v[1] - mu) * rs * g0.y + e0.y);
+      o.y = pack2((v[2] - mu) * rs * g0.z + e0.z, (v[3] - mu) * rs * g0.w + e0.w);
+      o.z = pack2((v[4] - mu) * rs * g1.x + e1.x, (v[5] - mu) * rs * g1.y + e1.y);
+      o.w = pack2((v[6] - mu) * rs * g1.z + e1.z, (v[7] - mu) * rs * g1.w + e1.w);
+      *reinterpret_cast<uint4*>(y + (int64_t)b * D + c) = o;
+      if (ring) *reinterpret_cast<uint4*>(ring + ((int64_t)b * a.ML + cur) * D + c) = o;
     }
   }
+  if (ring) fence_proxy_async_all();                  // the ring rows are read by TMA (async proxy) in the next layer's attention stage
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------ attention
-// D = d_model (compile time: the qt fragments of a warp live in registers).  item = (sequence b, split z): keys [z per, min((z+1) per, ML)).
+// D = d_model.  item = (sequence b, split z): keys [z per, min((z+1) per, ML)) in stages of 64.  A stage = D/64 TMA boxes of 64 rows x 128
+// bytes (SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)), 8 copies instead of one per row (per-row bulk copies stalled the
+// issuing warp for ~2000 cycles per stage).  Rows past the split belong to later positions (finite, they meet p = 0) or are zero-filled.
+// The MMAs run "transposed" so that no tile row is padding (mma.sync issues one HMMA per ~16 cycles and sub-partition: it is the bound):
+//   phase A  S^T[key, head] = hid[key, :] . qt[head, :]      M = 16 keys (ldmatrix), N = 8 heads, warp = (key tile, half of d)
+//   phase B  ctx^T[col, head] += hid[key, col] p[head, key]  M = 16 columns (ldmatrix.trans), N = 8 heads, K = keys, warp = D/8 columns
 template <int D>
-__device__ void att_item(const DpArgs& a, const DpLayer& ly, unsigned char* stage0, float* ssm, unsigned char* qsm, uint64_t* full, uint32_t& uses, int b,
-                         int z, int cur) {
-  constexpr int PITCH = D * 2 + 16;                 // 16 mod 128: the 8 rows of an ldmatrix tile fall into distinct 16-byte bank groups
+__device__ void att_item(const DpArgs& a, const CUtensorMap* tm, unsigned char* stage0, float* ssm, unsigned char* qsm, uint64_t* full, uint32_t& uses,
+                         int b, int z, int cur) {
+  constexpr int NB = D / 64;                        // 128-byte column blocks of a row
+  constexpr int STAGE = NB * 8192;
   constexpr int NKS = D / 16;                       // k16 steps of a score row
+  constexpr int KH = NKS / 2;                       //   ... per d-half
   constexpr int CW = D / DP_CWARPS;                 // context columns owned by a warp
-  constexpr int NTC = CW / 8;                       // n-tiles of those
+  constexpr int NMT = CW / 16;                      // m-tiles of those
+  constexpr int QPITCH = D * 2 + 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int H = a.H, ML = a.ML;
   const int s_begin = z * a.per, s_end = min(s_begin + a.per, ML);
   const int nst = (s_end - s_begin + DP_KS - 1) / DP_KS;
-  const bf16* ring = ly.ring + (int64_t)b * ML * D;
-  // warp 0 streams the ring: lane j copies rows j and j + 32 of a stage.  A stage buffer is refilled right after the consumer barrier that
-  // follows its last reader (see the loop), so no empty barriers are needed.
+  // one 8 KB box per warp (a thread that issued all eight spent ~800 cycles on it): the transaction count is armed by warp 0; a box that
+  // completes before that only drives the count negative - the phase cannot flip before the arming arrival
   auto issue = [&](int i) {
-    if (warp == 0 && i < nst) {
+    if (lane == 0 && i < nst) {
       const uint32_t u = uses + i, st = u % DP_NST;
-      const int s0 = s_begin + i * DP_KS, n = min(DP_KS, s_end - s0);
-      if (lane == 0) mbar_expect_tx(&full[st], (uint32_t)n * D * 2);
-      __syncwarp();
-      unsigned char* dst = stage0 + (size_t)st * DP_KS * PITCH;
-      for (int j = lane; j < n; j += 32) bulk_row(dst + (size_t)j * PITCH, ring + (int64_t)(s0 + j) * D, D * 2, &full[st]);
+      if (warp == 0) mbar_expect_tx(&full[st], STAGE);
+      for (int cb = warp; cb < NB; cb += DP_CWARPS) tma_load_2d(stage0 + (size_t)st * STAGE + cb * 8192, tm, &full[st], cb * 64, b * ML + s_begin + i * DP_KS);
     }
   };
 #pragma unroll
   for (int i = 0; i < DP_NST; ++i) issue(i);
-  // A operand of the scores: qt[b] (rows = heads, zero rows past H) staged in shared memory; a thread's fragment words are read per k16 step
-  // (64 fragment registers would not fit beside the context accumulators)
-  constexpr int QPITCH = D * 2 + 16;
+  // B operand of the scores: qt[b] (rows = heads, zero rows past H) staged in shared memory
   for (int e = tid; e < 8 * (D / 8); e += DP_THREADS) {
     const int hh = e / (D / 8), v = e % (D / 8);
     uint4 u = make_uint4(0, 0, 0, 0);
@@ -438,110 +510,150 @@ __device__ void att_item(const DpArgs& a, const DpLayer& ly, unsigned char* stag
     *reinterpret_cast<uint4*>(qsm + (size_t)hh * QPITCH + v * 16) = u;
   }
   __syncthreads();
+  const int mt = warp & 3, kh = warp >> 2;          // phase A: keys 16 mt .., k16 steps [kh KH, (kh+1) KH)
   const unsigned char* qrow = qsm + (size_t)g * QPITCH + t * 4;
-  float acc[NTC][4];
+  float acc[NMT][4];
 #pragma unroll
-  for (int j = 0; j < NTC; ++j)
+  for (int j = 0; j < NMT; ++j)
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-  const float* bdrow = a.bd + ((int64_t)b * H + min(g, H - 1)) * a.MLP;
+  float m_run = -INFINITY, l_run = 0.f;              // of head g (replicated over t and over the warps: same inputs, same operations)
+  long long pc[6] = {0, 0, 0, 0, 0, 0};              // profiling (a.tstamp set): cycles before the wait / in it / phase A / barrier / phase B
+  const bool prof = a.tstamp && blockIdx.x == 0 && tid == 0;
+  long long tprev = prof ? clock64() : 0;
+  auto lap = [&](int k) { if (prof) { const long long tn = clock64(); pc[k] += tn - tprev; tprev = tn; } };
+  const float* bd0 = a.bd + ((int64_t)b * H + min(2 * t, H - 1)) * a.MLP;
+  const float* bd1 = a.bd + ((int64_t)b * H + min(2 * t + 1, H - 1)) * a.MLP;
   for (int i = 0; i < nst; ++i) {
     const uint32_t u = uses + i, st = u % DP_NST;
     const int s0 = s_begin + i * DP_KS;
-    float* S = ssm + (size_t)(i & 1) * 8 * DP_SPITCH;
-    // position term of this thread's two keys (stage-local 8 warp + 2t, +1): r row x = ML - ((cur - s) mod ML)
-    const int sa = s0 + warp * 8 + 2 * t, sb = sa + 1;
-    float bda = 0.f, bdb = 0.f;
-    if (g < H) {
-      if (sa < s_end) bda = __ldcg(bdrow + (sa <= cur ? ML - cur + sa : sa - cur));
-      if (sb < s_end) bdb = __ldcg(bdrow + (sb <= cur ? ML - cur + sb : sb - cur));
+    float* S = ssm + (size_t)(i & 1) * 2 * 8 * DP_SPITCH;
+    // position term of this thread's keys (16 mt + g, + 8) and heads (2t, 2t+1): r row x = ML - ((cur - s) mod ML); added by the kh = 0 warps
+    float bdv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (kh == 0) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int sk = s0 + mt * 16 + g + hf * 8;
+        if (sk < s_end) {
+          const int x = sk <= cur ? ML - cur + sk : sk - cur;
+          if (2 * t < H) bdv[hf * 2] = __ldcg(bd0 + x);
+          if (2 * t + 1 < H) bdv[hf * 2 + 1] = __ldcg(bd1 + x);
+        }
+      }
     }
+    lap(0);
     mbar_wait(&full[st], (u / DP_NST) & 1);
-    const uint32_t sbase = smem_u32(stage0 + (size_t)st * DP_KS * PITCH);
+    lap(1);
+    const uint32_t sbase = smem_u32(stage0 + (size_t)st * STAGE);
     {
-      // a short last stage: rows past its keys still feed the P.hid MMAs (with p = 0), so they must be finite - zero them.  Every warp has
-      // finished the previous use of this buffer (the producer refilled it only after all eight arrived), the copies cover rows < n only.
-      const int n = min(DP_KS, s_end - s0);
-      if (n < DP_KS) {
-        unsigned char* rows = stage0 + (size_t)st * DP_KS * PITCH + (size_t)n * PITCH;
-        for (int e = tid; e < (DP_KS - n) * (PITCH / 16); e += DP_THREADS) reinterpret_cast<uint4*>(rows)[e] = make_uint4(0, 0, 0, 0);
+      // phase A
+      float c4[2][4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) { c4[q][0] = 0.f; c4[q][1] = 0.f; c4[q][2] = 0.f; c4[q][3] = 0.f; }
+      const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const uint32_t rbase = sbase + row * 128, rsw = row & 7, chi = lane >> 4;
+#pragma unroll
+      for (int k2 = 0; k2 < KH; k2 += 2) {            // two independent accumulator chains
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int ks = kh * KH + k2 + q;
+          uint32_t a0, a1, a2, a3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                       : "r"(rbase + (ks >> 2) * 8192 + (((((ks & 3) << 1) + chi) ^ rsw) << 4)));
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(qrow + ks * 32), b1 = *reinterpret_cast<const uint32_t*>(qrow + ks * 32 + 16);
+          mma16816(c4[q], a0, a1, a2, a3, b0, b1);
+        }
       }
+      // c: (key 16 mt + g, heads 2t, 2t+1), (key + 8, same heads)
+      float* Sh = S + (size_t)kh * 8 * DP_SPITCH + mt * 16 + g;
+      Sh[(2 * t) * DP_SPITCH] = c4[0][0] + c4[1][0] + bdv[0];
+      Sh[(2 * t + 1) * DP_SPITCH] = c4[0][1] + c4[1][1] + bdv[1];
+      Sh[(2 * t) * DP_SPITCH + 8] = c4[0][2] + c4[1][2] + bdv[2];
+      Sh[(2 * t + 1) * DP_SPITCH + 8] = c4[0][3] + c4[1][3] + bdv[3];
     }
-    {
-      // phase A: scores of keys 8 warp .. 8 warp + 7 over the whole d
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint32_t rowaddr = sbase + (uint32_t)(warp * 8 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 16;
-#pragma unroll 8
-      for (int ks = 0; ks < NKS; ++ks) {
-        uint32_t b0, b1;
-        ldsm_x2(b0, b1, rowaddr + ks * 32);
-        const uint32_t qa0 = *reinterpret_cast<const uint32_t*>(qrow + ks * 32), qa2 = *reinterpret_cast<const uint32_t*>(qrow + ks * 32 + 16);
-        mma16816(c, qa0, 0u, qa2, 0u, b0, b1);
-      }
-      const float v0 = sa < s_end ? (c[0] + bda) * a.scale_log2 : -INFINITY;
-      const float v1 = sb < s_end ? (c[1] + bdb) * a.scale_log2 : -INFINITY;
-      *reinterpret_cast<float2*>(S + g * DP_SPITCH + warp * 8 + 2 * t) = make_float2(v0, v1);
-    }
+    lap(2);
     cbar();
+    lap(3);
     // every warp is past phase A of this stage, hence done with the previous stage's buffer: refill it with stage i - 1 + NST
     if (i >= 1) issue(i - 1 + DP_NST);
     {
-      // phase B: every warp needs head g's probabilities of all 64 keys as A fragments (k16 step ks: keys 16 ks + 2t, +1, +8, +9)
+      // phase B: this thread's probabilities of head g (k16 block ks: keys 16 ks + 2t, +1, +8, +9) are the B fragments of every m-tile
       float sc[4][4];
       float mx = -INFINITY;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const float2 lo = *reinterpret_cast<const float2*>(S + g * DP_SPITCH + ks * 16 + 2 * t);
-        const float2 hi = *reinterpret_cast<const float2*>(S + g * DP_SPITCH + ks * 16 + 8 + 2 * t);
-        sc[ks][0] = lo.x; sc[ks][1] = lo.y; sc[ks][2] = hi.x; sc[ks][3] = hi.y;
-        mx = fmaxf(fmaxf(mx, fmaxf(lo.x, lo.y)), fmaxf(hi.x, hi.y));
+        const float* p0 = S + g * DP_SPITCH + ks * 16 + 2 * t;
+        const float2 lo0 = *reinterpret_cast<const float2*>(p0), hi0 = *reinterpret_cast<const float2*>(p0 + 8);
+        const float2 lo1 = *reinterpret_cast<const float2*>(p0 + 8 * DP_SPITCH), hi1 = *reinterpret_cast<const float2*>(p0 + 8 * DP_SPITCH + 8);
+        const int kb = s0 + ks * 16 + 2 * t;
+        sc[ks][0] = kb < s_end ? (lo0.x + lo1.x) * a.scale_log2 : -INFINITY;
+        sc[ks][1] = kb + 1 < s_end ? (lo0.y + lo1.y) * a.scale_log2 : -INFINITY;
+        sc[ks][2] = kb + 8 < s_end ? (hi0.x + hi1.x) * a.scale_log2 : -INFINITY;
+        sc[ks][3] = kb + 9 < s_end ? (hi0.y + hi1.y) * a.scale_log2 : -INFINITY;
+        mx = fmaxf(fmaxf(mx, fmaxf(sc[ks][0], sc[ks][1])), fmaxf(sc[ks][2], sc[ks][3]));
       }
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       const float m_new = fmaxf(m_run, mx);
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
       const float corr = exp2f(m_run - m_safe);         // m_run = -inf -> 0
-      uint32_t pa0[4], pa2[4];
+      uint32_t pb0[4], pb1[4];
       float ls = 0.f;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const float p0 = exp2f(sc[ks][0] - m_safe), p1 = exp2f(sc[ks][1] - m_safe), p2 = exp2f(sc[ks][2] - m_safe), p3 = exp2f(sc[ks][3] - m_safe);
         ls += (p0 + p1) + (p2 + p3);
-        pa0[ks] = pack2(p0, p1); pa2[ks] = pack2(p2, p3);
+        pb0[ks] = pack2(p0, p1); pb1[ks] = pack2(p2, p3);
       }
       ls += __shfl_xor_sync(0xffffffffu, ls, 1);
       ls += __shfl_xor_sync(0xffffffffu, ls, 2);
       l_run = l_run * corr + ls;
       m_run = m_new;
+      // the accumulators hold heads 2t, 2t+1: their rescale factors live in lanes 8t and 8t + 4
+      const float ce = __shfl_sync(0xffffffffu, corr, 8 * t), co = __shfl_sync(0xffffffffu, corr, 8 * t + 4);
 #pragma unroll
-      for (int j = 0; j < NTC; ++j) { acc[j][0] *= corr; acc[j][1] *= corr; }
-      // context += P . hid over this warp's CW columns: B fragments through ldmatrix.trans (rows = keys, 16-byte pieces = 8 columns)
-      const uint32_t rowaddr = sbase + (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (warp * CW + (lane >> 4) * 8) * 2;
+      for (int j = 0; j < NMT; ++j) { acc[j][0] *= ce; acc[j][1] *= co; acc[j][2] *= ce; acc[j][3] *= co; }
+      // A fragments = hid^T through ldmatrix.trans: matrices (keys 0-7 | cols 0-7), (keys 0-7 | cols 8-15), (keys 8-15 | cols 0-7), (keys 8-15 | 8-15)
+      const int krow = (lane & 7) + (lane >> 4) * 8;
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
+      for (int ks = 0; ks < 4; ++ks) {                // k16 block outer, m-tiles inner: NMT independent accumulator chains
+        const int row = ks * 16 + krow;
+        const uint32_t roff = row * 128, rsw = row & 7;
 #pragma unroll
-        for (int j = 0; j < NTC; j += 2) {
-          uint32_t b0, b1, b2, b3;
-          ldsm_x4_t(b0, b1, b2, b3, rowaddr + ks * 16 * PITCH + j * 16);
-          mma16816(acc[j], pa0[ks], 0u, pa2[ks], 0u, b0, b1);
-          mma16816(acc[j + 1], pa0[ks], 0u, pa2[ks], 0u, b2, b3);
+        for (int j = 0; j < NMT; ++j) {
+          const int col0 = warp * CW + j * 16;
+          const uint32_t ch = ((col0 & 63) >> 3) + ((lane >> 3) & 1);
+          uint32_t a0, a1, a2, a3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                       : "r"(sbase + (col0 >> 6) * 8192 + roff + ((ch ^ rsw) << 4)));
+          mma16816(acc[j], a0, a1, a2, a3, pb0[ks], pb1[ks]);
         }
+      }
     }
+    lap(4);
   }
   uses += nst;
-  // ---- normalised partial context of this split + its (max, sum)
-  if (g < H) {
+  if (prof) for (int k = 0; k < 5; ++k) a.tstamp[120 + k] = (unsigned long long)pc[k];
+  // ---- normalised partial context of this split + its (max, sum): acc[j] = (col0 + g | heads 2t, 2t+1), (col0 + g + 8 | same heads)
+  {
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    bf16* dst = a.pctx + (((int64_t)b * a.S + z) * H + g) * D + warp * CW + 2 * t;
+    const float ie = __shfl_sync(0xffffffffu, inv, 8 * t), io = __shfl_sync(0xffffffffu, inv, 8 * t + 4);
+    bf16* de = a.pctx + (((int64_t)b * a.S + z) * H + 2 * t) * D;
+    bf16* d_odd = de + D;
 #pragma unroll
-    for (int j = 0; j < NTC; ++j) *reinterpret_cast<uint32_t*>(dst + j * 8) = pack2(acc[j][0] * inv, acc[j][1] * inv);
-    if (warp == 0 && t == 0) {
+    for (int j = 0; j < NMT; ++j) {
+      const int c = warp * CW + j * 16 + g;
+      if (2 * t < H) { de[c] = __float2bfloat16_rn(acc[j][0] * ie); de[c + 8] = __float2bfloat16_rn(acc[j][2] * ie); }
+      if (2 * t + 1 < H) { d_odd[c] = __float2bfloat16_rn(acc[j][1] * io); d_odd[c + 8] = __float2bfloat16_rn(acc[j][3] * io); }
+    }
+    if (warp == 0 && t == 0 && g < H) {
       float* ml = a.pml + (((int64_t)b * a.S + z) * H + g) * 2;
       ml[0] = m_run; ml[1] = l_run;
     }
   }
-  cbar();      // the score tiles are reused by this CTA's next item
+  cbar();      // the score tiles and qsm are reused by this CTA's next item
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------ the step
@@ -549,6 +661,7 @@ template <int MT, int D>
 __global__ void __launch_bounds__(DP_THREADS, 1) decode_persist_kernel(const DpArgs a) {
   extern __shared__ __align__(128) unsigned char dp_smem[];
   __shared__ uint64_t full[DP_NST];
+  __shared__ float lnred[DP_CWARPS];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int G = gridDim.x, cta = blockIdx.x;
   const int d = a.d, B = a.B, H = a.H;
@@ -560,74 +673,111 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persist_kernel(const DpA
   sm.A2 = sm.W + (size_t)64 * sm.pitchA;
   sm.W2 = sm.A2 + (size_t)MT * 16 * (DP_DH * 2 + 64);
   sm.red = reinterpret_cast<float*>(sm.W2 + (size_t)128 * (DP_DH * 2 + 64));
-  // attention view of the same memory: ring stages, then the score tiles
-  unsigned char* stage0 = dp_smem;
-  float* ssm = reinterpret_cast<float*>(dp_smem + (size_t)DP_NST * DP_KS * (D * 2 + 16));
-  unsigned char* qsm = reinterpret_cast<unsigned char*>(ssm + 2 * 8 * DP_SPITCH);
+  // attention view of the same memory: ring stages (1024-byte aligned: swizzle atoms), then the score tiles and the staged qt rows
+  unsigned char* stage0 = dp_smem + ((1024u - (smem_u32(dp_smem) & 1023u)) & 1023u);
+  float* ssm = reinterpret_cast<float*>(stage0 + (size_t)DP_NST * (D / 64) * 8192);
+  unsigned char* qsm = reinterpret_cast<unsigned char*>(ssm + 2 * 2 * 8 * DP_SPITCH);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < DP_NST; ++s) mbar_init(&full[s], 1);
     fence_barrier_init();
   }
   __syncthreads();
-  uint32_t uses = 0;                                  // ring-stage uses of this CTA so far (same count in the producer and the consumers)
+  uint32_t uses = 0;                                  // ring-stage uses of this CTA so far
   const int p = *a.pos;
   const int cur = p % a.ML;
   // barrier numbering continues over the steps of one generation (the counter is never reset): 7 per layer
   unsigned long long kbar = (unsigned long long)p * (7ull * a.L);
-  const int nQT = H * (d / 64), nBD = H * ((a.ML + 1 + 127) / 128);
+  int nstamp = 0;
+  auto stamp = [&]() {
+    if (a.tstamp && cta == 0 && tid == 0) {
+      unsigned long long tt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+      a.tstamp[nstamp++] = tt;
+    }
+  };
+  stamp();
+  const int nC = d / 64;                              // 64-column chunks of a row
+  const int nQT = H * nC, nD = (a.ML + 1 + 127) / 128, nBD = H * nD;
+  const int nFF1 = (a.di + 15) / 16, nbF2 = (d + 15) / 16, nFF2 = nbF2 * a.KSL, nLM = (a.Vx + 15) / 16;
+  // Weight slices do not depend on other CTAs: those of a stage's FIRST item are requested before the grid barrier in front of it (and even
+  // across a LayerNorm stage, which leaves the operand memory alone), so after the barrier only the activations are still to come.
+  auto qtbd_weights = [&](const DpLayer& ly, int item) {
+    if (item < nQT) chain_weights<0>(a, ly, sm, item / nC, item % nC);
+    else chain_weights<1>(a, ly, sm, (item - nQT) / nD, (item - nQT) % nD);
+  };
   for (int l = 0; l < a.L; ++l) {
     const DpLayer ly = a.layers[l];
     // ---- QTBD (layer 0 also stores the embedding row into its ring slot; later layers got theirs from the previous LN2)
-    if (l == 0)
+    if (l == 0) {
       for (int e = cta * DP_THREADS + tid; e < B * (d / 8); e += G * DP_THREADS) {
         const int b = e / (d / 8), c = (e % (d / 8)) * 8;
         *reinterpret_cast<uint4*>(ly.ring + ((int64_t)b * a.ML + cur) * d + c) = __ldcg(reinterpret_cast<const uint4*>(a.x + (int64_t)b * d + c));
       }
-    for (int item = cta; item < nQT + nBD; item += G) {
-      if (item < nQT) chain_item<MT, 0>(a, ly, sm, item / (d / 64), item % (d / 64));
-      else { const int q = item - nQT, nd = nBD / H; chain_item<MT, 1>(a, ly, sm, q / nd, q % nd); }
+      fence_proxy_async_all();
+    }
+    for (int item = cta, first = 1; item < nQT + nBD; item += G, first = 0) {
+      const bool wr = first && l > 0;
+      if (item < nQT) chain_item<MT, 0>(a, ly, sm, item / nC, item % nC, wr);
+      else chain_item<MT, 1>(a, ly, sm, (item - nQT) / nD, (item - nQT) % nD, wr);
     }
     grid_barrier(a.bar, kbar++);
-    // ---- ATT
-    for (int item = cta; item < B * a.S; item += G) att_item<D>(a, ly, stage0, ssm, qsm, full, uses, item / a.S, item % a.S, cur);
+    stamp();
+    // ---- ATT (the operand memory changes hands: generic writes so far, TMA writes from here)
+    fence_proxy_async_all();
+    __syncthreads();
+    if (a.tstamp && tid == 0 && l == a.L - 1) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); a.tstamp[200 + 2 * cta] = tt; }
+    for (int item = cta; item < B * a.S; item += G) att_item<D>(a, &a.tmaps[l], stage0, ssm, qsm, full, uses, item / a.S, item % a.S, cur);
+    if (a.tstamp && tid == 0 && l == a.L - 1) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); a.tstamp[201 + 2 * cta] = tt; }
     // every ring copy this CTA issued has landed and been consumed (each stage's full barrier was waited on) before the memory is reused
+    if (cta < nQT) chain_weights<2>(a, ly, sm, cta / nC, cta % nC);
     grid_barrier(a.bar, kbar++);
+    stamp();
     // ---- VAON
-    for (int item = cta; item < nQT; item += G) chain_item<MT, 2>(a, ly, sm, item / (d / 64), item % (d / 64));
+    for (int item = cta, first = 1; item < nQT; item += G, first = 0) chain_item<MT, 2>(a, ly, sm, item / nC, item % nC, first != 0);
+    if (cta < nFF1) lin_weights(sm, ly.w1, d, a.di, d, cta * 16, 0);
     grid_barrier(a.bar, kbar++);
+    stamp();
     // ---- LN1
-    ln_rows(a, a.x, H, nullptr, ly.ln1w, ly.ln1b, a.y1, nullptr, 0);
+    ln_rows<D>(a, a.x, H, nullptr, ly.ln1w, ly.ln1b, a.y1, nullptr, 0, lnred);
     grid_barrier(a.bar, kbar++);
+    stamp();
     // ---- FF1
-    for (int item = cta; item < (a.di + 15) / 16; item += G) lin_item<MT, 0>(a, sm, a.y1, d, ly.w1, d, ly.b1, a.di, d, item * 16, 0, a.h1, a.di);
+    for (int item = cta, first = 1; item < nFF1; item += G, first = 0)
+      lin_item<MT, 0>(a, sm, a.y1, d, ly.w1, d, ly.b1, a.di, d, item * 16, 0, a.h1, a.di, first != 0);
+    if (cta < nFF2) lin_weights(sm, ly.w2, a.di, d, a.KW, (cta % nbF2) * 16, (cta / nbF2) * a.KW);
     grid_barrier(a.bar, kbar++);
+    stamp();
     // ---- FF2
-    {
-      const int nb = (d + 15) / 16;
-      for (int item = cta; item < nb * a.KSL; item += G) {
-        const int ks = item / nb, n0 = (item % nb) * 16;
-        lin_item<MT, 1>(a, sm, a.h1, a.di, ly.w2, a.di, nullptr, d, a.KW, n0, ks * a.KW, a.planes + (int64_t)ks * B * d, d);
-      }
+    for (int item = cta, first = 1; item < nFF2; item += G, first = 0) {
+      const int ks = item / nbF2, n0 = (item % nbF2) * 16;
+      lin_item<MT, 1>(a, sm, a.h1, a.di, ly.w2, a.di, nullptr, d, a.KW, n0, ks * a.KW, a.planes + (int64_t)ks * B * d, d, first != 0);
     }
+    if (l + 1 < a.L) { if (cta < nQT + nBD) qtbd_weights(a.layers[l + 1], cta); }
+    else if (cta < nLM) lin_weights(sm, a.E, d, a.Vx, d, cta * 16, 0);
     grid_barrier(a.bar, kbar++);
+    stamp();
     // ---- LN2 (+ next layer's ring slot)
-    ln_rows(a, a.y1, a.KSL, ly.b2, ly.ln2w, ly.ln2b, a.x, l + 1 < a.L ? a.layers[l + 1].ring : nullptr, cur);
+    ln_rows<D>(a, a.y1, a.KSL, ly.b2, ly.ln2w, ly.ln2b, a.x, l + 1 < a.L ? a.layers[l + 1].ring : nullptr, cur, lnred);
     grid_barrier(a.bar, kbar++);
+    stamp();
   }
   // ---- LM head
-  for (int item = cta; item < (a.Vx + 15) / 16; item += G) lin_item<MT, 2>(a, sm, a.x, d, a.E, d, a.out_bias, a.Vx, d, item * 16, 0, a.logits, a.ldl);
+  for (int item = cta, first = 1; item < nLM; item += G, first = 0)
+    lin_item<MT, 2>(a, sm, a.x, d, a.E, d, a.out_bias, a.Vx, d, item * 16, 0, a.logits, a.ldl, first != 0);
+  stamp();
   (void)warp;
 }
 
 struct DpHostTable {          // what txl_decode_persist_step(build = 1) leaves at the start of the workspace
   DpLayer layers[64];
+  CUtensorMap tm[64];
 };
 
 size_t dp_smem_bytes(int MT, int d, int KW) {
   const size_t pitchA = (size_t)(d > KW ? d : KW) * 2 + 64;
   const size_t gemm = (size_t)MT * 16 * pitchA + 64 * pitchA + (size_t)MT * 16 * (DP_DH * 2 + 64) + 128 * (DP_DH * 2 + 64) + (size_t)DP_CWARPS * MT * 16 * 17 * 4;
-  const size_t att = (size_t)DP_NST * DP_KS * ((size_t)d * 2 + 16) + 2 * 8 * DP_SPITCH * 4 + 8 * ((size_t)d * 2 + 16);
+  const size_t att = 1024 + (size_t)DP_NST * (d / 64) * 8192 + 2 * 2 * 8 * DP_SPITCH * 4 + 8 * ((size_t)d * 2 + 16);
   return (gemm > att ? gemm : att) + 128;
 }
 }  // namespace
@@ -649,6 +799,9 @@ static int dp_geometry(int B, int H, int dh, int d, int di, int ML, int L, int V
   *MLP = (ML + 1 + 3) / 4 * 4;
   return 1;
 }
+
+static unsigned long long* g_dp_tstamp = nullptr;
+extern "C" int txl_decode_persist_set_timestamps(unsigned long long* dev_buf) { g_dp_tstamp = dev_buf; return TXL_OK; }
 
 extern "C" int txl_decode_persist_supported(int B, int H, int dh, int d, int di, int ML, int L, int Vx) {
   int S, per, KW, KSL, MLP;
@@ -688,6 +841,7 @@ extern "C" int txl_decode_persist_step(const void* const* wqkv, const void* cons
   DpHostTable* tab = (DpHostTable*)take(sizeof(DpHostTable));
   DpArgs a;
   a.layers = tab->layers;
+  a.tmaps = tab->tm;
   a.qt = (bf16*)take((int64_t)B * H * d * 2);
   a.bd = (float*)take((int64_t)B * H * MLP * 4);
   a.pctx = (bf16*)take((int64_t)B * S * H * d * 2);
@@ -698,7 +852,7 @@ extern "C" int txl_decode_persist_step(const void* const* wqkv, const void* cons
   a.bar = (unsigned long long*)take(8);
   if (build_table) {
     TXL_CHECK_ARG(wqkv && wkT && wo && w1 && w2 && rtab && b1 && b2 && rwb && rrb && ln1w && ln1b && ln2w && ln2b && ring, "decode_persist: null table");
-    DpHostTable h;
+    static DpHostTable h;          // (16 KB: not on the stack)
     memset(&h, 0, sizeof(h));
     for (int l = 0; l < L; ++l) {
       DpLayer& y = h.layers[l];
@@ -706,6 +860,8 @@ extern "C" int txl_decode_persist_step(const void* const* wqkv, const void* cons
       y.w1 = (const bf16*)w1[l]; y.w2 = (const bf16*)w2[l]; y.r = (const bf16*)rtab[l];
       y.b1 = b1[l]; y.b2 = b2[l]; y.rwb = rwb[l]; y.rrb = rrb[l]; y.ln1w = ln1w[l]; y.ln1b = ln1b[l]; y.ln2w = ln2w[l]; y.ln2b = ln2b[l];
       y.ring = (bf16*)ring[l];
+      int rc = txl_make_tmap_2d(&h.tm[l], y.ring, (uint64_t)B * ML, (uint64_t)d, (uint64_t)d, 64, 64);
+      if (rc) return rc;
       TXL_CHECK_ARG(y.wq && y.wkT && y.wo && y.w1 && y.w2 && y.r && y.ring && ((uintptr_t)y.ring & 15) == 0 && ((uintptr_t)y.wkT & 15) == 0 && ((uintptr_t)y.wq & 15) == 0,
                     "decode_persist: layer %d pointers (16-byte alignment)", l);
     }
@@ -715,6 +871,7 @@ extern "C" int txl_decode_persist_step(const void* const* wqkv, const void* cons
     return TXL_OK;
   }
   TXL_CHECK_ARG(E && out_bias && x && pos && logits && ldl >= Vx && ((uintptr_t)x & 15) == 0 && ((uintptr_t)E & 15) == 0, "decode_persist: bad step args");
+  a.tstamp = g_dp_tstamp;
   a.E = (const bf16*)E; a.out_bias = out_bias; a.x = (bf16*)x; a.logits = logits; a.pos = pos; a.ldl = ldl;
   a.B = B; a.H = H; a.d = d; a.di = di; a.ML = ML; a.MLP = MLP; a.L = L; a.Vx = Vx; a.S = S; a.per = per; a.KW = KW; a.KSL = KSL;
   a.eps = eps; a.scale_log2 = 1.4426950408889634f / sqrtf((float)dh);

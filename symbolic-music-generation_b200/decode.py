@@ -46,7 +46,7 @@ _SPLIT_COLS = int(os.environ.get('TXL_DEC_SPLIT_COLS', '1000000'))   # A/B switc
 _ABL = int(os.environ.get('TXL_DECODE_ABL', '0'))       # timing ablations (results are garbage): 1 = no attention launch, 2 = no Linear / LayerNorm launches
 
 
-_PERSIST = os.environ.get('TXL_DECODE_PERSIST', '1') != '0'
+_PERSIST = os.environ.get('TXL_DECODE_PERSIST', '0') == '1'       # grid-barrier variant: correct, measured slower than the launch chain (profiles/r02_decode_ab.txt)
 
 
 def persist_supported(model, B):
