@@ -300,6 +300,24 @@ int txl_decode_persist_step(const void* const* wqkv, const void* const* wkT, con
                             float* logits, int64_t ldl, void* ws, int build_table, int B, int H, int dh, int d, int di, int mem_len, int L, int Vx,
                             float eps, void* stream);
 
+/* Fourth-generation bf16 decode step (csrc/decode_cluster.cu): the contract of txl_decode_persist_step (same arguments, same hidden-state ring,
+ * same absorbed projections), executed by thread-block CLUSTERS of 8 CTAs - CTA r = attention head r - each of which carries up to 8
+ * sequences through all L layers and the LM head on its own: activations cross CTAs through distributed shared memory behind hardware
+ * cluster barriers (8 per layer), weights stream through warp-private cp.async rings, nothing synchronises across clusters.  Geometry:
+ * 8 heads of 64 (d_model 512), d_inner a multiple of 256 (<= 4096), B <= 8 x (SMs / 8).  txl_decode_cluster_set_timestamps: profiling hook
+ * (CTA 0's %globaltimer at the start and after the stages of every layer, >= 7 L + 4 uint64). */
+int txl_decode_cluster_set_timestamps(unsigned long long* dev_buf);
+/* co-resident clusters of 8 CTAs this kernel gets on the current device (cudaOccupancyMaxActiveClusters) */
+int txl_decode_cluster_max_clusters(int di);
+int txl_decode_cluster_supported(int B, int H, int dh, int d, int di, int mem_len, int L, int Vx);
+int64_t txl_decode_cluster_ws_bytes(int B, int H, int dh, int d, int di, int mem_len, int L, int Vx);
+int txl_decode_cluster_step(const void* const* wqkv, const void* const* wkT, const void* const* wo, const void* const* w1, const void* const* w2,
+                            const void* const* rtab, const float* const* b1, const float* const* b2, const float* const* rwb,
+                            const float* const* rrb, const float* const* ln1w, const float* const* ln1b, const float* const* ln2w,
+                            const float* const* ln2b, void* const* ring, const void* E, const float* out_bias, void* x, const int32_t* pos,
+                            float* logits, int64_t ldl, void* ws, int build_table, int B, int H, int dh, int d, int di, int mem_len, int L, int Vx,
+                            float eps, void* stream);
+
 /* ---- mems ring / layout helpers  [A.8' _update_mems] ----------------------------------------------
  * time-major (L?,rows,B,d) <-> batch-major copies used at the Python boundary */
 int txl_tm_to_bm(const void* src, void* dst, int rows, int B, int d, int dtype_src, int dtype_dst, void* stream);

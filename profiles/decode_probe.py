@@ -19,26 +19,27 @@ torch.cuda.synchronize()
 print(out.shape)
 
 if os.environ.get('PROBE_STAGES'):
-    # per-stage time of the persistent step (CTA 0's %globaltimer after every grid barrier), summed over the layers
+    # per-stage time of the one-kernel step (CTA 0's %globaltimer after every stage), summed over the layers
     L_ = importlib.import_module('symbolic-music-generation_b200._lib')
+    decode = importlib.import_module('symbolic-music-generation_b200.decode')
     lib = L_.load()
     nl = cfg.n_layer
     buf = torch.zeros(600, dtype=torch.int64, device='cuda')
-    lib.txl_decode_persist_set_timestamps(buf.data_ptr())
+    cluster = decode.cluster_supported(model, B)
+    setter = lib.txl_decode_cluster_set_timestamps if cluster else lib.txl_decode_persist_set_timestamps
+    setter(buf.data_ptr())
     out = model.generate(input_ids=prompt, max_length=16 + 4, do_sample=True, top_k=8, eos_token_id=None, seed=77, use_cuda_graph=False)
     torch.cuda.synchronize()
-    lib.txl_decode_persist_set_timestamps(None)
+    setter(None)
     t = buf.cpu().tolist()
-    names = [f'L{l}.{s}' for l in range(nl) for s in ('qtbd', 'att', 'vaon', 'ln1', 'ff1', 'ff2', 'ln2')] + ['head']
+    stages = ('q+qt+bd', 'att', 'va+on', 'ln1', 'ff1+ff2', 'ln2') if cluster else ('qtbd', 'att', 'vaon', 'ln1', 'ff1', 'ff2', 'ln2')
+    names = [f'L{l}.{s}' for l in range(nl) for s in stages] + ['head']
     d = [(t[i + 1] - t[i]) / 1e3 for i in range(len(names))]
     agg = {}
     for n, v in zip(names, d):
         k = n.split('.')[-1]
         agg[k] = agg.get(k, 0) + v
-    print('layer 5 stages (us):', {n: round(v, 2) for n, v in zip(names, d) if n.startswith('L5.')})
-    print('attention item of CTA 0, last layer (cycles): before-wait / wait-full / phase A / consumer barrier / phase B =', t[120:125])
-    st = [t[200 + 2 * c] for c in range(148)]; en = [t[201 + 2 * c] for c in range(148)]
-    t0 = min(st)
-    print('ATT last layer, per CTA (us after the first start): start min/max', 0, round((max(st) - t0) / 1e3, 2), ' end min/median/max', round((min(en) - t0) / 1e3, 2), round((sorted(en)[74] - t0) / 1e3, 2), round((max(en) - t0) / 1e3, 2), ' durations min/max', round(min(e - s_ for e, s_ in zip(en, st)) / 1e3, 2), round(max(e - s_ for e, s_ in zip(en, st)) / 1e3, 2))
-    print('LN1 of the last layer on CTA 0 (ns): rows', t[131] - t[130], ' barrier', t[132] - t[131])
-    print('persistent step, stage times summed over layers (us):', {k: round(v, 1) for k, v in agg.items()}, 'total', round(sum(d), 1))
+    print('engine:', 'cluster' if cluster else 'persistent', ' layer 5 stages (us):', {n: round(v, 2) for n, v in zip(names, d) if n.startswith('L5.')})
+    print('one-kernel step, stage times of CTA 0 summed over layers (us):', {k: round(v, 1) for k, v in agg.items()}, 'total', round(sum(d), 1))
+    if cluster:
+        print('co-resident clusters of 8 CTAs:', lib.txl_decode_cluster_max_clusters(cfg.d_inner))

@@ -88,6 +88,11 @@ SIGNATURES = {
     'txl_decode_persist_supported': (_i, [_i] * 8),
     'txl_decode_persist_ws_bytes': (_i64, [_i] * 8),
     'txl_decode_persist_step': (_i, [_vp] * 15 + [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i] + [_i] * 8 + [_f, _vp]),
+    'txl_decode_cluster_set_timestamps': (_i, [_vp]),
+    'txl_decode_cluster_max_clusters': (_i, [_i]),
+    'txl_decode_cluster_supported': (_i, [_i] * 8),
+    'txl_decode_cluster_ws_bytes': (_i64, [_i] * 8),
+    'txl_decode_cluster_step': (_i, [_vp] * 15 + [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i] + [_i] * 8 + [_f, _vp]),
     'txl_decode_tail': (_i, [_vp, _i64, _vp, _i, _i, _i, _f, _i, _f, _u64, _i64, _vp, _vp, _vp, _i64, _i, _vp, _vp, _i64, _i64, _i, _vp, _vp, _i, _f, _vp]),
     'txl_set_pdl': (_i, [_i]),
     'txl_decode_attn_pipe_config': (_i, [_i]),

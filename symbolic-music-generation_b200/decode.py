@@ -58,6 +58,19 @@ def persist_supported(model, B):
     return bool(load().txl_decode_persist_supported(int(B), cfg.n_head, cfg.d_head, cfg.d_model, cfg.d_inner, cfg.mem_len, cfg.n_layer, Vx))
 
 
+_CLUSTER = os.environ.get('TXL_DECODE_CLUSTER', '1') != '0'
+CL_MAXB = 64       # sequences per chain of the cluster engine: 8 per cluster x the co-resident clusters of 8 SMs (>= 8 on a B200)
+
+
+def cluster_supported(model, B):
+    """The cluster engine (csrc/decode_cluster.cu: 8-CTA clusters, one per attention head, DSMEM hand-over) takes this model and `B` sequences."""
+    cfg = model.config
+    if not _CLUSTER or model._E.dtype != torch.bfloat16 or not cfg.same_length or cfg.mem_len <= 0:
+        return False
+    Vx = cfg.vocab_size + len(getattr(cfg, 'cutoffs', []) or [])
+    return bool(load().txl_decode_cluster_supported(int(B), cfg.n_head, cfg.d_head, cfg.d_model, cfg.d_inner, cfg.mem_len, cfg.n_layer, Vx))
+
+
 def _dec_linear_ok(A, W):
     return (A.dtype == torch.bfloat16 and A.shape[1] % 32 == 0 and A.stride(1) == 1 and W.stride(1) == 1 and A.stride(0) % 8 == 0
             and W.stride(0) % 8 == 0)
@@ -114,6 +127,11 @@ def sequence_groups(model, B, requested=None):
     """How many independent sequence groups generate() decodes as parallel graph branches (GroupedDecoder).  bf16 second-generation path only."""
     if requested is None:
         requested = int(os.environ.get('TXL_DECODE_GROUPS', '0')) or None
+    if hasattr(model, '_W'):
+        nc = (B + CL_MAXB - 1) // CL_MAXB
+        if cluster_supported(model, (B + nc - 1) // nc):
+            # clusters of 8 SMs own their sequences end to end: one chain per 144 sequences, no sequence groups
+            return max(nc, min(int(requested), B)) if requested is not None else nc
     need = (B + SK_MAXM - 1) // SK_MAXM              # a Decoder (one chain of kernels) takes at most SK_MAXM sequences
     if hasattr(model, '_W') and persist_supported(model, (B + need - 1) // need):
         # the persistent step occupies every SM: sequence groups would only serialise, so as few chains as the 64-row limit allows
@@ -149,7 +167,8 @@ class Decoder:
         pos_tab = ops.posemb_table(ML + 1, cfg.clamp_len, d, dt, dev)
         self.kc, self.vc, self.kvc, self.r, self.r_hm = [], [], [], [], []
         self.pipe_attn = dt == torch.bfloat16
-        self.persist = persist and persist_supported(model, B)
+        self.cluster = persist and cluster_supported(model, B)
+        self.persist = self.cluster or (persist and persist_supported(model, B))       # both run over the hidden-state ring
         if self.persist:
             # the cache IS the hidden-state mems (chronological rows: slot 0 = oldest = the first one to be overwritten); private copies,
             # the step writes into them.  K projection transposed per head once: wkT[h, c, e] = W_k[h*64 + e, c].
@@ -224,7 +243,8 @@ class Decoder:
                               [w.b2 for w in W], [w.rwb for w in W], [w.rrb for w in W], [w.ln1_w for w in W], [w.ln1_b for w in W],
                               [w.ln2_w for w in W], [w.ln2_b for w in W], self.ring]
         self._persist_arrays = [arr(ts) for ts in self._persist_keep]
-        nbytes = lib.txl_decode_persist_ws_bytes(self.B, cfg.n_head, cfg.d_head, self.d, cfg.d_inner, self.ML, L, self.Vx)
+        ws_bytes = lib.txl_decode_cluster_ws_bytes if self.cluster else lib.txl_decode_persist_ws_bytes
+        nbytes = ws_bytes(self.B, cfg.n_head, cfg.d_head, self.d, cfg.d_inner, self.ML, L, self.Vx)
         self._persist_ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.dev)
         off = (-self._persist_ws.data_ptr()) % 256
         self._persist_ws_ptr = self._persist_ws.data_ptr() + off
@@ -234,10 +254,11 @@ class Decoder:
 
     def _persist_call(self, build):
         cfg = self.cfg
-        check(load().txl_decode_persist_step(*self._persist_arrays, ptr(self.model._E_ext), ptr(self.model._out_bias_ext), ptr(self.x0), ptr(self.pos),
-                                             ptr(self.logits), self.logits.stride(0), self._persist_ws_ptr, int(build), self.B, cfg.n_head, cfg.d_head,
-                                             self.d, cfg.d_inner, self.ML, cfg.n_layer, self.Vx, float(cfg.layer_norm_epsilon), stream_ptr()),
-              'decode_persist_step')
+        step = load().txl_decode_cluster_step if self.cluster else load().txl_decode_persist_step
+        check(step(*self._persist_arrays, ptr(self.model._E_ext), ptr(self.model._out_bias_ext), ptr(self.x0), ptr(self.pos),
+                   ptr(self.logits), self.logits.stride(0), self._persist_ws_ptr, int(build), self.B, cfg.n_head, cfg.d_head,
+                   self.d, cfg.d_inner, self.ML, cfg.n_layer, self.Vx, float(cfg.layer_norm_epsilon), stream_ptr()),
+              'decode_cluster_step' if self.cluster else 'decode_persist_step')
 
     # one decode step: every line is a kernel launch on the current stream
     def _step_kernels(self):
