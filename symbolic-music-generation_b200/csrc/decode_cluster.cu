@@ -202,50 +202,81 @@ __device__ __forceinline__ void warp_gemm(const unsigned char* X, int pitchX, co
   cpa_wait<0>();
 }
 
-// ------------------------------------------------------------------------------------------------------------------------------ attention item
-// (the stage loop of decode_persist.cu's att_item: TMA boxes of 64 keys x 128 bytes with SWIZZLE_128B; phase A S^T[key, head] on mma.sync with
-// keys as M, phase B ctx^T[col, head]; two stages).  qt of the sequence is already staged in sm.qsm; output: normalised partial context of
-// all heads -> ctx_out [8][d] bf16, (max, sum) -> ml_out [8][2] (global: read by the head owners after the cluster barrier).
-__device__ void dc_attention(const DcArgs& a, const CUtensorMap* tm, const DcSmem& sm, uint64_t* full, uint32_t& uses, int seq, int s_begin, int s_end,
-                             int cur, bf16* ctx_out, float* ml_out) {
+// ------------------------------------------------------------------------------------------------------------------------------ attention items
+// The stage loop of decode_persist.cu's att_item (TMA boxes of 64 keys x 128 bytes with SWIZZLE_128B; phase A S^T[key, head] on mma.sync with
+// keys as M, phase B ctx^T[col, head]; two stages), run over ALL items of this CTA as ONE pipeline: item k = keys [sb, se) of sequence
+// seq_first + k; the ring stages of item k + 1 are requested while item k is still being consumed, and its qt rows (pulled from the eight
+// head owners' shared memory) land in the other half of sm.qsm meanwhile.  Per item: normalised partial context of all heads ->
+// pctx[seq, part] [8][d] bf16, (max, sum) -> pml[seq, part] [8][2] (global: read by the head owners after the cluster barrier).
+__device__ void dc_attention(cg::cluster_group& cluster, const DcArgs& a, const CUtensorMap* tm, const DcSmem& sm, uint64_t* full, uint32_t& uses,
+                             int n_items, int seq_first, int part, int sb, int se, int cur) {
   constexpr int D = DC_D, NB = D / 64, NKS = D / 16, KH = NKS / 2, CW = D / DC_WARPS, NMT = CW / 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int ML = a.ML, H = DC_H;
-  const int nst = (s_end - s_begin + DC_KS - 1) / DC_KS;
+  const int nst = (se - sb + DC_KS - 1) / DC_KS, ntot = n_items * nst;
+  const int seq_loc0 = seq_first - (blockIdx.x / DC_CS) * a.NS;          // row of the first item's sequence in the owners' qtl
   unsigned char* stage0 = sm.r1;
   const uint64_t pol = l2_policy_evict_first();
-  auto issue = [&](int i) {
-    if (lane == 0 && i < nst) {
-      const uint32_t u = uses + i, st = u % DC_NST;
+  auto issue = [&](int j) {
+    if (lane == 0 && j < ntot) {
+      const uint32_t u = uses + j, st = u % DC_NST;
+      const int row = (seq_first + j / nst) * ML + sb + (j % nst) * DC_KS;
       if (warp == 0) mbar_expect_tx(&full[st], DC_STAGE);
-      for (int cb = warp; cb < NB; cb += DC_WARPS) {
-        if (a.hints & 2) tma_load_2d_hint(stage0 + (size_t)st * DC_STAGE + cb * 8192, tm, &full[st], cb * 64, seq * ML + s_begin + i * DC_KS, pol);
-        else tma_load_2d(stage0 + (size_t)st * DC_STAGE + cb * 8192, tm, &full[st], cb * 64, seq * ML + s_begin + i * DC_KS);
-      }
+      for (int cb = warp; cb < NB; cb += DC_WARPS) tma_load_2d_hint(stage0 + (size_t)st * DC_STAGE + cb * 8192, tm, &full[st], cb * 64, row, pol);
+    }
+  };
+  // qt[sequence of the item][head] from the eight head owners -> sm.qsm half (item & 1): two 16-byte pieces per thread, loaded into registers
+  // when the previous item starts and stored just before the barrier of its last stage (a remote read takes ~1 us: never waited for)
+  static_assert(8 * (D / 8) == 2 * DC_THREADS, "two qt pieces per thread");
+  uint4 qpre[2];
+  auto qt_load = [&](int item) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * DC_THREADS, hh = e / (D / 8), v = e % (D / 8);
+      const unsigned char* rp = cluster.map_shared_rank(sm.qtl, hh);
+      qpre[q] = *reinterpret_cast<const uint4*>(rp + (size_t)(seq_loc0 + item) * D * 2 + v * 16);
+    }
+  };
+  auto qt_store = [&](int item) {
+    unsigned char* dst = sm.qsm + (size_t)(item & 1) * 8 * DC_QP;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * DC_THREADS, hh = e / (D / 8), v = e % (D / 8);
+      *reinterpret_cast<uint4*>(dst + (size_t)hh * DC_QP + v * 16) = qpre[q];
     }
   };
 #pragma unroll
-  for (int i = 0; i < DC_NST; ++i) issue(i);
+  for (int j = 0; j < DC_NST; ++j) issue(j);
+  qt_load(0);
+  qt_store(0);
+  __syncthreads();
   const int mt = warp & 3, kh = warp >> 2;
-  const unsigned char* qrow = sm.qsm + (size_t)g * DC_QP + t * 4;
   float acc[NMT][4];
-#pragma unroll
-  for (int j = 0; j < NMT; ++j)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
-  const float* bd0 = a.bd + ((int64_t)seq * H + 2 * t) * a.MLP;
-  const float* bd1 = bd0 + a.MLP;
-  for (int i = 0; i < nst; ++i) {
-    const uint32_t u = uses + i, st = u % DC_NST;
-    const int s0 = s_begin + i * DC_KS;
-    float* S = sm.ssm + (size_t)(i & 1) * 2 * 8 * DC_SPITCH;
+  const unsigned char* qrow = nullptr;
+  const float *bd0 = nullptr, *bd1 = nullptr;
+  for (int j = 0; j < ntot; ++j) {
+    const int item = j / nst, i = j - item * nst;
+    if (i == 0) {
+#pragma unroll
+      for (int jj = 0; jj < NMT; ++jj)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[jj][q] = 0.f;
+      m_run = -INFINITY; l_run = 0.f;
+      qrow = sm.qsm + (size_t)(item & 1) * 8 * DC_QP + (size_t)g * DC_QP + t * 4;
+      bd0 = a.bd + ((int64_t)(seq_first + item) * H + 2 * t) * a.MLP;
+      bd1 = bd0 + a.MLP;
+      if (item + 1 < n_items) qt_load(item + 1);
+    }
+    const uint32_t u = uses + j, st = u % DC_NST;
+    const int s0 = sb + i * DC_KS;
+    float* S = sm.ssm + (size_t)(j & 1) * 2 * 8 * DC_SPITCH;
     float bdv[4] = {0.f, 0.f, 0.f, 0.f};
     if (kh == 0) {
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int sk = s0 + mt * 16 + g + hf * 8;
-        if (sk < s_end) {
+        if (sk < se) {
           const int x = sk <= cur ? ML - cur + sk : sk - cur;
           bdv[hf * 2] = __ldcg(bd0 + x);
           bdv[hf * 2 + 1] = __ldcg(bd1 + x);
@@ -279,8 +310,9 @@ __device__ void dc_attention(const DcArgs& a, const CUtensorMap* tm, const DcSme
       Sh[(2 * t) * DC_SPITCH + 8] = c4[0][2] + c4[1][2] + bdv[2];
       Sh[(2 * t + 1) * DC_SPITCH + 8] = c4[0][3] + c4[1][3] + bdv[3];
     }
+    if (i == nst - 1 && item + 1 < n_items) qt_store(item + 1);      // (that half of qsm was last read two items ago)
     __syncthreads();
-    if (i >= 1) issue(i - 1 + DC_NST);                // every warp is done with the previous stage's buffer
+    if (j >= 1) issue(j - 1 + DC_NST);                // every warp is done with the previous stage's buffer
     {
       float sc[4][4];
       float mx = -INFINITY;
@@ -290,10 +322,10 @@ __device__ void dc_attention(const DcArgs& a, const CUtensorMap* tm, const DcSme
         const float2 lo0 = *reinterpret_cast<const float2*>(p0), hi0 = *reinterpret_cast<const float2*>(p0 + 8);
         const float2 lo1 = *reinterpret_cast<const float2*>(p0 + 8 * DC_SPITCH), hi1 = *reinterpret_cast<const float2*>(p0 + 8 * DC_SPITCH + 8);
         const int kb = s0 + ks * 16 + 2 * t;
-        sc[ks][0] = kb < s_end ? (lo0.x + lo1.x) * a.scale_log2 : -INFINITY;
-        sc[ks][1] = kb + 1 < s_end ? (lo0.y + lo1.y) * a.scale_log2 : -INFINITY;
-        sc[ks][2] = kb + 8 < s_end ? (hi0.x + hi1.x) * a.scale_log2 : -INFINITY;
-        sc[ks][3] = kb + 9 < s_end ? (hi0.y + hi1.y) * a.scale_log2 : -INFINITY;
+        sc[ks][0] = kb < se ? (lo0.x + lo1.x) * a.scale_log2 : -INFINITY;
+        sc[ks][1] = kb + 1 < se ? (lo0.y + lo1.y) * a.scale_log2 : -INFINITY;
+        sc[ks][2] = kb + 8 < se ? (hi0.x + hi1.x) * a.scale_log2 : -INFINITY;
+        sc[ks][3] = kb + 9 < se ? (hi0.y + hi1.y) * a.scale_log2 : -INFINITY;
         mx = fmaxf(fmaxf(mx, fmaxf(sc[ks][0], sc[ks][1])), fmaxf(sc[ks][2], sc[ks][3]));
       }
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -315,39 +347,42 @@ __device__ void dc_attention(const DcArgs& a, const CUtensorMap* tm, const DcSme
       m_run = m_new;
       const float ce = __shfl_sync(0xffffffffu, corr, 8 * t), co = __shfl_sync(0xffffffffu, corr, 8 * t + 4);
 #pragma unroll
-      for (int j = 0; j < NMT; ++j) { acc[j][0] *= ce; acc[j][1] *= co; acc[j][2] *= ce; acc[j][3] *= co; }
+      for (int jj = 0; jj < NMT; ++jj) { acc[jj][0] *= ce; acc[jj][1] *= co; acc[jj][2] *= ce; acc[jj][3] *= co; }
       const int krow = (lane & 7) + (lane >> 4) * 8;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const int row = ks * 16 + krow;
         const uint32_t roff = row * 128, rsw = row & 7;
 #pragma unroll
-        for (int j = 0; j < NMT; ++j) {
-          const int col0 = warp * CW + j * 16;
+        for (int jj = 0; jj < NMT; ++jj) {
+          const int col0 = warp * CW + jj * 16;
           const uint32_t ch = ((col0 & 63) >> 3) + ((lane >> 3) & 1);
           uint32_t a0, a1, a2, a3;
           asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                        : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
                        : "r"(sbase + (col0 >> 6) * 8192 + roff + ((ch ^ rsw) << 4)));
-          mma16816(acc[j], a0, a1, a2, a3, pb0[ks], pb1[ks]);
+          mma16816(acc[jj], a0, a1, a2, a3, pb0[ks], pb1[ks]);
         }
       }
     }
-  }
-  uses += nst;
-  {
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    const float ie = __shfl_sync(0xffffffffu, inv, 8 * t), io = __shfl_sync(0xffffffffu, inv, 8 * t + 4);
-    bf16* de = ctx_out + (size_t)(2 * t) * D;
-    bf16* dodd = de + D;
+    if (i == nst - 1) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      const float ie = __shfl_sync(0xffffffffu, inv, 8 * t), io = __shfl_sync(0xffffffffu, inv, 8 * t + 4);
+      bf16* de = a.pctx + (((int64_t)(seq_first + item) * DC_CS + part) * H + 2 * t) * D;
+      bf16* dodd = de + D;
 #pragma unroll
-    for (int j = 0; j < NMT; ++j) {
-      const int c = warp * CW + j * 16 + g;
-      de[c] = __float2bfloat16_rn(acc[j][0] * ie); de[c + 8] = __float2bfloat16_rn(acc[j][2] * ie);
-      dodd[c] = __float2bfloat16_rn(acc[j][1] * io); dodd[c + 8] = __float2bfloat16_rn(acc[j][3] * io);
+      for (int jj = 0; jj < NMT; ++jj) {
+        const int c = warp * CW + jj * 16 + g;
+        de[c] = __float2bfloat16_rn(acc[jj][0] * ie); de[c + 8] = __float2bfloat16_rn(acc[jj][2] * ie);
+        dodd[c] = __float2bfloat16_rn(acc[jj][1] * io); dodd[c + 8] = __float2bfloat16_rn(acc[jj][3] * io);
+      }
+      if (warp == 0 && t == 0) {
+        float* ml = a.pml + (((int64_t)(seq_first + item) * DC_CS + part) * H + g) * 2;
+        ml[0] = m_run; ml[1] = l_run;
+      }
     }
-    if (warp == 0 && t == 0) { ml_out[g * 2] = m_run; ml_out[g * 2 + 1] = l_run; }
   }
+  uses += ntot;
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------ residual + LayerNorm
@@ -425,7 +460,7 @@ __global__ void __cluster_dims__(DC_CS, 1, 1) __launch_bounds__(DC_THREADS, 1) d
     sm.vs = p; p += DC_NS * DC_P64;
     sm.h1s = p; p += DC_NS * (DS * 2 + 64);
     sm.qtl = p; p += DC_NS * DC_D * 2;
-    sm.qsm = p; p += 8 * DC_QP;
+    sm.qsm = p; p += 2 * 8 * DC_QP;
     sm.partl = reinterpret_cast<float*>(p); p += DC_NS * DC_D * 4;
     sm.ssm = reinterpret_cast<float*>(p); p += 2 * 2 * 8 * DC_SPITCH * 4;
     sm.statl = reinterpret_cast<float*>(p); p += DC_NS * 2 * 4;
@@ -509,28 +544,25 @@ __global__ void __cluster_dims__(DC_CS, 1, 1) __launch_bounds__(DC_THREADS, 1) d
     });
     cluster.sync();                                                                                          // barrier 1
     stamp();
-    // ---- 3: attention items of this CTA
-    fence_proxy_async_all();                          // the stage memory held generic-proxy data (weight rings): TMA writes follow
-    for (int it = 0; it < (one_item ? 1 : nsc); ++it) {
-      const int it_s = one_item ? rank / KPC : it, it_kp = one_item ? rank % KPC : rank;
-      bf16* ctx_out = a.pctx + ((int64_t)(seq0 + it_s) * DC_CS + it_kp) * DC_H * DC_D;
-      float* ml_out = a.pml + ((int64_t)(seq0 + it_s) * DC_CS + it_kp) * DC_H * 2;
-      const int sb = it_kp * per, se = min(sb + per, ML);
-      if (sb < se) {
-        __syncthreads();                              // the previous item is done with qsm and the score tiles
-        // pull qt[sequence][head] from the eight head owners
-        for (int e = tid; e < 8 * (DC_D / 8); e += DC_THREADS) {
-          const int hh = e / (DC_D / 8), v = e % (DC_D / 8);
-          const unsigned char* rp = cluster.map_shared_rank(sm.qtl, hh);
-          *reinterpret_cast<uint4*>(sm.qsm + (size_t)hh * DC_QP + v * 16) = *reinterpret_cast<const uint4*>(rp + (size_t)it_s * DC_D * 2 + v * 16);
+    // ---- 3: attention items of this CTA (one pipeline over all of them)
+    {
+      const int n_items = one_item ? (rank < nsc * KPC ? 1 : 0) : nsc;
+      const int it_s0 = one_item ? rank / KPC : 0, part = one_item ? rank % KPC : rank;
+      const int sb = part * per, se = min(sb + per, ML);
+      if (n_items > 0) {
+        if (sb < se) {
+          fence_proxy_async_all();                    // the stage memory held generic-proxy data (weight rings): TMA writes follow
+          __syncthreads();
+          dc_attention(cluster, a, &a.tmaps[l], sm, full, uses, n_items, seq0 + it_s0, part, sb, se, cur);
+        } else if (tid < 8) {                         // an empty key part (mem_len shorter than the parts): weight 0 (its rows are never read)
+          for (int k = 0; k < n_items; ++k) {
+            float* ml = a.pml + (((int64_t)(seq0 + it_s0 + k) * DC_CS + part) * DC_H + tid) * 2;
+            ml[0] = -INFINITY; ml[1] = 0.f;
+          }
         }
-        __syncthreads();
-        dc_attention(a, &a.tmaps[l], sm, full, uses, seq0 + it_s, sb, se, cur, ctx_out, ml_out);
-      } else if (tid < 8) {                           // an empty key part (mem_len shorter than the parts): weight 0 (its rows are never read)
-        ml_out[tid * 2] = -INFINITY; ml_out[tid * 2 + 1] = 0.f;
       }
+      __syncthreads();                                // every warp is done with the stage memory: the weight rings take it back
     }
-    __syncthreads();                                  // every warp is done with the stage memory: the weight rings take it back
     wg_prefetch(spec_v(ly), wring, lane);
     cluster.sync();                                                                                          // barrier 2
     stamp();
@@ -633,7 +665,7 @@ struct DcHostTable {
 size_t dc_smem_bytes(int di) {
   const int DS = di / DC_CS;
   size_t n = 1024 + (size_t)DC_NST * DC_STAGE + 3 * DC_NS * DC_XP + 3 * DC_NS * DC_P64 + (size_t)DC_NS * (DS * 2 + 64) + DC_NS * DC_D * 2 + 8 * DC_QP +
-             DC_NS * DC_D * 4 + 2 * 2 * 8 * DC_SPITCH * 4 + DC_NS * 2 * 4;
+             8 * DC_QP + DC_NS * DC_D * 4 + 2 * 2 * 8 * DC_SPITCH * 4 + DC_NS * 2 * 4;
   return n + 128;
 }
 
