@@ -28,7 +28,7 @@
 namespace cg = cooperative_groups;
 
 namespace {
-constexpr int DC_CS = 8;                            // CTAs per cluster = heads
+constexpr int DC_PARTS = 16;                        // key parts per sequence in the partial-context scratch (>= the largest cluster)
 constexpr int DC_THREADS = 256, DC_WARPS = 8;
 constexpr int DC_D = 512, DC_DH = 64, DC_H = 8;
 constexpr int DC_NS = 8;                            // sequences per cluster = N of the weight MMAs
@@ -208,13 +208,15 @@ __device__ __forceinline__ void warp_gemm(const unsigned char* X, int pitchX, co
 // seq_first + k; the ring stages of item k + 1 are requested while item k is still being consumed, and its qt rows (pulled from the eight
 // head owners' shared memory) land in the other half of sm.qsm meanwhile.  Per item: normalised partial context of all heads ->
 // pctx[seq, part] [8][d] bf16, (max, sum) -> pml[seq, part] [8][2] (global: read by the head owners after the cluster barrier).
+template <int CS>
 __device__ void dc_attention(cg::cluster_group& cluster, const DcArgs& a, const CUtensorMap* tm, const DcSmem& sm, uint64_t* full, uint32_t& uses,
                              int n_items, int seq_first, int part, int sb, int se, int cur) {
   constexpr int D = DC_D, NB = D / 64, NKS = D / 16, KH = NKS / 2, CW = D / DC_WARPS, NMT = CW / 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int ML = a.ML, H = DC_H;
   const int nst = (se - sb + DC_KS - 1) / DC_KS, ntot = n_items * nst;
-  const int seq_loc0 = seq_first - (blockIdx.x / DC_CS) * a.NS;          // row of the first item's sequence in the owners' qtl
+  constexpr int RPH = CS / 8, VPS = 64 / RPH;      // CTAs per head; 16-byte pieces of a qt row held by each of them
+  const int seq_loc0 = seq_first - (blockIdx.x / CS) * a.NS;          // row of the first item's sequence in the owners' qtl
   unsigned char* stage0 = sm.r1;
   const uint64_t pol = l2_policy_evict_first();
   auto issue = [&](int j) {
@@ -233,8 +235,8 @@ __device__ void dc_attention(cg::cluster_group& cluster, const DcArgs& a, const 
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int e = tid + q * DC_THREADS, hh = e / (D / 8), v = e % (D / 8);
-      const unsigned char* rp = cluster.map_shared_rank(sm.qtl, hh);
-      qpre[q] = *reinterpret_cast<const uint4*>(rp + (size_t)(seq_loc0 + item) * D * 2 + v * 16);
+      const unsigned char* rp = cluster.map_shared_rank(sm.qtl, hh * RPH + v / VPS);
+      qpre[q] = *reinterpret_cast<const uint4*>(rp + ((size_t)(seq_loc0 + item) * VPS + (v % VPS)) * 16);
     }
   };
   auto qt_store = [&](int item) {
@@ -368,7 +370,7 @@ __device__ void dc_attention(cg::cluster_group& cluster, const DcArgs& a, const 
     if (i == nst - 1) {
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       const float ie = __shfl_sync(0xffffffffu, inv, 8 * t), io = __shfl_sync(0xffffffffu, inv, 8 * t + 4);
-      bf16* de = a.pctx + (((int64_t)(seq_first + item) * DC_CS + part) * H + 2 * t) * D;
+      bf16* de = a.pctx + (((int64_t)(seq_first + item) * DC_PARTS + part) * H + 2 * t) * D;
       bf16* dodd = de + D;
 #pragma unroll
       for (int jj = 0; jj < NMT; ++jj) {
@@ -377,7 +379,7 @@ __device__ void dc_attention(cg::cluster_group& cluster, const DcArgs& a, const 
         dodd[c] = __float2bfloat16_rn(acc[jj][1] * io); dodd[c + 8] = __float2bfloat16_rn(acc[jj][3] * io);
       }
       if (warp == 0 && t == 0) {
-        float* ml = a.pml + (((int64_t)(seq_first + item) * DC_CS + part) * H + g) * 2;
+        float* ml = a.pml + (((int64_t)(seq_first + item) * DC_PARTS + part) * H + g) * 2;
         ml[0] = m_run; ml[1] = l_run;
       }
     }
@@ -386,65 +388,79 @@ __device__ void dc_attention(cg::cluster_group& cluster, const DcArgs& a, const 
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------ residual + LayerNorm
-// CTA j owns columns [64 j, 64 j + 64).  z = residual + sum over the 8 CTAs' partials (pulled) (+ bias); (mean, M2) of its 64 columns per row
-// -> statl; barrier; combined statistics (Chan) -> normalise -> its slice of `dst` (local); barrier; all-gather of the other slices (pulled).
+// CTA j owns COLS = d / CS columns.  z = residual + sum over the CS CTAs' partials (pulled) (+ bias); (mean, M2) of its columns per row ->
+// statl; barrier; combined statistics (Chan) -> normalise -> its slice of `dst` (local); barrier; all-gather of the other slices (pulled).
+template <int CS>
 __device__ void dc_residual_ln(cg::cluster_group& cluster, const DcSmem& sm, unsigned char* res, unsigned char* dst, const float* bias, const float* gamma,
                                const float* beta, float eps, int rank) {
-  const int tid = threadIdx.x, lane = tid & 31, s = tid >> 5;      // one warp per sequence, two columns per lane
-  const int c = rank * 64 + lane * 2;
-  const float2 gm = *reinterpret_cast<const float2*>(gamma + c), bt = *reinterpret_cast<const float2*>(beta + c);
-  float2 bs = make_float2(0.f, 0.f);
-  if (bias) bs = *reinterpret_cast<const float2*>(bias + c);
-  float2 pv[DC_CS];
+  constexpr int COLS = DC_D / CS, CPL = COLS / 32;                 // columns per CTA, per lane (2 or 1)
+  const int tid = threadIdx.x, lane = tid & 31, s = tid >> 5;      // one warp per sequence
+  const int c = rank * COLS + lane * CPL;
+  float gm[2] = {0.f, 0.f}, bt[2] = {0.f, 0.f}, bs[2] = {0.f, 0.f}, z[2] = {0.f, 0.f};
 #pragma unroll
-  for (int r = 0; r < DC_CS; ++r) {
-    const float* rp = cluster.map_shared_rank(sm.partl, r);
-    pv[r] = *reinterpret_cast<const float2*>(rp + s * DC_D + c);
+  for (int k = 0; k < CPL; ++k) { gm[k] = gamma[c + k]; bt[k] = beta[c + k]; if (bias) bs[k] = bias[c + k]; }
+  float pv[CS][2];
+#pragma unroll
+  for (int r = 0; r < CS; ++r) {                                   // every remote read is issued before the first add
+    const float* rp = cluster.map_shared_rank(sm.partl, r) + s * DC_D + c;
+    if (CPL == 2) { const float2 v = *reinterpret_cast<const float2*>(rp); pv[r][0] = v.x; pv[r][1] = v.y; }
+    else { pv[r][0] = rp[0]; pv[r][1] = 0.f; }
   }
-  const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(res + (size_t)s * DC_XP + c * 2);
-  float z0 = __bfloat162float(rv.x) + bs.x, z1 = __bfloat162float(rv.y) + bs.y;
 #pragma unroll
-  for (int r = 0; r < DC_CS; ++r) { z0 += pv[r].x; z1 += pv[r].y; }
-  const float mj = warp_sum(z0 + z1) * (1.f / 64.f);
-  const float m2j = warp_sum((z0 - mj) * (z0 - mj) + (z1 - mj) * (z1 - mj));
+  for (int k = 0; k < CPL; ++k) z[k] = __bfloat162float(reinterpret_cast<const bf16*>(res + (size_t)s * DC_XP)[c + k]) + bs[k];
+#pragma unroll
+  for (int r = 0; r < CS; ++r)
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) z[k] += pv[r][k];
+  const float mj = warp_sum(CPL == 2 ? z[0] + z[1] : z[0]) * (1.f / COLS);
+  const float m2j = warp_sum(CPL == 2 ? (z[0] - mj) * (z[0] - mj) + (z[1] - mj) * (z[1] - mj) : (z[0] - mj) * (z[0] - mj));
   if (lane == 0) { sm.statl[s * 2] = mj; sm.statl[s * 2 + 1] = m2j; }
   cluster.sync();
   float mean = 0.f, m2 = 0.f;
   {
-    float mr[DC_CS], qr[DC_CS];
+    float mr[CS], qr[CS];
 #pragma unroll
-    for (int r = 0; r < DC_CS; ++r) {
+    for (int r = 0; r < CS; ++r) {
       const float* rp = cluster.map_shared_rank(sm.statl, r);
       mr[r] = rp[s * 2]; qr[r] = rp[s * 2 + 1];
     }
 #pragma unroll
-    for (int r = 0; r < DC_CS; ++r) mean += mr[r];
-    mean *= (1.f / DC_CS);
+    for (int r = 0; r < CS; ++r) mean += mr[r];
+    mean *= (1.f / CS);
 #pragma unroll
-    for (int r = 0; r < DC_CS; ++r) m2 += qr[r] + 64.f * (mr[r] - mean) * (mr[r] - mean);
+    for (int r = 0; r < CS; ++r) m2 += qr[r] + (float)COLS * (mr[r] - mean) * (mr[r] - mean);
   }
   const float rs = rsqrtf(m2 * (1.f / DC_D) + eps);
-  *reinterpret_cast<uint32_t*>(dst + (size_t)s * DC_XP + c * 2) = pack2((z0 - mean) * rs * gm.x + bt.x, (z1 - mean) * rs * gm.y + bt.y);
+  bf16* drow = reinterpret_cast<bf16*>(dst + (size_t)s * DC_XP);
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) drow[c + k] = __float2bfloat16_rn((z[k] - mean) * rs * gm[k] + bt[k]);
   cluster.sync();
-  // all-gather: the 7 other column slices, 16 bytes per thread and step (8 sequences x 8 vectors per slice)
-  for (int e = tid; e < (DC_CS - 1) * 64; e += DC_THREADS) {
-    int r = e >> 6;
+  // all-gather: the other CTAs' column slices, 16 bytes per thread and step (8 sequences x COLS / 8 vectors per slice)
+  constexpr int VPR = COLS / 8;
+  for (int e = tid; e < (CS - 1) * 8 * VPR; e += DC_THREADS) {
+    int r = e / (8 * VPR);
+    const int ss = (e / VPR) & 7, v = e % VPR;
     r += (r >= rank);
-    const int ss = (e >> 3) & 7, v = e & 7;
     const unsigned char* rp = cluster.map_shared_rank(dst, r);
-    const size_t off = (size_t)ss * DC_XP + r * 128 + v * 16;
+    const size_t off = (size_t)ss * DC_XP + r * COLS * 2 + v * 16;
     *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(rp + off);
   }
   __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------ the step
-__global__ void __cluster_dims__(DC_CS, 1, 1) __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const DcArgs a) {
+// CS = CTAs per cluster: 8 (CTA = head) or 16 (two CTAs per head: both compute the head's q, each takes half of its qt columns / bd rows /
+// v features, and a 1/16 slice of everything else - half the weight bytes per SM).  Launched with the cluster dimension as an attribute.
+template <int CS>
+__global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const DcArgs a) {
+  constexpr int RPH = CS / 8;                         // CTAs per head
+  constexpr int DC_CS = CS;
   extern __shared__ __align__(128) unsigned char dc_smem[];
   __shared__ uint64_t full[DC_NST];
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int rank = (int)cluster.block_rank();
+  const int head = rank / RPH, sub = rank % RPH;
   const int cl = blockIdx.x / DC_CS;
   const int seq0 = cl * a.NS, nsc = min(a.NS, a.B - seq0);         // this cluster's sequences
   const int ML = a.ML, DS = a.di / DC_CS;                           // DS = inner features of this CTA
@@ -495,11 +511,12 @@ __global__ void __cluster_dims__(DC_CS, 1, 1) __launch_bounds__(DC_THREADS, 1) d
   };
   stamp();
   // the GEMMs of a layer (this CTA's slices) as streaming specs; each one's first two units are requested while the previous one drains
-  auto spec_q = [&](const DcLayer& ly) { return WgSpec{ly.wq + (int64_t)rank * DC_DH * DC_D, DC_D, DC_D, DC_DH, warp, DC_WARPS}; };
-  auto spec_qt = [&](const DcLayer& ly) { return WgSpec{ly.wkT + (int64_t)rank * DC_D * DC_DH, DC_DH, DC_DH, DC_D, warp, DC_WARPS}; };
-  auto spec_bd = [&](const DcLayer& ly) { return WgSpec{ly.r + rank * DC_DH, DC_D, DC_DH, ML + 1, warp, DC_WARPS}; };
-  auto spec_v = [&](const DcLayer& ly) { return WgSpec{ly.wv + (int64_t)rank * DC_DH * DC_D, DC_D, DC_D, DC_DH, warp, DC_WARPS}; };
-  auto spec_o = [&](const DcLayer& ly) { return WgSpec{ly.wo + rank * DC_DH, DC_D, DC_DH, DC_D, warp, DC_WARPS}; };
+  const int XR = (((a.ML + 1 + RPH - 1) / RPH) + 15) / 16 * 16;         // bd rows (distances) per CTA of a head
+  auto spec_q = [&](const DcLayer& ly) { return WgSpec{ly.wq + (int64_t)head * DC_DH * DC_D, DC_D, DC_D, DC_DH, warp, DC_WARPS}; };
+  auto spec_qt = [&](const DcLayer& ly) { return WgSpec{ly.wkT + ((int64_t)head * DC_D + sub * (DC_D / RPH)) * DC_DH, DC_DH, DC_DH, DC_D / RPH, warp, DC_WARPS}; };
+  auto spec_bd = [&](const DcLayer& ly) { return WgSpec{ly.r + (int64_t)sub * XR * DC_D + head * DC_DH, DC_D, DC_DH, min(XR, ML + 1 - sub * XR), warp, DC_WARPS}; };
+  auto spec_v = [&](const DcLayer& ly) { return WgSpec{ly.wv + ((int64_t)head * DC_DH + sub * (DC_DH / RPH)) * DC_D, DC_D, DC_D, DC_DH / RPH, warp, DC_WARPS}; };
+  auto spec_o = [&](const DcLayer& ly) { return WgSpec{ly.wo + head * DC_DH + sub * (DC_DH / RPH), DC_D, DC_DH / RPH, DC_D, warp, DC_WARPS}; };
   auto spec_f1 = [&](const DcLayer& ly) { return WgSpec{ly.w1 + (int64_t)rank * DS * DC_D, DC_D, DC_D, DS, warp, DC_WARPS}; };
   auto spec_f2 = [&](const DcLayer& ly) { return WgSpec{ly.w2 + rank * DS, a.di, DS, DC_D, warp, DC_WARPS}; };
   const WgSpec spec_lm = WgSpec{a.E, DC_D, DC_D, a.Vx, rank * DC_WARPS + warp, DC_CS * DC_WARPS};
@@ -513,8 +530,8 @@ __global__ void __cluster_dims__(DC_CS, 1, 1) __launch_bounds__(DC_THREADS, 1) d
     }
     // ---- 1: q_r -> qa, qb   (bias pairs of this lane's rows: r_w_bias through the hoisted slot, r_r_bias loaded next to it)
     {
-      const float* rrb = ly.rrb + rank * DC_DH;
-      warp_gemm(sm.xs, DC_XP, spec_q(ly), ly.rwb + rank * DC_DH, wring, lane, pre, [&](int tile, const float* c, float bw0, float bw1) {
+      const float* rrb = ly.rrb + head * DC_DH;
+      warp_gemm(sm.xs, DC_XP, spec_q(ly), ly.rwb + head * DC_DH, wring, lane, pre, [&](int tile, const float* c, float bw0, float bw1) {
         const int n = tile * 16 + g;
         const float br0 = rrb[n], br1 = rrb[n + 8];
         bf16* qa0 = reinterpret_cast<bf16*>(sm.qa + (size_t)(2 * t) * DC_P64); bf16* qa1 = reinterpret_cast<bf16*>(sm.qa + (size_t)(2 * t + 1) * DC_P64);
@@ -528,17 +545,17 @@ __global__ void __cluster_dims__(DC_CS, 1, 1) __launch_bounds__(DC_THREADS, 1) d
     // ---- 2: qt_r (local) and bd_r (global table)
     warp_gemm(sm.qa, DC_P64, spec_qt(ly), nullptr, wring, lane, true, [&](int tile, const float* c, float, float) {
       const int n = tile * 16 + g;
-      bf16* q0 = reinterpret_cast<bf16*>(sm.qtl) + (size_t)(2 * t) * DC_D; bf16* q1 = q0 + DC_D;
+      bf16* q0 = reinterpret_cast<bf16*>(sm.qtl) + (size_t)(2 * t) * (DC_D / RPH); bf16* q1 = q0 + DC_D / RPH;       // this CTA's columns of qt_head
       q0[n] = __float2bfloat16_rn(c[0]); q1[n] = __float2bfloat16_rn(c[1]); q0[n + 8] = __float2bfloat16_rn(c[2]); q1[n + 8] = __float2bfloat16_rn(c[3]);
     });
     wg_prefetch(spec_bd(ly), wring, lane);
     warp_gemm(sm.qb, DC_P64, spec_bd(ly), nullptr, wring, lane, true, [&](int tile, const float* c, float, float) {
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        const int x = tile * 16 + g + hf * 8;
-        if (x <= ML) {
-          if (2 * t < nsc) a.bd[((int64_t)(seq0 + 2 * t) * DC_H + rank) * a.MLP + x] = c[hf * 2];
-          if (2 * t + 1 < nsc) a.bd[((int64_t)(seq0 + 2 * t + 1) * DC_H + rank) * a.MLP + x] = c[hf * 2 + 1];
+        const int x = sub * XR + tile * 16 + g + hf * 8;
+        if (x <= ML && tile * 16 + g + hf * 8 < XR) {
+          if (2 * t < nsc) a.bd[((int64_t)(seq0 + 2 * t) * DC_H + head) * a.MLP + x] = c[hf * 2];
+          if (2 * t + 1 < nsc) a.bd[((int64_t)(seq0 + 2 * t + 1) * DC_H + head) * a.MLP + x] = c[hf * 2 + 1];
         }
       }
     });
@@ -553,10 +570,10 @@ __global__ void __cluster_dims__(DC_CS, 1, 1) __launch_bounds__(DC_THREADS, 1) d
         if (sb < se) {
           fence_proxy_async_all();                    // the stage memory held generic-proxy data (weight rings): TMA writes follow
           __syncthreads();
-          dc_attention(cluster, a, &a.tmaps[l], sm, full, uses, n_items, seq0 + it_s0, part, sb, se, cur);
+          dc_attention<CS>(cluster, a, &a.tmaps[l], sm, full, uses, n_items, seq0 + it_s0, part, sb, se, cur);
         } else if (tid < 8) {                         // an empty key part (mem_len shorter than the parts): weight 0 (its rows are never read)
           for (int k = 0; k < n_items; ++k) {
-            float* ml = a.pml + (((int64_t)(seq0 + it_s0 + k) * DC_CS + part) * DC_H + tid) * 2;
+            float* ml = a.pml + (((int64_t)(seq0 + it_s0 + k) * DC_PARTS + part) * DC_H + tid) * 2;
             ml[0] = -INFINITY; ml[1] = 0.f;
           }
         }
@@ -566,32 +583,39 @@ __global__ void __cluster_dims__(DC_CS, 1, 1) __launch_bounds__(DC_THREADS, 1) d
     wg_prefetch(spec_v(ly), wring, lane);
     cluster.sync();                                                                                          // barrier 2
     stamp();
-    // ---- 4: merge the parts of head `rank` for every sequence -> ctxA; v_r; partial_r
+    // ---- 4: merge the parts of this CTA's head for every sequence -> ctxA; v (its features of the head); partial over those features
     for (int e = tid; e < nsc * (DC_D / 8); e += DC_THREADS) {
       const int s = e / (DC_D / 8), v = e % (DC_D / 8);
-      const float* mlp = a.pml + ((int64_t)(seq0 + s) * DC_CS * DC_H + rank) * 2;
-      const bf16* cxp = a.pctx + ((int64_t)(seq0 + s) * DC_CS * DC_H + rank) * DC_D + v * 8;
-      float2 ml[DC_CS];
-      uint4 cu[DC_CS];
+      const float* mlp = a.pml + ((int64_t)(seq0 + s) * DC_PARTS * DC_H + head) * 2;
+      const bf16* cxp = a.pctx + ((int64_t)(seq0 + s) * DC_PARTS * DC_H + head) * DC_D + v * 8;
+      float lz[DC_PARTS];
+      float M = -INFINITY, Ls = 0.f;
+      {
+        float2 ml[DC_PARTS];
 #pragma unroll
-      for (int kp = 0; kp < DC_CS; ++kp) {            // every load of the vector is issued before the first use
-        ml[kp] = kp < KPC ? __ldcg(reinterpret_cast<const float2*>(mlp + (size_t)kp * DC_H * 2)) : make_float2(-INFINITY, 0.f);
-        cu[kp] = (kp < KPC && ml[kp].y > 0.f) ? __ldcg(reinterpret_cast<const uint4*>(cxp + (size_t)kp * DC_H * DC_D)) : make_uint4(0, 0, 0, 0);
+        for (int kp = 0; kp < DC_PARTS; ++kp) ml[kp] = kp < KPC ? __ldcg(reinterpret_cast<const float2*>(mlp + (size_t)kp * DC_H * 2)) : make_float2(-INFINITY, 0.f);
+#pragma unroll
+        for (int kp = 0; kp < DC_PARTS; ++kp) M = fmaxf(M, ml[kp].x);
+#pragma unroll
+        for (int kp = 0; kp < DC_PARTS; ++kp) { lz[kp] = (ml[kp].x == -INFINITY) ? 0.f : exp2f(ml[kp].x - M) * ml[kp].y; Ls += lz[kp]; }
       }
-      float M = -INFINITY;
-#pragma unroll
-      for (int kp = 0; kp < DC_CS; ++kp) M = fmaxf(M, ml[kp].x);
-      float lz[DC_CS], Ls = 0.f;
-#pragma unroll
-      for (int kp = 0; kp < DC_CS; ++kp) { lz[kp] = (ml[kp].x == -INFINITY) ? 0.f : exp2f(ml[kp].x - M) * ml[kp].y; Ls += lz[kp]; }
       const float inv = Ls > 0.f ? 1.f / Ls : 0.f;
       float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int kp = 0; kp < DC_CS; ++kp) {
-        const bf16* eb = reinterpret_cast<const bf16*>(&cu[kp]);
-        const float cf = lz[kp] * inv;
+      for (int k0 = 0; k0 < DC_PARTS; k0 += 8) {        // eight loads in flight at a time
+        if (k0 < KPC) {
+          uint4 cu[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc8[k] = fmaf(cf, __bfloat162float(eb[k]), acc8[k]);
+          for (int q = 0; q < 8; ++q)
+            cu[q] = (k0 + q < KPC && lz[k0 + q] > 0.f) ? __ldcg(reinterpret_cast<const uint4*>(cxp + (size_t)(k0 + q) * DC_H * DC_D)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const bf16* eb = reinterpret_cast<const bf16*>(&cu[q]);
+            const float cf = lz[k0 + q] * inv;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc8[k] = fmaf(cf, __bfloat162float(eb[k]), acc8[k]);
+          }
+        }
       }
       uint4 o;
       o.x = pack2(acc8[0], acc8[1]); o.y = pack2(acc8[2], acc8[3]); o.z = pack2(acc8[4], acc8[5]); o.w = pack2(acc8[6], acc8[7]);
@@ -614,7 +638,7 @@ __global__ void __cluster_dims__(DC_CS, 1, 1) __launch_bounds__(DC_THREADS, 1) d
     cluster.sync();                                                                                          // barrier 3
     stamp();
     // ---- 5: y1 = LayerNorm(x + attention output)  (barriers 4, 5)
-    dc_residual_ln(cluster, sm, sm.xs, sm.ys, nullptr, ly.ln1w, ly.ln1b, a.eps, rank);
+    dc_residual_ln<CS>(cluster, sm, sm.xs, sm.ys, nullptr, ly.ln1w, ly.ln1b, a.eps, rank);
     stamp();
     // ---- 6: h1_r
     warp_gemm(sm.ys, DC_XP, spec_f1(ly), ly.b1 + rank * DS, wring, lane, true, [&](int tile, const float* c, float b0, float b1) {
@@ -636,7 +660,7 @@ __global__ void __cluster_dims__(DC_CS, 1, 1) __launch_bounds__(DC_THREADS, 1) d
     cluster.sync();                                                                                          // barrier 6
     stamp();
     // ---- 8: x = LayerNorm(y1 + FF output + b2)  (barriers 7, 8)
-    dc_residual_ln(cluster, sm, sm.ys, sm.xs, ly.b2, ly.ln2w, ly.ln2b, a.eps, rank);
+    dc_residual_ln<CS>(cluster, sm, sm.ys, sm.xs, ly.b2, ly.ln2w, ly.ln2b, a.eps, rank);
     stamp();
   }
   // ---- LM head: the 16-row tiles of [E ; cluster_weight] round-robin over the 64 warps of the cluster; final hidden rows back to global
@@ -662,61 +686,86 @@ struct DcHostTable {
   CUtensorMap tm[64];
 };
 
-size_t dc_smem_bytes(int di) {
-  const int DS = di / DC_CS;
-  size_t n = 1024 + (size_t)DC_NST * DC_STAGE + 3 * DC_NS * DC_XP + 3 * DC_NS * DC_P64 + (size_t)DC_NS * (DS * 2 + 64) + DC_NS * DC_D * 2 + 8 * DC_QP +
-             8 * DC_QP + DC_NS * DC_D * 4 + 2 * 2 * 8 * DC_SPITCH * 4 + DC_NS * 2 * 4;
+size_t dc_smem_bytes(int di, int CS) {
+  const int DS = di / CS;
+  size_t n = 1024 + (size_t)DC_NST * DC_STAGE + 3 * DC_NS * DC_XP + 3 * DC_NS * DC_P64 + (size_t)DC_NS * (DS * 2 + 64) + DC_NS * DC_D * 2 + 2 * 8 * DC_QP +
+             DC_NS * DC_D * 4 + 2 * 2 * 8 * DC_SPITCH * 4 + DC_NS * 2 * 4;
   return n + 128;
 }
 
-int g_dc_max_clusters = 0;                          // co-resident clusters of 8 (cudaOccupancyMaxActiveClusters, set at the first step call)
-int dc_clusters(int B, int* NS) {
-  int ncl_max = g_dc_max_clusters > 0 ? g_dc_max_clusters : txl_num_sms() / DC_CS;               // (148 SMs: at most 18 clusters)
-  if (ncl_max < 1) ncl_max = 1;
+int g_dc_max_clusters[2] = {0, 0};                  // co-resident clusters of 8 / 16 CTAs (cudaOccupancyMaxActiveClusters)
+
+template <int CS>
+void dc_query_clusters(int di) {
+  int& slot = g_dc_max_clusters[CS == 16];
+  if (slot != 0) return;
+  slot = -1;
+  const size_t smem = dc_smem_bytes(di, CS);
+  if (cudaFuncSetAttribute(decode_cluster_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return; }
+  if (CS > 8 && cudaFuncSetAttribute(decode_cluster_kernel<CS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CS * (144 / CS)); cfg.blockDim = dim3(DC_THREADS); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel<CS>, &cfg) == cudaSuccess && n > 0) slot = n;
+  else cudaGetLastError();
+}
+
+bool dc_shape_ok(int di, int CS) {
+  if (di % (CS * 32) || di / CS > 512) return false;
+  const int ds = di / CS;                            // K of the CoreNet.3 slices: 32, 64 or whole 128-column units
+  if (!(ds == 32 || ds == 64 || ds % 128 == 0)) return false;
+  return dc_smem_bytes(di, CS) <= 232448;
+}
+
+// clusters and sequences per cluster for B sequences with clusters of CS CTAs; 0 if that does not fit one wave of co-resident clusters
+int dc_clusters(int B, int di, int CS, int* NS) {
+  if (!dc_shape_ok(di, CS)) return 0;
+  if (CS == 16) dc_query_clusters<16>(di); else dc_query_clusters<8>(di);
+  const int ncl_max = g_dc_max_clusters[CS == 16];
+  if (ncl_max < 1) return 0;
   int ncl = B < ncl_max ? B : ncl_max;
-  int ns = (B + ncl - 1) / ncl;
-  // spread evenly: with ns sequences per cluster fewer clusters may do
-  ncl = (B + ns - 1) / ns;
+  const int ns = (B + ncl - 1) / ncl;
+  if (ns > DC_NS) return 0;
+  ncl = (B + ns - 1) / ns;                           // with ns sequences per cluster fewer clusters may do
   *NS = ns;
   return ncl;
+}
+
+// cluster size for B sequences: TXL_DC_CS forces 8 or 16; otherwise 16 CTAs per cluster (half the weight bytes per SM: the bound of small
+// batches) whenever one wave of them holds the batch, else 8
+int dc_pick(int B, int di, int* NS, int* ncl) {
+  static const int forced = [] { const char* e = getenv("TXL_DC_CS"); return e ? atoi(e) : 0; }();
+  for (int CS : {16, 8}) {
+    if (forced && forced != CS) continue;
+    const int n = dc_clusters(B, di, CS, NS);
+    if (n > 0) { *ncl = n; return CS; }
+  }
+  return 0;
 }
 }  // namespace
 
 static unsigned long long* g_dc_tstamp = nullptr;
 extern "C" int txl_decode_cluster_set_timestamps(unsigned long long* dev_buf) { g_dc_tstamp = dev_buf; return TXL_OK; }
-
-static void dc_query_clusters(int di) {
-  if (g_dc_max_clusters > 0) return;
-  const size_t smem = dc_smem_bytes(di);
-  if (cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return; }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(DC_CS * 18); cfg.blockDim = dim3(DC_THREADS); cfg.dynamicSmemBytes = smem;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = DC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel, &cfg) == cudaSuccess && n > 0) g_dc_max_clusters = n;
-  else cudaGetLastError();
+extern "C" int txl_decode_cluster_max_clusters(int di) {
+  if (dc_shape_ok(di, 8)) dc_query_clusters<8>(di);
+  if (dc_shape_ok(di, 16)) dc_query_clusters<16>(di);
+  return (g_dc_max_clusters[0] > 0 ? g_dc_max_clusters[0] : 0) + 100 * (g_dc_max_clusters[1] > 0 ? g_dc_max_clusters[1] : 0);
 }
-extern "C" int txl_decode_cluster_max_clusters(int di) { dc_query_clusters(di); return g_dc_max_clusters; }
 
 extern "C" int txl_decode_cluster_supported(int B, int H, int dh, int d, int di, int ML, int L, int Vx) {
   if (!(B >= 1 && H == DC_H && dh == DC_DH && d == DC_D && ML >= 1 && L >= 1 && L <= 64 && Vx >= 1)) return 0;
-  if (di % (DC_CS * 32) || di / DC_CS > 512) return 0;
-  { const int ds = di / DC_CS; if (!(ds == 32 || ds == 64 || ds % 128 == 0)) return 0; }      // K of the CoreNet.3 slices: 32, 64 or whole 128-column units
-  if (dc_smem_bytes(di) > 232448) return 0;
-  dc_query_clusters(di);
-  int ns;
-  dc_clusters(B, &ns);
-  if (ns > DC_NS) return 0;
-  return dc_smem_bytes(di) <= 232448 ? 1 : 0;
+  int ns, ncl;
+  return dc_pick(B, di, &ns, &ncl) != 0 ? 1 : 0;
 }
 
 extern "C" int64_t txl_decode_cluster_ws_bytes(int B, int H, int dh, int d, int di, int ML, int L, int Vx) {
   if (!txl_decode_cluster_supported(B, H, dh, d, di, ML, L, Vx)) return 0;
   const int MLP = (ML + 1 + 3) / 4 * 4;
-  return (int64_t)sizeof(DcHostTable) + 256 + (int64_t)B * H * MLP * 4 + 256 + (int64_t)B * DC_CS * H * d * 2 + 256 + (int64_t)B * DC_CS * H * 2 * 4 + 256;
+  return (int64_t)sizeof(DcHostTable) + 256 + (int64_t)B * H * MLP * 4 + 256 + (int64_t)B * DC_PARTS * H * d * 2 + 256 + (int64_t)B * DC_PARTS * H * 2 * 4 + 256;
 }
 
 // One decode step of all layers + the LM-head GEMM by clusters of 8 CTAs.  build_table = 1: upload the per-layer pointer table and the ring
@@ -728,7 +777,7 @@ extern "C" int txl_decode_cluster_step(const void* const* wqkv, const void* cons
                                        void* x, const int32_t* pos, float* logits, int64_t ldl, void* ws, int build_table, int B, int H, int dh, int d,
                                        int di, int ML, int L, int Vx, float eps, void* stream) {
   TXL_CHECK_ARG(txl_decode_cluster_supported(B, H, dh, d, di, ML, L, Vx),
-                "decode_cluster: unsupported geometry (needs 8 heads of 64, d_model 512, d_inner a multiple of 256 up to 4096, B <= 8 x (SMs / 8))");
+                "decode_cluster: unsupported geometry (needs 8 heads of 64, d_model 512, d_inner a multiple of 256 up to 4096, B <= 8 x co-resident clusters)");
   TXL_CHECK_ARG(ws && ((uintptr_t)ws & 255) == 0, "decode_cluster: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int MLP = (ML + 1 + 3) / 4 * 4;
@@ -738,7 +787,7 @@ extern "C" int txl_decode_cluster_step(const void* const* wqkv, const void* cons
   float* bd = (float*)w;
   w += ((int64_t)B * H * MLP * 4 + 255) / 256 * 256;
   bf16* pctx = (bf16*)w;
-  w += ((int64_t)B * DC_CS * H * d * 2 + 255) / 256 * 256;
+  w += ((int64_t)B * DC_PARTS * H * d * 2 + 255) / 256 * 256;
   float* pml = (float*)w;
   if (build_table) {
     TXL_CHECK_ARG(wqkv && wkT && wo && w1 && w2 && rtab && b1 && b2 && rwb && rrb && ln1w && ln1b && ln2w && ln2b && ring, "decode_cluster: null table");
@@ -766,15 +815,32 @@ extern "C" int txl_decode_cluster_step(const void* const* wqkv, const void* cons
   a.layers = tab->layers; a.tmaps = tab->tm; a.E = (const bf16*)E; a.out_bias = out_bias; a.x = (bf16*)x; a.bd = bd; a.pctx = pctx; a.pml = pml; a.logits = logits; a.pos = pos;
   a.tstamp = g_dc_tstamp; a.ldl = ldl; a.B = B; a.ML = ML; a.MLP = MLP; a.L = L; a.Vx = Vx; a.di = di;
   a.eps = eps; a.scale_log2 = 1.4426950408889634f / sqrtf((float)dh);
-  static const int hints = [] { const char* e = getenv("TXL_DC_HINTS"); return e ? atoi(e) : 2; }();
-  a.hints = hints;
-  const int ncl = dc_clusters(B, &a.NS);
-  const size_t smem = dc_smem_bytes(di);
-  static size_t attr[64] = {0};
+  a.hints = 2;
+  int ncl = 0;
+  const int CS = dc_pick(B, di, &a.NS, &ncl);
+  TXL_CHECK_ARG(CS != 0, "decode_cluster: no cluster configuration holds %d sequences in one wave", B);
+  const size_t smem = dc_smem_bytes(di, CS);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ncl * CS); cfg.blockDim = dim3(DC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  // the occupancy query set the function attributes for the d_inner it was first asked about: grow the shared-memory size when needed
+  static size_t attr[2][64] = {{0}, {0}};
   int dev = 0;
   TXL_CUDA(cudaGetDevice(&dev));
-  if (smem > attr[dev & 63]) { TXL_CUDA(cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[dev & 63] = smem; }
-  decode_cluster_kernel<<<dim3((unsigned)ncl * DC_CS), dim3(DC_THREADS), smem, st>>>(a);
+  if (smem > attr[CS == 16][dev & 63]) {
+    if (CS == 16) {
+      TXL_CUDA(cudaFuncSetAttribute(decode_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TXL_CUDA(cudaFuncSetAttribute(decode_cluster_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    } else {
+      TXL_CUDA(cudaFuncSetAttribute(decode_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    attr[CS == 16][dev & 63] = smem;
+  }
+  if (CS == 16) { TXL_CUDA(cudaLaunchKernelEx(&cfg, decode_cluster_kernel<16>, a)); }
+  else { TXL_CUDA(cudaLaunchKernelEx(&cfg, decode_cluster_kernel<8>, a)); }
   TXL_LAUNCH_CHECK();
   return TXL_OK;
 }

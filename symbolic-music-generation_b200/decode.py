@@ -60,12 +60,15 @@ def persist_supported(model, B):
 
 _CLUSTER = os.environ.get('TXL_DECODE_CLUSTER', '1') != '0'
 CL_MAXB = 64       # sequences per chain of the cluster engine: 8 per cluster x the co-resident clusters of 8 SMs (>= 8 on a B200)
+# The cluster engine is the default up to this many sequences per GPU (measured, profiles/r02_decode_ab.txt: 378 vs 416 us/step at 8 sequences,
+# 412 vs 414 at 16; at 32 / 64 the launch chain with sequence groups still wins: 515 vs 422, 624 vs 543).  TXL_DECODE_CLUSTER_MAXB overrides.
+CL_AUTO_MAXB = int(os.environ.get('TXL_DECODE_CLUSTER_MAXB', '16'))
 
 
 def cluster_supported(model, B):
     """The cluster engine (csrc/decode_cluster.cu: 8-CTA clusters, one per attention head, DSMEM hand-over) takes this model and `B` sequences."""
     cfg = model.config
-    if not _CLUSTER or model._E.dtype != torch.bfloat16 or not cfg.same_length or cfg.mem_len <= 0:
+    if not _CLUSTER or B > CL_AUTO_MAXB or model._E.dtype != torch.bfloat16 or not cfg.same_length or cfg.mem_len <= 0:
         return False
     Vx = cfg.vocab_size + len(getattr(cfg, 'cutoffs', []) or [])
     return bool(load().txl_decode_cluster_supported(int(B), cfg.n_head, cfg.d_head, cfg.d_model, cfg.d_inner, cfg.mem_len, cfg.n_layer, Vx))
@@ -127,11 +130,9 @@ def sequence_groups(model, B, requested=None):
     """How many independent sequence groups generate() decodes as parallel graph branches (GroupedDecoder).  bf16 second-generation path only."""
     if requested is None:
         requested = int(os.environ.get('TXL_DECODE_GROUPS', '0')) or None
-    if hasattr(model, '_W'):
-        nc = (B + CL_MAXB - 1) // CL_MAXB
-        if cluster_supported(model, (B + nc - 1) // nc):
-            # clusters of 8 SMs own their sequences end to end: one chain per 144 sequences, no sequence groups
-            return max(nc, min(int(requested), B)) if requested is not None else nc
+    if hasattr(model, '_W') and cluster_supported(model, B):
+        # clusters own their sequences end to end: one chain, no sequence groups
+        return max(1, min(int(requested), B)) if requested is not None else 1
     need = (B + SK_MAXM - 1) // SK_MAXM              # a Decoder (one chain of kernels) takes at most SK_MAXM sequences
     if hasattr(model, '_W') and persist_supported(model, (B + need - 1) // need):
         # the persistent step occupies every SM: sequence groups would only serialise, so as few chains as the 64-row limit allows

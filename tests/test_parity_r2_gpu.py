@@ -119,10 +119,26 @@ def test_decode_step_bf16_vs_oracle(pkg, mem_len, dh, H):
     assert worst < 1e-2, worst
 
 
-def test_decode_cfg4_shape_bf16_vs_oracle(pkg):
-    """BASELINE configs[3] shape: 64 sequences, 12 layers, d_model 512, mem_len 1024, bf16; 32 decode steps vs the oracle (TXL_TEST_FAST=1: 6)."""
+@pytest.mark.parametrize('B', [64, 8, 5])
+def test_decode_cfg4_shape_bf16_vs_oracle(pkg, B):
+    """BASELINE configs[3] shape: 12 layers, d_model 512, mem_len 1024, bf16, with 64 sequences (one GPU), 8 (the per-GPU share of the 8-GPU run:
+    clusters of 16 CTAs) and 5 (a count that does not divide the cluster: 8 / 16 key parts per sequence); 32 decode steps vs the oracle
+    (TXL_TEST_FAST=1: 6)."""
     ref, model = make_pair(pkg, 'bf16', vocab_size=1190, d_model=512, n_head=8, d_head=64, d_inner=2048, n_layer=12, mem_len=1024, clamp_len=1024)
-    worst = _decode_vs_oracle(pkg, ref, model, 64, 16, 6 if FAST else 32, 1190, 1e-2)
+    worst = _decode_vs_oracle(pkg, ref, model, B, 16, 6 if FAST else (32 if B == 64 else 12), 1190, 1e-2)
+    assert worst < 1e-2, worst
+
+
+@pytest.mark.parametrize('engine', ['cluster', 'persist'])
+def test_decode_one_kernel_engines_64_sequences_vs_oracle(pkg, engine, monkeypatch):
+    """The two one-kernel engines at 64 sequences (where the launch chain is the default): the cluster engine (13 clusters of 8 CTAs x 5
+    sequences) and the grid-barrier engine, cfg4 shape, against the oracle."""
+    decode = importlib.import_module('symbolic-music-generation_b200.decode')
+    monkeypatch.setattr(decode, 'CL_AUTO_MAXB', 64 if engine == 'cluster' else 0)
+    monkeypatch.setattr(decode, '_PERSIST', engine == 'persist')
+    ref, model = make_pair(pkg, 'bf16', vocab_size=1190, d_model=512, n_head=8, d_head=64, d_inner=2048, n_layer=12, mem_len=1024, clamp_len=1024)
+    assert decode.cluster_supported(model, 64) == (engine == 'cluster') and decode.persist_supported(model, 64) == (engine == 'persist')
+    worst = _decode_vs_oracle(pkg, ref, model, 64, 16, 4 if FAST else 10, 1190, 1e-2)
     assert worst < 1e-2, worst
 
 
