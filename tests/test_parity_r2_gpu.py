@@ -137,6 +137,7 @@ def test_decode_one_kernel_engines_64_sequences_vs_oracle(pkg, engine, monkeypat
     monkeypatch.setattr(decode, 'CL_AUTO_MAXB', 64 if engine == 'cluster' else 0)
     monkeypatch.setattr(decode, '_PERSIST', engine == 'persist')
     ref, model = make_pair(pkg, 'bf16', vocab_size=1190, d_model=512, n_head=8, d_head=64, d_inner=2048, n_layer=12, mem_len=1024, clamp_len=1024)
+    model._ensure_engine()
     assert decode.cluster_supported(model, 64) == (engine == 'cluster') and decode.persist_supported(model, 64) == (engine == 'persist')
     worst = _decode_vs_oracle(pkg, ref, model, 64, 16, 4 if FAST else 10, 1190, 1e-2)
     assert worst < 1e-2, worst
