@@ -435,19 +435,29 @@ def decode_probe(torch, pkg, pdist, cfg_train, args, dev, rank, world):
         ms = float(t.item())
     assert out.shape == (Bl, 16 + args.decode_new)
     peaks = measured_peaks()
-    n_groups = importlib.import_module(PKG + '.decode').sequence_groups(model, Bl)
+    dmod = importlib.import_module(PKG + '.decode')
+    n_groups = dmod.sequence_groups(model, Bl)
+    if dmod.cluster_supported(model, Bl):
+        engine = ('cluster engine: one kernel per step, thread-block clusters (CTA = attention head) carry their sequences through all layers, DSMEM '
+                  'hand-over, hidden-state ring with absorbed K/V projections; + the sampling tail kernel; CUDA-graph replay')
+        ring_note = 'the ring that is read IS the hidden-state mems (1x the mems term); every cluster streams the weights from L2'
+    elif dmod.persist_supported(model, Bl):
+        engine = 'persistent cooperative kernel with grid barriers over the hidden-state ring; + the sampling tail kernel; CUDA-graph replay'
+        ring_note = 'the ring that is read IS the hidden-state mems (1x the mems term)'
+    else:
+        engine = (f'launch chain: projected-K/V ring cache, CUDA-graph step with {n_groups} sequence group(s) as parallel branches, programmatic '
+                  'dependent launch')
+        ring_note = 'the K/V cache actually read is 2x the mems term'
     L, M, d = cfg.n_layer, cfg.mem_len, cfg.d_model
     n_params = sum(p.numel() for p in model.parameters())
     step_bytes = Bl * L * M * d * 2 + n_params * 2 + L * M * d * 2        # hidden-state mems + weights + R tables, bf16
     ms_step = ms / args.decode_new
     ach = step_bytes / (ms_step / 1e3) / 1e9
     return {'metric': 'TXL decode tokens/s', 'value': args.decode_seqs * args.decode_new / (ms / 1e3), 'unit': 'tokens/s', 'ms_per_token_step': ms_step,
-            'config': {'workload': f'cfg4: {args.decode_seqs} sequences ({Bl} per GPU), prompt 16, {args.decode_new} new tokens, top_k 8, mem_len {M}, '
-                                   f'projected-K/V ring cache, CUDA-graph step with {n_groups} sequence group(s) as parallel branches, '
-                                   'programmatic dependent launch'},
+            'config': {'workload': f'cfg4: {args.decode_seqs} sequences ({Bl} per GPU), prompt 16, {args.decode_new} new tokens, top_k 8, mem_len {M}, ' + engine},
             'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': ach / peaks['hbm'], 'traffic': None,
                          'algorithmic_bytes_per_step': step_bytes,
-                         'note': 'denominator bytes = hidden-state mems once + weights + R tables (SURVEY §8d); the K/V cache actually read is 2x the mems term'}}
+                         'note': 'denominator bytes = hidden-state mems once + weights + R tables (SURVEY §8d); ' + ring_note}}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dQ pass (ncu --set full, cfg2 shape, 32 sequences)

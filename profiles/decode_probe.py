@@ -40,6 +40,8 @@ if os.environ.get('PROBE_STAGES'):
         k = n.split('.')[-1]
         agg[k] = agg.get(k, 0) + v
     print('engine:', 'cluster' if cluster else 'persistent', ' layer 5 stages (us):', {n: round(v, 2) for n, v in zip(names, d) if n.startswith('L5.')})
+    if cluster:
+        print('LN1 of the last layer on CTA 0 (ns): pull partials + slice statistics', t[131] - t[130], ' barrier', t[132] - t[131], ' pull statistics + normalise', t[133] - t[132], ' barrier', t[134] - t[133], ' all-gather', t[135] - t[134])
     print('one-kernel step, stage times of CTA 0 summed over layers (us):', {k: round(v, 1) for k, v in agg.items()}, 'total', round(sum(d), 1))
     if cluster:
         print('co-resident clusters of 8 CTAs:', lib.txl_decode_cluster_max_clusters(cfg.d_inner))

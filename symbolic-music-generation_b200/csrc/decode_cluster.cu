@@ -392,8 +392,10 @@ __device__ void dc_attention(cg::cluster_group& cluster, const DcArgs& a, const 
 // statl; barrier; combined statistics (Chan) -> normalise -> its slice of `dst` (local); barrier; all-gather of the other slices (pulled).
 template <int CS>
 __device__ void dc_residual_ln(cg::cluster_group& cluster, const DcSmem& sm, unsigned char* res, unsigned char* dst, const float* bias, const float* gamma,
-                               const float* beta, float eps, int rank) {
-  constexpr int COLS = DC_D / CS, CPL = COLS / 32;                 // columns per CTA, per lane (2 or 1)
+                               const float* beta, float eps, int rank, unsigned long long* ts = nullptr) {
+  constexpr int COLS = DC_D / CS, CPL = COLS / 32;
+  auto tick = [&](int k) { if (ts && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); ts[k] = tt; } };
+  tick(0);                 // columns per CTA, per lane (2 or 1)
   const int tid = threadIdx.x, lane = tid & 31, s = tid >> 5;      // one warp per sequence
   const int c = rank * COLS + lane * CPL;
   float gm[2] = {0.f, 0.f}, bt[2] = {0.f, 0.f}, bs[2] = {0.f, 0.f}, z[2] = {0.f, 0.f};
@@ -415,7 +417,9 @@ __device__ void dc_residual_ln(cg::cluster_group& cluster, const DcSmem& sm, uns
   const float mj = warp_sum(CPL == 2 ? z[0] + z[1] : z[0]) * (1.f / COLS);
   const float m2j = warp_sum(CPL == 2 ? (z[0] - mj) * (z[0] - mj) + (z[1] - mj) * (z[1] - mj) : (z[0] - mj) * (z[0] - mj));
   if (lane == 0) { sm.statl[s * 2] = mj; sm.statl[s * 2 + 1] = m2j; }
+  tick(1);
   cluster.sync();
+  tick(2);
   float mean = 0.f, m2 = 0.f;
   {
     float mr[CS], qr[CS];
@@ -434,7 +438,9 @@ __device__ void dc_residual_ln(cg::cluster_group& cluster, const DcSmem& sm, uns
   bf16* drow = reinterpret_cast<bf16*>(dst + (size_t)s * DC_XP);
 #pragma unroll
   for (int k = 0; k < CPL; ++k) drow[c + k] = __float2bfloat16_rn((z[k] - mean) * rs * gm[k] + bt[k]);
+  tick(3);
   cluster.sync();
+  tick(4);
   // all-gather: the other CTAs' column slices, 16 bytes per thread and step (8 sequences x COLS / 8 vectors per slice)
   constexpr int VPR = COLS / 8;
   for (int e = tid; e < (CS - 1) * 8 * VPR; e += DC_THREADS) {
@@ -446,6 +452,7 @@ __device__ void dc_residual_ln(cg::cluster_group& cluster, const DcSmem& sm, uns
     *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(rp + off);
   }
   __syncthreads();
+  tick(5);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------ the step
@@ -638,7 +645,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_cluster_kernel(const DcA
     cluster.sync();                                                                                          // barrier 3
     stamp();
     // ---- 5: y1 = LayerNorm(x + attention output)  (barriers 4, 5)
-    dc_residual_ln<CS>(cluster, sm, sm.xs, sm.ys, nullptr, ly.ln1w, ly.ln1b, a.eps, rank);
+    dc_residual_ln<CS>(cluster, sm, sm.xs, sm.ys, nullptr, ly.ln1w, ly.ln1b, a.eps, rank, (a.tstamp && l == a.L - 1) ? a.tstamp + 130 : nullptr);
     stamp();
     // ---- 6: h1_r
     warp_gemm(sm.ys, DC_XP, spec_f1(ly), ly.b1 + rank * DS, wring, lane, true, [&](int tile, const float* c, float b0, float b1) {

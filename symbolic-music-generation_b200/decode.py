@@ -424,6 +424,7 @@ class GroupedDecoder:
             lo = hi
         # the other groups keep the chip busy while one group's attention kernel runs: no ring splits (4 splits: 727.6 us/step, none: 546.0)
         kw.setdefault('attn_splits', 1)
+        kw.setdefault('persist', False)       # sequence groups are the launch chain's way to fill the chip: its sub-decoders never pick a one-kernel engine
         self.decs = [Decoder(model, _BmSlice(bm, lo, hi), out_ids[lo:hi], col0, seq_offset=seq_offset + lo, **kw) for lo, hi in self.bounds]
         self.eos = self.decs[0].eos
         self.use_graph = self.decs[0].use_graph
