@@ -106,6 +106,15 @@ int txl_gemm(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_
 int txl_add_ln_fwd(const void* x, const void* r, const float* gamma, const float* beta, void* y, void* z,
                    float* mean, float* rstd, int64_t rows, int d, float eps, int dtype,
                    float drop_p, uint64_t seed, uint32_t site, void* stream);
+/* Linear + dropout + residual + LayerNorm in one tensor-core kernel (bf16): y = LN(resid + dropout(A W^T + bias)) * gamma + beta, the
+ * o_net -> layer_norm tail of RelPartialLearnableMultiHeadAttn and the CoreNet.3 -> layer_norm tail of PositionwiseFF  [A.3 step 8, A.6].
+ * A [M, K] (row pitch lda), W [N, K] (row pitch ldw), resid / y / z [M, N] contiguous; the accumulator is not rounded before the add.
+ * z (the LayerNorm input), mean, rstd: what txl_add_ln_bwd reads — all three or none (evaluation).  Same dropout site indexing as
+ * txl_add_ln_fwd.  *handled = 0 (and nothing launched) when the shape is not covered (N not 256 / 512, M < 256, fp32 mode, TXL_GEMM_LN=0):
+ * the caller then runs txl_gemm + txl_add_ln_fwd. */
+int txl_gemm_add_ln_fwd(const void* A, const void* W, const float* bias, const void* resid, const float* gamma, const float* beta,
+                        void* y, void* z, float* mean, float* rstd, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldw,
+                        float eps, float drop_p, uint64_t seed, uint32_t site, void* stream, int* handled);
 /* dyt = dy (+ dy2 if non-NULL: the two branches that meet at a residual node);  dz = LN'(dyt);
  * dgamma += sum dyt*xhat; dbeta += sum dyt.   dx_out = dz (+ dx_out if accumulate);  dr_out = dz * dropout-mask.  dx_out may alias dy. */
 int txl_add_ln_bwd(const void* dy, const void* dy2, const void* z, const float* gamma, const float* mean, const float* rstd,

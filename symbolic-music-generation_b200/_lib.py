@@ -49,6 +49,7 @@ SIGNATURES = {
     'txl_posemb_table': (_i, [_vp, _i, _i, _i, _i, _f, _u64, _u32, _vp]),
     'txl_gemm': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i, _i, _i, _i, C.POINTER(TxlEpilogue), _vp]),
     'txl_add_ln_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _i, _f, _u64, _u32, _vp]),
+    'txl_gemm_add_ln_fwd': (_i, [_vp] * 10 + [_i64] * 5 + [_f, _f, _u64, _u32, _vp, _vp]),
     'txl_add_ln_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _i, _f, _u64, _u32, _vp]),
     'txl_colsum': (_i, [_vp, _i64, _i64, _i64, _i, _vp, _vp]),
     'txl_dropout': (_i, [_vp, _vp, _i64, _i, _f, _u64, _u32, _vp]),

@@ -142,6 +142,14 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* r) {
       : "memory");
 }
 
+// 32 lanes x 8 consecutive 32-bit columns, registers -> TMEM (thread t writes row lane base + t); pair with tmem_st_wait before the data is re-read
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ------------------------------------------------------------------ UMMA descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp)
 // Shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell).
 //   K-major  tile (rows x 64 bf16, 128-byte rows, 8-row atoms of 1024 B): LBO unused (1), SBO = 1024 B

@@ -101,11 +101,17 @@ struct GemmParams {
   int tiles_m, tiles_n, ksplits, nkb, kb_per_split;
   int a_mn, b_mn;
   int tma_store;
+  // LN > 0 (fused dropout + residual + LayerNorm epilogue): y = LN(resid + dropout(A W^T + bias)), z = the LayerNorm input
+  const bf16* resid;
+  const float *gamma, *beta;
+  float *mean, *rstd;
+  float eps;
+  int store_z;
 };
 
 // CG = 2: a CTA pair (cluster of two CTAs on one TPC) computes one 256 x BN tile with tcgen05.mma.cta_group::2 — each CTA stages its
 // own 128 rows of A and HALF of the B tile, so every byte pulled from L2 feeds twice the MMA work; the leader CTA (rank 0) issues.
-template <int BN, int STAGES, int CG = 1, int EG = 2>
+template <int BN, int STAGES, int CG = 1, int EG = 2, int LN = 0>
 struct Cfg {
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -114,8 +120,10 @@ struct Cfg {
   // one buffer every 64-column block waits out a full store; the pair kernel has the room for two
   static constexpr int NCST = (CG == 2 && EG == 2) ? 2 : 1;
   static constexpr int BAR_OFF = CSTAGE_OFF + EG * NCST * STAGE_C_BYTES;
-  static constexpr int SMEM = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr int PART_OFF = BAR_OFF + 256;                     // LN: per-row partial sums of the epilogue groups, [2][EG][128] fp32
+  static constexpr int SMEM = LN ? PART_OFF + 2 * EG * BM * 4 + 1024 : BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
+  static_assert((2 * STAGES + 4) * 8 + 16 <= 256, "barrier block overlaps the LN partial sums");
 };
 
 // butterfly transpose-reduce: on return v[0] of lane l holds sum over the warp's 32 rows of column l (31 shuffles)
@@ -184,10 +192,217 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
 }
 
-template <int BN, int STAGES, typename TC, int CG, int EG>
+// ---- fused dropout + residual + LayerNorm epilogue (LN column tiles of BN columns = the whole output row).
+// Thread (group g, lane quadrant q, lane) owns row 32q + lane of the CTA's 128 rows and, in every column tile, the 64-column block g.
+// Pass 1 (per column tile, as soon as its accumulator is complete — the MMAs of the next tile run meanwhile):
+//   z = round_bf16(resid + dropout(acc + bias)), row sum.  The bf16 z of the row has to wait for the row statistics, and 96 registers per
+//   thread (18 warps) cannot hold it: the first of two tiles parks its z block in the group's staging buffer (where its TMA store reads
+//   it anyway) and returns its accumulator at once; the LAST tile writes its packed z back into the first 32 of the 64 TMEM columns it has
+//   just read (tcgen05.st) and returns the accumulator after pass 2 — by then the MMAs of the next row block are still in the other buffer.
+// The EG groups meet in shared memory for the mean and once more for the centred second moment (the two-pass statistics of
+// add_ln_fwd_kernel); pass 2 turns z into y = (z - mean) rstd gamma + beta block by block through the staging buffer -> TMA stores.
+template <int BN, int CG, int EG, int LN, typename C_>
+__device__ __forceinline__ void ln_epilogue(const GemmParams& p, const CUtensorMap& tmZ, const CUtensorMap& tmY, uint8_t* sm, uint64_t* tfull, uint64_t* tempty,
+                                            uint32_t tmem_base, uint32_t cta_rank, int unit0, int unit_step, int q, int grp, int lane, bool leader, uint8_t* cst) {
+  static_assert(BN == 64 * EG && (LN == 1 || LN == 2), "one 64-column block per epilogue group and column tile; one tile may wait in the staging buffer");
+  const int r_in_tile = q * 32 + lane;
+  const TxlEpilogue& e = p.epi;
+  float* part = reinterpret_cast<float*>(sm + C_::PART_OFF);
+  const uint32_t dkey = dropout_key(e.seed, e.site);
+  const uint32_t dthr = dropout_threshold(e.drop_p);
+  const bool drop = (e.flags & TXL_EPI_DROPOUT) != 0;
+  const float inv_n = 1.f / (float)p.N;
+  uint8_t* const crow = cst + r_in_tile * 128;                      // this thread's 128-byte row of the staging block (16-byte chunks swizzled by row)
+  const int sw = r_in_tile & 7;
+  const uint32_t tm_mine = tmem_base + grp * 64 + ((uint32_t)(q * 32) << 16);      // this thread's lane, its group's 64 columns of accumulator 0
+  auto stage_wait = [&]() { if (leader) tma_store_wait_read<0>(); named_bar_sync(1 + grp, 128); };          // the last TMA store has read the staging buffer
+  auto stage_store = [&](const CUtensorMap* m, int col, int row) {                                            // staging buffer -> global (rows >= M clipped)
+    fence_proxy_async_smem();
+    named_bar_sync(1 + grp, 128);
+    if (leader) { tma_store_2d(m, cst, col, row); tma_store_commit(); }
+  };
+  auto release = [&](int acc) {        // whole warp: its reads (and writes) of this accumulator are done
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[acc]), 0)); else mbar_arrive(&tempty[acc]); }
+  };
+  int it = 0;
+  for (int tm = unit0; tm < p.tiles_m; tm += unit_step) {
+    const int64_t row0 = (int64_t)tm * (BM * CG) + (int64_t)cta_rank * BM;
+    const int64_t row = row0 + r_in_tile;
+    const bool row_ok = row < p.M;
+    float s = 0.f;
+    int acc_last = 0;
+#pragma unroll
+    for (int tn = 0; tn < LN; ++tn, ++it) {
+      const bool in_tmem = tn == LN - 1;
+      const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+      const int blk_col0 = tn * BN + grp * 64;
+      acc_last = acc;
+      // this thread's 64 residual values of the block: requested before the accumulator is waited for, so the global-load latency
+      // hides behind the MMAs instead of sitting in front of every 16-column step
+      uint4 rxa[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) rxa[c] = make_uint4(0, 0, 0, 0);
+      if (row_ok) {
+        const uint4* xr = reinterpret_cast<const uint4*>(p.resid + row * p.N + blk_col0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) rxa[c] = __ldg(xr + c);
+      }
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      if (!in_tmem) stage_wait();
+#pragma unroll
+      for (int qt = 0; qt < 4; ++qt) {                  // 16 columns at a time
+        const int col0 = blk_col0 + qt * 16;
+        const uint4* rx = rxa + 2 * qt;
+        float v[16];
+        tmem_ld_32x16(tm_mine + acc * BN + qt * 16, v);
+        tmem_ld_wait();
+        if (!in_tmem && qt == 3) release(acc);
+        if (e.bias) {
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + g4 * 4));
+            v[g4 * 4] += b4.x; v[g4 * 4 + 1] += b4.y; v[g4 * 4 + 2] += b4.z; v[g4 * 4 + 3] += b4.w;
+          }
+        }
+        if (drop) {
+          const uint64_t base_idx = (uint64_t)row * (uint64_t)p.N + (uint64_t)col0;
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const uint32_t hsh = dropout_hash(dkey, (base_idx + i) >> 1);
+            v[i] *= (hsh & 0xFFFFu) >= dthr ? p.inv_keep : 0.f;
+            v[i + 1] *= (hsh >> 16) >= dthr ? p.inv_keep : 0.f;
+          }
+        }
+        uint32_t zw[8];
+        const uint32_t xw[8] = {rx[0].x, rx[0].y, rx[0].z, rx[0].w, rx[1].x, rx[1].y, rx[1].z, rx[1].w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float z0 = __uint_as_float(xw[k] << 16) + v[2 * k];
+          const float z1 = __uint_as_float(xw[k] & 0xFFFF0000u) + v[2 * k + 1];
+          __nv_bfloat162 zz = __floats2bfloat162_rn(z0, z1);
+          const uint32_t w = row_ok ? *reinterpret_cast<uint32_t*>(&zz) : 0u;
+          zw[k] = w;
+          s += __uint_as_float(w << 16) + __uint_as_float(w & 0xFFFF0000u);
+        }
+        if (in_tmem) {
+          tmem_st_32x8(tm_mine + acc * BN + qt * 8, zw);          // columns 8 qt .. 8 qt + 7: their accumulator values were read in steps <= qt
+        } else {
+          *reinterpret_cast<uint4*>(crow + (((qt * 2) ^ sw) << 4)) = make_uint4(zw[0], zw[1], zw[2], zw[3]);
+          *reinterpret_cast<uint4*>(crow + (((qt * 2 + 1) ^ sw) << 4)) = make_uint4(zw[4], zw[5], zw[6], zw[7]);
+        }
+      }
+      if (in_tmem) tmem_st_wait();
+      else if (p.store_z) stage_store(&tmZ, blk_col0, (int)row0);
+    }
+    // ---- row statistics across the EG groups
+    part[grp * BM + r_in_tile] = s;
+    named_bar_sync(6, EG * 128);
+    float mu = 0.f;
+#pragma unroll
+    for (int g = 0; g < EG; ++g) mu += part[g * BM + r_in_tile];
+    mu *= inv_n;
+    float qs = 0.f;
+    const uint32_t tm_z = tm_mine + acc_last * BN;        // the last tile's packed z: 32 TMEM columns
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      float zf[16];
+      tmem_ld_32x16(tm_z + hb * 16, zf);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t w = __float_as_uint(zf[i]);
+        const float a = __uint_as_float(w << 16) - mu, b = __uint_as_float(w & 0xFFFF0000u) - mu;
+        qs = fmaf(a, a, qs); qs = fmaf(b, b, qs);
+      }
+    }
+    if (LN == 2) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(crow + ((c ^ sw) << 4));
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = __uint_as_float(w4[k] << 16) - mu, b = __uint_as_float(w4[k] & 0xFFFF0000u) - mu;
+          qs = fmaf(a, a, qs); qs = fmaf(b, b, qs);
+        }
+      }
+    }
+    part[(EG + grp) * BM + r_in_tile] = qs;
+    named_bar_sync(6, EG * 128);
+    float var = 0.f;
+#pragma unroll
+    for (int g = 0; g < EG; ++g) var += part[(EG + g) * BM + r_in_tile];
+    const float rs = rsqrtf(var * inv_n + p.eps);
+    if (grp == 0 && row_ok && p.mean) { p.mean[row] = mu; p.rstd[row] = rs; }
+    // ---- pass 2: y = (z - mu) rstd gamma + beta, one 64-column block at a time through the staging buffer
+    auto norm8 = [&](const uint32_t* zw, int col, uint32_t* yw) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + col + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float y0 = (__uint_as_float(zw[k] << 16) - mu) * rs * gm[2 * k] + bt[2 * k];
+        const float y1 = (__uint_as_float(zw[k] & 0xFFFF0000u) - mu) * rs * gm[2 * k + 1] + bt[2 * k + 1];
+        __nv_bfloat162 yy = __floats2bfloat162_rn(y0, y1);
+        yw[k] = *reinterpret_cast<uint32_t*>(&yy);
+      }
+    };
+    // last tile: packed z back from TMEM, then the accumulator goes back to the MMA warp (before the y stores: the next row block's
+    // second tile is waiting for it)
+    uint32_t zp[32];
+    {
+      float* zf = reinterpret_cast<float*>(zp);
+      tmem_ld_32x16(tm_z, zf);
+      tmem_ld_32x16(tm_z + 16, zf + 16);
+      tmem_ld_wait();
+      release(acc_last);
+    }
+    // (y straight from registers with 16-byte st.global instead of staging + TMA store measured slower: o_net 52.7 vs 46.3 us)
+    if (LN == 2) {      // first tile: z block sits in the staging buffer; normalise it in place once its own store (if any) has read it
+      if (p.store_z) stage_wait();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4* slot = reinterpret_cast<uint4*>(crow + ((c ^ sw) << 4));
+        const uint4 u = *slot;
+        const uint32_t zw[4] = {u.x, u.y, u.z, u.w};
+        uint32_t yw[4];
+        norm8(zw, grp * 64 + c * 8, yw);
+        *slot = make_uint4(yw[0], yw[1], yw[2], yw[3]);
+        asm volatile("" ::: "memory");
+      }
+      stage_store(&tmY, grp * 64, (int)row0);
+    }
+    const int last_col0 = (LN - 1) * BN + grp * 64;
+    if (p.store_z) {    // last tile's z block: staging -> global
+      stage_wait();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(crow + ((c ^ sw) << 4)) = make_uint4(zp[c * 4], zp[c * 4 + 1], zp[c * 4 + 2], zp[c * 4 + 3]);
+      stage_store(&tmZ, last_col0, (int)row0);
+    }
+    stage_wait();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t yw[4];
+      norm8(zp + c * 4, last_col0 + c * 8, yw);
+      *reinterpret_cast<uint4*>(crow + ((c ^ sw) << 4)) = make_uint4(yw[0], yw[1], yw[2], yw[3]);
+      asm volatile("" ::: "memory");
+    }
+    stage_store(&tmY, last_col0, (int)row0);
+  }
+  if (leader) tma_store_wait_all();
+}
+
+// LN > 0: the output row is LN x BN columns wide and every row block's LN column tiles run back to back on the same CTA (pair), so the
+// epilogue warps see whole rows: they add bias, dropout and the residual, keep the bf16 LayerNorm input packed in registers, meet once per
+// row block for the row statistics (shared-memory partial sums) and write z (optional) and y = LayerNorm(z) through the staging buffers.
+template <int BN, int STAGES, typename TC, int CG, int EG, int LN = 0>
 __global__ void __launch_bounds__(threads_for(EG), 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using C_ = Cfg<BN, STAGES, CG, EG>;
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmY, const GemmParams p) {
+  using C_ = Cfg<BN, STAGES, CG, EG, LN>;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;      // 0 = leader of the pair (issues the MMAs)
   const int unit0 = (int)blockIdx.x / CG, unit_step = (int)gridDim.x / CG;
   extern __shared__ uint8_t smem_raw[];
@@ -214,13 +429,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int total_units = p.tiles_m * p.tiles_n * p.ksplits;
+  // work item vi of this CTA (pair): plain GEMM = unit0 + vi * step over (ks, tn, tm); LN = column tile vi % LN of row block unit0 + (vi / LN) * step
+  auto unit_of = [&](int vi, int& tm, int& tn, int& ks) -> bool {
+    if constexpr (LN > 0) {
+      tm = unit0 + (vi / LN) * unit_step; tn = vi % LN; ks = 0;
+      return tm < p.tiles_m;
+    } else {
+      const int unit = unit0 + vi * unit_step;
+      if (unit >= total_units) return false;
+      tm = unit % p.tiles_m; tn = (unit / p.tiles_m) % p.tiles_n; ks = unit / (p.tiles_m * p.tiles_n);
+      return true;
+    }
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       // ================= TMA producer
       int s = 0; uint32_t ph = 0;
-      for (int unit = unit0; unit < total_units; unit += unit_step) {
-        const int tm = unit % p.tiles_m, tn = (unit / p.tiles_m) % p.tiles_n, ks = unit / (p.tiles_m * p.tiles_n);
+      int tm, tn, ks;
+      for (int vi = 0; unit_of(vi, tm, tn, ks); ++vi) {
         const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.nkb);
         const int m0 = tm * (BM * CG) + (int)cta_rank * BM, n0 = tn * BN + (int)cta_rank * (BN / CG) * (CG - 1);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -268,8 +495,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ================= MMA issuer (the pair's leader for CG = 2: M = 256 rows, 128 per CTA)
       const uint32_t idesc = umma_idesc_bf16(BM * CG, BN, p.a_mn, p.b_mn);
       int s = 0; uint32_t ph = 0; int it = 0;
-      for (int unit = unit0; unit < total_units; unit += unit_step, ++it) {
-        const int ks = unit / (p.tiles_m * p.tiles_n);
+      int tm, tn, ks;
+      for (int vi = 0; unit_of(vi, tm, tn, ks); ++vi, ++it) {
         const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.nkb);
         const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_ph ^ 1);
@@ -306,8 +533,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t dthr = dropout_threshold(e.drop_p);
     const bool pair_hash = (p.N & 1) == 0;
     int it = 0;
-    for (int unit = unit0; unit < total_units; unit += unit_step, ++it) {
-      const int tm = unit % p.tiles_m, tn = (unit / p.tiles_m) % p.tiles_n;
+    int tm, tn, ks;
+    if constexpr (LN > 0) {
+      ln_epilogue<BN, CG, EG, LN, C_>(p, tmC, tmY, sm, tfull, tempty, tmem_base, cta_rank, unit0, unit_step, q, grp, lane, leader, cst0);
+    } else
+    for (int vi = 0; unit_of(vi, tm, tn, ks); ++vi, ++it) {
       const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
       const int64_t row0 = (int64_t)tm * (BM * CG) + (int64_t)cta_rank * BM;      // first output row of this CTA's half of the tile
       const int64_t row = row0 + r_in_tile;
@@ -516,17 +746,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) { if (CG == 2) tmem_dealloc_2sm<C_::TMEM_COLS>(tmem_base); else tmem_dealloc<C_::TMEM_COLS>(tmem_base); }
 }
 
-template <int BN, int STAGES, typename TC, int CG = 1, int EG = 2>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int grid, cudaStream_t st) {
-  using C_ = Cfg<BN, STAGES, CG, EG>;
+template <int BN, int STAGES, typename TC, int CG = 1, int EG = 2, int LN = 0>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int grid, cudaStream_t st, const CUtensorMap* tmY = nullptr) {
+  using C_ = Cfg<BN, STAGES, CG, EG, LN>;
   static_assert(C_::SMEM <= 232448, "GEMM shared-memory plan exceeds 227 KB");
   static bool attr_set = false;
   if (!attr_set) {
-    TXL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, TC, CG, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
+    TXL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, TC, CG, EG, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
     attr_set = true;
   }
+  const CUtensorMap& y = tmY ? *tmY : tmC;
   if (CG == 1) {
-    tc_gemm_kernel<BN, STAGES, TC, CG, EG><<<grid, threads_for(EG), C_::SMEM, st>>>(tmA, tmB, tmC, p);
+    tc_gemm_kernel<BN, STAGES, TC, CG, EG, LN><<<grid, threads_for(EG), C_::SMEM, st>>>(tmA, tmB, tmC, y, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads_for(EG)); cfg.dynamicSmemBytes = C_::SMEM; cfg.stream = st;
@@ -535,7 +766,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     ++g_txl_launches;
-    TXL_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, STAGES, TC, CG, EG>, tmA, tmB, tmC, p));
+    TXL_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, STAGES, TC, CG, EG, LN>, tmA, tmB, tmC, y, p));
     return TXL_OK;
   }
   TXL_LAUNCH_CHECK();
@@ -560,6 +791,7 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.C = C; p.dtype_c = dtype_c; p.epi = *epi;
+  p.resid = nullptr; p.gamma = p.beta = nullptr; p.mean = p.rstd = nullptr; p.eps = 0.f; p.store_z = 0;
   p.inv_keep = (epi->flags & (TXL_EPI_DROPOUT | TXL_EPI_MASK_SCALE)) ? 1.f / (1.f - epi->drop_p) : 1.f;
   p.a_mn = transA ? 1 : 0;   // transA: A stored [K, M] => M contiguous
   p.b_mn = transB ? 0 : 1;   // transB: B stored [N, K] => K contiguous
@@ -620,3 +852,46 @@ int txl_gemm_tc(const void* A, const void* B, void* C, int64_t M, int64_t N, int
   return TXL_OK;
 }
 
+
+// y = LayerNorm(resid + dropout(A W^T + bias)) in ONE kernel: the CTA-pair GEMM with the fused row-statistics epilogue (LN template
+// parameter above).  A [M, K] and W [N, K] bf16 row-major, resid / y / z [M, N] bf16 contiguous, N = 256 or 512 (the whole row lives in
+// the pair's TMEM: 2 column tiles of 256).  z (the LayerNorm input), mean and rstd are what add_ln_bwd reads; pass NULL for all three in
+// evaluation.  handled = 0: shape not covered, the caller runs txl_gemm + txl_add_ln_fwd.   [A.3 o_net + layer_norm, A.6 CoreNet.3 + layer_norm]
+extern "C" int txl_gemm_add_ln_fwd(const void* A, const void* W, const float* bias, const void* resid, const float* gamma, const float* beta, void* Y, void* Z,
+                                   float* mean, float* rstd, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldw, float eps, float drop_p, uint64_t seed,
+                                   uint32_t site, void* stream, int* handled) {
+  TXL_CHECK_ARG(handled != nullptr, "gemm_add_ln_fwd: handled must not be NULL");
+  *handled = 0;
+  TXL_CHECK_ARG(A && W && resid && gamma && beta && Y && M > 0 && N > 0 && K > 0, "gemm_add_ln_fwd: null operand or empty shape (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
+  TXL_CHECK_ARG((Z == nullptr) == (mean == nullptr) && (Z == nullptr) == (rstd == nullptr), "gemm_add_ln_fwd: z, mean and rstd are saved together or not at all");
+  TXL_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "gemm_add_ln_fwd: drop_p=%f outside [0, 1)", drop_p);
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("TXL_DISABLE_TC"); const char* e2 = getenv("TXL_GEMM_LN"); off = ((e && e[0] == '1') || (e2 && e2[0] == '0')) ? 1 : 0; }
+  if (off) return TXL_OK;
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if (!(N == 256 || N == 512) || M < 256 || K < 64 || (K % 8) || (lda % 8) || (ldw % 8) || M >= (1ll << 31)) return TXL_OK;
+  if (!al16(A) || !al16(W) || !al16(resid) || !al16(Y) || !al16(gamma) || !al16(beta) || (bias && !al16(bias)) || (Z && !al16(Z))) return TXL_OK;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.ldc = N; p.C = Y; p.dtype_c = TXL_BF16;
+  p.epi = TxlEpilogue{};
+  p.epi.bias = bias; p.epi.drop_p = drop_p; p.epi.seed = seed; p.epi.site = site; p.epi.flags = drop_p > 0.f ? TXL_EPI_DROPOUT : 0;
+  p.inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.a_mn = 0; p.b_mn = 0;
+  p.tiles_m = (int)cdiv64(M, 2 * BM); p.tiles_n = (int)(N / 256);
+  p.nkb = (int)cdiv64(K, BK); p.ksplits = 1; p.kb_per_split = p.nkb;
+  p.tma_store = 1;
+  p.resid = (const bf16*)resid; p.gamma = gamma; p.beta = beta; p.mean = mean; p.rstd = rstd; p.eps = eps; p.store_z = Z ? 1 : 0;
+  CUtensorMap tmA, tmB, tmZ, tmY;
+  int rc;
+  if ((rc = txl_make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK))) return rc;
+  if ((rc = txl_make_tmap_2d(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 128, BK))) return rc;
+  if ((rc = txl_make_tmap_2d(&tmY, Y, (uint64_t)M, (uint64_t)N, (uint64_t)N, BM, 64))) return rc;
+  if (Z) { if ((rc = txl_make_tmap_2d(&tmZ, Z, (uint64_t)M, (uint64_t)N, (uint64_t)N, BM, 64))) return rc; } else tmZ = tmY;
+  const int workers = txl_num_sms() / 2;
+  const int grid = (p.tiles_m < workers ? p.tiles_m : workers) * 2;
+  if (N == 512) rc = launch<256, 4, bf16, 2, 4, 2>(tmA, tmB, tmZ, p, grid, (cudaStream_t)stream, &tmY);
+  else rc = launch<256, 4, bf16, 2, 4, 1>(tmA, tmB, tmZ, p, grid, (cudaStream_t)stream, &tmY);
+  if (rc) return rc;
+  *handled = 1;
+  return TXL_OK;
+}

@@ -108,13 +108,12 @@ def forward(cfg, W: List[LayerW], E, out_bias, ids, mems_bm, labels_shift, *, dr
         v_mem = kvm[:, d:] if kvm is not None else None
         att = ops.relattn_fwd(qkv[:, :d], k_mem, v_mem, qkv[:, d:2 * d], qkv[:, 2 * d:], r, w.rwb, w.rrb, B, T, H, dh, g.band, save=bool(save))
         vec, lse, att_saved = att if save else (att[0], att[1], None)
-        ao = ops.gemm(vec, w.o, transB=True)
-        y1, z1, mean1, rstd1 = ops.add_ln_fwd(x, ao, w.ln1_w, w.ln1_b, cfg.layer_norm_epsilon, drop_p, seed, site + S_ATTN_OUT, save)
+        # o_net + dropout + residual + LayerNorm: one kernel (GEMM epilogue holds whole rows); falls back to GEMM + add_ln for other shapes
+        y1, z1, mean1, rstd1 = ops.gemm_add_ln_fwd(vec, w.o, None, x, w.ln1_w, w.ln1_b, cfg.layer_norm_epsilon, drop_p, seed, site + S_ATTN_OUT, save)
         # the backward mask of dropout(relu(.)) at one bit per element, written by the same epilogue ([di/32, N] words)
         hbits = torch.empty((cfg.d_inner + 31) // 32, N, dtype=torch.int32, device=dev) if save else None
         h = ops.gemm(y1, w.w1, transB=True, bias=w.b1, relu=True, drop_p=drop_p, seed=seed, site=site + S_FF_INNER, emit_live_bits=hbits)
-        f = ops.gemm(h, w.w2, transB=True, bias=w.b2)
-        y2, z2, mean2, rstd2 = ops.add_ln_fwd(y1, f, w.ln2_w, w.ln2_b, cfg.layer_norm_epsilon, drop_p, seed, site + S_FF_OUT, save)
+        y2, z2, mean2, rstd2 = ops.gemm_add_ln_fwd(h, w.w2, w.b2, y1, w.ln2_w, w.ln2_b, cfg.layer_norm_epsilon, drop_p, seed, site + S_FF_OUT, save)
         if save:
             sv.layers.append(dict(x=x, qkv=qkv, kvm=kvm if mems_real else None, kvm_fwd=kvm, r=r, vec=vec, lse=lse, att_saved=att_saved, z1=z1, mean1=mean1,
                                   rstd1=rstd1, y1=y1, h=h, hbits=hbits, z2=z2, mean2=mean2, rstd2=rstd2))

@@ -114,6 +114,26 @@ def add_ln_fwd(x, r, gamma, beta, eps, drop_p=0.0, seed=0, site=0, save=True):
     return y, z, mean, rstd
 
 
+def gemm_add_ln_fwd(A, W, bias, resid, gamma, beta, eps, drop_p=0.0, seed=0, site=0, save=True):
+    """y = LN(resid + dropout(A W^T + bias)): one tensor-core kernel when the library covers the shape (bf16, N in {256, 512}), else the
+    GEMM followed by the residual + LayerNorm kernel.  Returns (y, z, mean, rstd) exactly like add_ln_fwd."""
+    M, K = A.shape
+    N = W.shape[0]
+    if A.dtype == torch.bfloat16 and A.stride(1) == 1 and W.stride(1) == 1 and resid.is_contiguous():
+        y = torch.empty(M, N, dtype=A.dtype, device=A.device)
+        z = torch.empty_like(y) if save else None
+        mean = torch.empty(M, dtype=torch.float32, device=A.device) if save else None
+        rstd = torch.empty(M, dtype=torch.float32, device=A.device) if save else None
+        handled = C.c_int(0)
+        check(_lib().txl_gemm_add_ln_fwd(ptr(A), ptr(W), ptr(bias), ptr(resid), ptr(gamma), ptr(beta), ptr(y), ptr(z), ptr(mean), ptr(rstd), M, N, K,
+                                         A.stride(0), W.stride(0), float(eps), float(drop_p), int(seed), int(site), stream_ptr(), C.byref(handled)),
+              'gemm_add_ln_fwd')
+        if handled.value:
+            return y, z, mean, rstd
+    r = gemm(A, W, transB=True, bias=bias)
+    return add_ln_fwd(resid, r, gamma, beta, eps, drop_p, seed, site, save)
+
+
 def add_ln_bwd(dy, z, gamma, mean, rstd, dgamma, dbeta, dx_out=None, accumulate_dx=False, want_dr=True, drop_p=0.0, seed=0, site=0, dy2=None):
     rows, d = dy.shape
     if dx_out is None:

@@ -112,6 +112,47 @@ def test_add_ln_fwd_bwd(ops, mode):
     torch.testing.assert_close(db, beta.grad, rtol=1e-3, atol=1e-2 if mode == 'bf16' else 1e-3)
 
 
+@pytest.mark.parametrize('M,N,K,bias,p', [(512, 512, 512, False, 0.0), (1000, 512, 2048, True, 0.1), (300, 256, 192, True, 0.25), (4096, 512, 512, False, 0.1),
+                                          (257, 512, 72, True, 0.0)])
+def test_gemm_add_ln_fused(ops, M, N, K, bias, p):
+    """Linear + dropout + residual + LayerNorm in one tensor-core kernel (o_net / CoreNet.3 tails, A.3 step 8 / A.6) == the GEMM followed by the
+    residual + LayerNorm kernel (same counter-based dropout mask; the fused kernel does not round the accumulator before the add), and ==
+    torch where no dropout is drawn.  z / mean / rstd are the backward's inputs: checked too; evaluation mode (save=False) gives the same y."""
+    import ctypes as C
+    torch.manual_seed(M + K)
+    A = (0.5 * torch.randn(M, K, device='cuda')).bfloat16()
+    W = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+    b = (0.1 * torch.randn(N, device='cuda')) if bias else None
+    x = torch.randn(M, N, device='cuda').bfloat16()
+    gamma = 1 + 0.1 * torch.randn(N, device='cuda')
+    beta = 0.1 * torch.randn(N, device='cuda')
+    before = ops._lib().txl_launch_count()
+    y, z, mean, rstd = ops.gemm_add_ln_fwd(A, W, b, x, gamma, beta, 1e-5, p, 1234, 17, True)
+    assert ops._lib().txl_launch_count() - before == 1, 'the fused kernel did not take this shape'
+    r = ops.gemm(A, W, transB=True, bias=b)
+    y2, z2, mean2, rstd2 = ops.add_ln_fwd(x, r, gamma, beta, 1e-5, p, 1234, 17, True)
+
+    def fro(got, want):
+        return float((got.float() - want.float()).norm() / want.float().norm())
+    assert fro(z, z2) < 4e-3 and fro(y, y2) < 6e-3, (fro(z, z2), fro(y, y2))
+    torch.testing.assert_close(z.float(), z2.float(), rtol=2e-2, atol=3e-2)
+    torch.testing.assert_close(y.float(), y2.float(), rtol=2e-2, atol=5e-2)
+    # the saved statistics are those of the saved z (what add_ln_bwd recomputes xhat from)
+    zf = z.float()
+    torch.testing.assert_close(mean, zf.mean(-1), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rstd, torch.rsqrt(zf.var(-1, unbiased=False) + 1e-5), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(y.float(), torch.nn.functional.layer_norm(zf, (N,), gamma, beta, 1e-5), rtol=2e-2, atol=2e-2)
+    if p == 0.0:
+        zr = (x.float() + A.float() @ W.float().t() + (b if bias else 0.0))
+        torch.testing.assert_close(zf, zr, rtol=2e-2, atol=3e-2)
+    else:       # same keep-mask as the unfused kernels: dropped positions hold the residual exactly
+        dropped = (z2 == x)
+        assert 0.5 * p < float(dropped.float().mean()) < 1.5 * p + 0.01
+        assert float((z[dropped] != x[dropped]).float().mean()) < 2e-3        # (a kept position whose bf16-rounded branch output is ~0 also lands in `dropped`)
+    y3, z3, mean3, rstd3 = ops.gemm_add_ln_fwd(A, W, b, x, gamma, beta, 1e-5, p, 1234, 17, False)
+    assert z3 is None and mean3 is None and torch.equal(y3, y)
+
+
 def test_embed_posemb(ops):
     torch.manual_seed(3)
     E = torch.randn(50, 64, device='cuda')
