@@ -474,10 +474,43 @@ class RefTransfoXLLMHeadModel(nn.Module):
             s = F.log_softmax(s, dim=-1)
         return s
 
+    @staticmethod
+    def repetition_penalty(scores, prev_ids, penalty):
+        """HF 4.25 RepetitionPenaltyLogitsProcessor (a logits PROCESSOR: runs on the raw step scores, before every warper, in greedy
+        search too): the score of every token already in the sequence is divided by `penalty` if positive, multiplied if negative.
+        Row-by-row restatement (accepted key of the reference's `sample` strategy, musicnlp/trainer/eval.py:279)."""
+        out = scores.clone()
+        for b in range(scores.size(0)):
+            for t in set(prev_ids[b].tolist()):
+                v = scores[b, t]
+                out[b, t] = v * penalty if v < 0 else v / penalty
+        return out
+
+    @staticmethod
+    def typical_filter(scores, mass, min_tokens_to_keep=1):
+        """HF 4.25 TypicalLogitsWarper (locally typical sampling; `typical_p`, eval.py:279): keep the tokens whose surprisal is closest to
+        the entropy of the distribution until their mass reaches `mass`; the rest -> -inf.  Row-by-row restatement."""
+        out = scores.clone()
+        for b in range(scores.size(0)):
+            logp = F.log_softmax(scores[b].double(), dim=-1)
+            pr = logp.exp()
+            ent = -torch.nansum(logp * pr)
+            dist = ((-logp) - ent).abs().float()          # HF sorts the fp32 distances
+            order = torch.sort(dist, stable=False)[1]
+            cum = torch.softmax(scores[b][order], dim=-1).cumsum(-1)
+            last = int((cum < mass).sum().item())
+            last = min(last, scores.size(1) - 1)
+            thr = dist[order[last]]
+            remove = dist > thr
+            if min_tokens_to_keep > 1:
+                remove[order[:min_tokens_to_keep]] = False
+            out[b, remove] = -float('inf')
+        return out
+
     @torch.no_grad()
     def generate(self, input_ids, max_length, do_sample=False, temperature=1.0, top_k=50, top_p=1.0,
                  renormalize_logits=True, generator=None, eos_token_id=None, pad_token_id=None,
-                 return_step_scores=False):
+                 return_step_scores=False, typical_p=None, repetition_penalty=None):
         """greedy_search / sample loop of HF GenerationMixin 4.25 restricted to what eval.py:277-333 uses."""
         self.eval()
         ids = input_ids.clone()
@@ -489,8 +522,17 @@ class RefTransfoXLLMHeadModel(nn.Module):
             out = self.forward(**inp)
             s = out.logits[:, -1, :]
             past = out.mems
+            if repetition_penalty is not None and repetition_penalty != 1.0:
+                s = self.repetition_penalty(s, ids, repetition_penalty)
+                if not do_sample and renormalize_logits:
+                    s = F.log_softmax(s, dim=-1)
             if do_sample:
-                s = self.warp_scores(s, temperature, top_k, top_p, renormalize_logits)
+                typ = typical_p is not None and typical_p < 1.0
+                s = self.warp_scores(s, temperature, top_k, top_p, renormalize_logits and not typ)
+                if typ:      # HF order: temperature, top-k, top-p, typical, then the renormalisation
+                    s = self.typical_filter(s, typical_p)
+                    if renormalize_logits:
+                        s = F.log_softmax(s, dim=-1)
                 probs = F.softmax(s, dim=-1)
                 nxt = torch.multinomial(probs, 1, generator=generator).squeeze(1)
             else:

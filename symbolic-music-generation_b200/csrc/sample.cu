@@ -198,6 +198,208 @@ __global__ void __launch_bounds__(NT) sample_kernel(const float* __restrict__ sc
   if (threadIdx.x == 0) next[b] = pick;
 }
 
+// ------------------------------------------------------------------ large vocabularies (row does not fit the shared-memory sort)
+// Same warpers, no sort: the k-th largest score and the top-p boundary are found by radix selection over the order-preserving 32-bit
+// keys of the row (4 passes of 8 bits each, 256-bin histograms of counts and probability mass); ties at the boundary are kept in index
+// order, which is the total order of the small-vocabulary path (value descending, index ascending).  Mass is summed as 40-bit fixed point
+// (integer adds commute: the kept set and the draw are reproducible whatever order the atomics land in).  The inverse-CDF draw walks the
+// kept tokens in INDEX order (any fixed order samples the same distribution; the small path walks them by descending probability).
+// WordPiece 32k / the 267,735-token default TransfoXL vocabulary: reference musicnlp/models/transformer_xl.py:56-63.        [A.7]
+constexpr float MASS_SCALE = 1099511627776.f;      // 2^40
+__device__ __forceinline__ uint32_t fkey(float x) { const uint32_t u = __float_as_uint(x); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ unsigned long long mass_of(float x, float m) { return __float2ull_rn(__expf(x - m) * MASS_SCALE); }
+
+struct BigShared {
+  unsigned long long hmass[256];
+  int hcnt[256];
+  unsigned long long wmass[NT / 32];
+  int wcnt[NT / 32];
+  uint32_t prefix;
+  int found, base_cnt, bin_cnt;
+  unsigned long long base_mass, bin_mass;
+  float red[NT / 32];
+  int pick;
+};
+
+// Radix descent to the element where the running (count | mass) of the row, taken in descending key order, first reaches the target:
+//   by_mass == 0: the element of rank `k_target` (1-based)            -> sh.prefix = its key
+//   by_mass == 1: the first element whose inclusive mass exceeds `p_target` -> sh.prefix = its key; sh.found = 0 when the whole row stays below
+// On return base_cnt / base_mass describe the elements with a LARGER key, bin_cnt / bin_mass those with exactly this key.
+// Only elements with key >= min_key and a finite score take part.
+__device__ void radix_select(const float* __restrict__ s, int V, float inv_t, float m, uint32_t min_key, int by_mass, int k_target,
+                             unsigned long long p_target, BigShared& sh) {
+  const int tid = threadIdx.x;
+  if (tid == 0) { sh.prefix = 0; sh.found = 1; sh.base_cnt = 0; sh.base_mass = 0; }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    const uint32_t hi_mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    if (tid < 256) { sh.hmass[tid] = 0; sh.hcnt[tid] = 0; }
+    __syncthreads();
+    const uint32_t prefix = sh.prefix;
+    for (int v = tid; v < V; v += NT) {
+      const float x = s[v] * inv_t;
+      const uint32_t key = fkey(x);
+      if (key < min_key || !(x > -INFINITY) || (key & hi_mask) != prefix) continue;
+      const int bin = (key >> shift) & 255;
+      atomicAdd(&sh.hcnt[bin], 1);
+      atomicAdd(&sh.hmass[bin], mass_of(x, m));
+    }
+    __syncthreads();
+    if (tid == 0 && sh.found) {
+      int cnt = sh.base_cnt; unsigned long long mass = sh.base_mass;
+      int bin = 255;
+      bool hit = false;
+      for (; bin >= 0; --bin) {
+        const int c = sh.hcnt[bin]; const unsigned long long w = sh.hmass[bin];
+        if (c > 0 && (by_mass ? (mass + w > p_target) : (cnt + c >= k_target))) { hit = true; break; }
+        cnt += c; mass += w;
+      }
+      if (!hit) { sh.found = 0; }
+      else {
+        sh.prefix = prefix | ((uint32_t)bin << shift);
+        sh.base_cnt = cnt; sh.base_mass = mass; sh.bin_cnt = sh.hcnt[bin]; sh.bin_mass = sh.hmass[bin];
+      }
+    }
+    __syncthreads();
+    if (!sh.found) break;
+  }
+}
+
+// exclusive prefix over the block of one (count, mass) pair per thread; totals in tot_cnt / tot_mass
+__device__ void block_scan_pair(int cnt, unsigned long long mass, int& ex_cnt, unsigned long long& ex_mass, int& tot_cnt, unsigned long long& tot_mass, BigShared& sh) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int c = cnt; unsigned long long w = mass;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int oc = __shfl_up_sync(0xffffffffu, c, o); const unsigned long long ow = __shfl_up_sync(0xffffffffu, w, o);
+    if (lane >= o) { c += oc; w += ow; }
+  }
+  __syncthreads();
+  if (lane == 31) { sh.wcnt[warp] = c; sh.wmass[warp] = w; }
+  __syncthreads();
+  int bc = 0; unsigned long long bw = 0;
+  tot_cnt = 0; tot_mass = 0;
+  for (int i = 0; i < NT / 32; ++i) {
+    if (i < warp) { bc += sh.wcnt[i]; bw += sh.wmass[i]; }
+    tot_cnt += sh.wcnt[i]; tot_mass += sh.wmass[i];
+  }
+  ex_cnt = bc + c - cnt; ex_mass = bw + w - mass;
+}
+
+__global__ void __launch_bounds__(NT) sample_large_kernel(const float* __restrict__ scores, int V, int do_sample, float temperature, int top_k, float top_p,
+                                                          const float* __restrict__ u, int64_t* __restrict__ next, uint8_t* __restrict__ keep,
+                                                          float* __restrict__ warped) {
+  __shared__ BigShared sh;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* s = scores + (int64_t)b * V;
+  uint8_t* keep_row = keep ? keep + (int64_t)b * V : nullptr;
+  float* warped_row = warped ? warped + (int64_t)b * V : nullptr;
+  const float inv_t = (do_sample && temperature != 1.0f) ? 1.0f / temperature : 1.0f;
+  // ---- row maximum and its first index (greedy answer; softmax shift)
+  float bv = -INFINITY; int bi = -1;
+  for (int v = tid; v < V; v += NT) { const float x = s[v] * inv_t; if (bi < 0 || before(x, v, bv, bi)) { bv = x; bi = v; } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi >= 0 && (bi < 0 || before(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+  }
+  if ((tid & 31) == 0) { sh.red[tid >> 5] = bv; sh.wcnt[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NT / 32; ++w) { const float ov = sh.red[w]; const int oi = sh.wcnt[w]; if (oi >= 0 && (bi < 0 || before(ov, oi, bv, bi))) { bv = ov; bi = oi; } }
+    sh.red[0] = bv; sh.pick = bi;
+  }
+  __syncthreads();
+  const float m = sh.red[0];
+  const int arg = sh.pick;
+  __syncthreads();
+  if (!do_sample) {
+    if (keep_row) for (int v = tid; v < V; v += NT) keep_row[v] = (v == arg);
+    if (warped_row) for (int v = tid; v < V; v += NT) warped_row[v] = s[v];
+    if (tid == 0) next[b] = arg;
+    return;
+  }
+  // ---- top-k: everything >= the k-th largest score stays (ties kept, as HF's `scores < kth` removal)
+  uint32_t min_key = 0;
+  if (top_k > 0 && top_k < V) {
+    radix_select(s, V, inv_t, m, 0u, 0, top_k, 0ull, sh);
+    if (sh.found) min_key = sh.prefix;
+    __syncthreads();
+  }
+  // ---- mass of the top-k survivors (finite scores only), this thread's share over a CONTIGUOUS index range (index-order scans below)
+  const int chunk = (V + NT - 1) / NT, v0 = min(tid * chunk, V), v1 = min(v0 + chunk, V);
+  unsigned long long my_mass = 0; int my_cnt = 0;
+  for (int v = v0; v < v1; ++v) {
+    const float x = s[v] * inv_t;
+    if (fkey(x) >= min_key && x > -INFINITY) { my_mass += mass_of(x, m); ++my_cnt; }
+  }
+  int ex_c, tot_c; unsigned long long ex_m, total1;
+  block_scan_pair(my_cnt, my_mass, ex_c, ex_m, tot_c, total1, sh);
+  __syncthreads();
+  // ---- top-p: tokens in descending order stay while the mass BEFORE them is <= top_p (the first one past the boundary is kept)
+  uint32_t tau = min_key; int ties_kept = 0x7fffffff; bool bounded = false;
+  if (top_p < 1.0f) {
+    const unsigned long long P = __double2ull_rd((double)top_p * (double)total1);
+    radix_select(s, V, inv_t, m, min_key, 1, 0, P, sh);
+    if (sh.found) {
+      bounded = true;
+      tau = sh.prefix;
+      const unsigned long long each = sh.bin_cnt > 0 ? sh.bin_mass / (unsigned long long)sh.bin_cnt : 0ull;      // all ties carry the same mass
+      const unsigned long long room = P - sh.base_mass;                                                          // >= 0: the elements above tau stayed at or below P
+      ties_kept = each > 0 ? (int)min((unsigned long long)sh.bin_cnt, room / each + 1ull) : sh.bin_cnt;
+    }
+    __syncthreads();
+  }
+  // ---- kept set in index order: score above tau, or one of the first `ties_kept` scores equal to tau
+  int my_ties = 0;
+  if (bounded) for (int v = v0; v < v1; ++v) { const float x = s[v] * inv_t; if (fkey(x) == tau && x > -INFINITY) ++my_ties; }
+  int tie_rank0, tot_t; unsigned long long dummy0, dummy1;
+  block_scan_pair(my_ties, 0ull, tie_rank0, dummy0, tot_t, dummy1, sh);
+  __syncthreads();
+  auto kept = [&](float x, int& tie_rank) -> bool {
+    if (!(x > -INFINITY)) return false;
+    const uint32_t key = fkey(x);
+    if (!bounded) return key >= min_key;
+    if (key > tau) return true;
+    if (key == tau) return tie_rank++ < ties_kept;
+    return false;
+  };
+  unsigned long long kept_mass = 0; int kept_cnt = 0;
+  { int tr = tie_rank0; for (int v = v0; v < v1; ++v) { const float x = s[v] * inv_t; if (kept(x, tr)) { kept_mass += mass_of(x, m); ++kept_cnt; } } }
+  int ex_kc, tot_kc; unsigned long long ex_km, total2;
+  block_scan_pair(kept_cnt, kept_mass, ex_kc, ex_km, tot_kc, total2, sh);
+  __syncthreads();
+  if (total2 == 0) {      // nothing representable survived (cannot happen with a finite maximum: its mass is 2^40): fall back to the arg-max
+    if (tid == 0) next[b] = arg;
+    return;
+  }
+  const float lse = m + __logf((float)((double)total2 / (double)MASS_SCALE));
+  if (keep_row || warped_row) {
+    int tr = tie_rank0;
+    for (int v = v0; v < v1; ++v) {
+      const float x = s[v] * inv_t;
+      const bool k = kept(x, tr);
+      if (keep_row) keep_row[v] = k;
+      if (warped_row) warped_row[v] = k ? x - lse : -INFINITY;
+    }
+  }
+  // ---- inverse-CDF draw over the kept tokens in index order
+  const unsigned long long target = min(__double2ull_rd((double)u[b] * (double)total2), total2 - 1);
+  if (tid == 0) sh.pick = -1;
+  __syncthreads();
+  if (kept_cnt > 0 && target >= ex_km && target < ex_km + kept_mass) {
+    unsigned long long acc = ex_km; int tr = tie_rank0; int choice = -1;
+    for (int v = v0; v < v1 && choice < 0; ++v) {
+      const float x = s[v] * inv_t;
+      if (kept(x, tr)) { acc += mass_of(x, m); if (target < acc) choice = v; }
+    }
+    sh.pick = choice;
+  }
+  __syncthreads();
+  if (tid == 0) next[b] = sh.pick >= 0 ? sh.pick : arg;
+}
+
 // The tail of a decode step in ONE kernel (one CTA per sequence): log-softmax of the LM-head logits (warp 0, in the exact operation order of
 // lsm_nll_fwd_kernel, so the scores are bit-identical to the forward path's), the keyed uniform of decode_uniform_kernel, warpers + draw
 // (sample_block), HF's eos / pad bookkeeping (decode_commit_kernel), the embedding row of the chosen token for the next step, and the
@@ -271,7 +473,11 @@ extern "C" int txl_sample(const float* scores, int B, int V, int do_sample, floa
   TXL_CHECK_ARG(!do_sample || (u && temperature > 0.f && top_p > 0.f), "sample: sampling needs u, temperature>0, top_p>0");
   int NP = 32;
   while (NP < V) NP <<= 1;
-  TXL_CHECK_ARG(NP <= 16384, "sample: vocab %d too large for the shared-memory sampler", V);
+  if (NP > 16384) {      // the row does not fit the shared-memory sort: radix-selection sampler
+    sample_large_kernel<<<B, NT, 0, (cudaStream_t)stream>>>(scores, V, do_sample, temperature, top_k, top_p, u, next, keep, warped);
+    TXL_LAUNCH_CHECK();
+    return TXL_OK;
+  }
   size_t smem = (size_t)NP * 12;
   static size_t attr_smem[64] = {0};      // per device: the attribute belongs to the (function, device) pair
   int dev = 0;

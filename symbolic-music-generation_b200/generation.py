@@ -9,7 +9,9 @@ The device-resident decode step (ring cache, CUDA graph; decode.py) is the DEFAU
 HF's `torch.multinomial`, and consecutive calls differ.  Passing a `torch.Generator` (`generator=`) or asking for per-step
 scores selects the one-forward-per-token host loop.  Any batch size: more than 64 sequences are decoded as further sequence groups.
 
-Beam search, contrastive search, typical-p and repetition penalty are outside the measured path and raise.
+`typical_p` and `repetition_penalty` (accepted by the reference's `sample` strategy, eval.py:279) run on the host loop as well: the
+penalty is a processor on the raw step scores, typical filtering sits between the top-p filter and the renormalisation (HF 4.25 order),
+both as a few torch ops on the device around the sampling kernel.  Beam search and contrastive search are outside the path and raise.
 """
 from __future__ import annotations
 
@@ -18,6 +20,28 @@ from typing import Optional
 import torch
 
 from . import decode, ops
+
+
+def repetition_penalty_scores(scores, prev_ids, penalty: float):
+    """HF RepetitionPenaltyLogitsProcessor: scores of tokens already in `prev_ids` are divided by `penalty` when positive, multiplied when negative."""
+    s = torch.gather(scores, 1, prev_ids)
+    s = torch.where(s < 0, s * penalty, s / penalty)
+    return scores.scatter(1, prev_ids, s)
+
+
+def typical_filter_scores(scores, mass: float, min_tokens_to_keep: int = 1):
+    """HF TypicalLogitsWarper: keep the tokens whose surprisal is nearest the entropy until their mass reaches `mass`; -inf elsewhere."""
+    logp = torch.log_softmax(scores, dim=-1)
+    p = logp.exp()
+    ent = -(logp * p).nansum(-1, keepdim=True)
+    dist = torch.abs(-logp - ent)
+    sorted_dist, order = torch.sort(dist, descending=False)
+    cum = scores.gather(-1, order).softmax(dim=-1).cumsum(dim=-1)
+    last = (cum < mass).sum(dim=1).clamp_(max=scores.shape[-1] - 1)
+    remove_sorted = sorted_dist > sorted_dist.gather(1, last.view(-1, 1))
+    remove_sorted[..., :min_tokens_to_keep] = False
+    remove = remove_sorted.scatter(1, order, remove_sorted)
+    return scores.masked_fill(remove, -float('inf'))
 
 
 def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_tokens: Optional[int] = None, do_sample: Optional[bool] = None,
@@ -32,8 +56,12 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
         raise ValueError('generate needs input_ids (the reference always passes a tokenised prompt, eval.py:276)')
     if (num_beams or 1) > 1 or (num_beam_groups or 1) > 1 or penalty_alpha:
         raise NotImplementedError('beam / diverse-beam / contrastive search are not on the measured path (SURVEY §8b)')
-    if (typical_p is not None and typical_p < 1.0) or (repetition_penalty is not None and repetition_penalty != 1.0):
-        raise NotImplementedError('typical_p / repetition_penalty warpers are not implemented')
+    typical = typical_p is not None and typical_p < 1.0
+    if typical and not (0.0 < typical_p):
+        raise ValueError(f'typical_p has to be in (0, 1), got {typical_p}')
+    penalise = repetition_penalty is not None and repetition_penalty != 1.0
+    if penalise and not repetition_penalty > 0:
+        raise ValueError(f'repetition_penalty has to be > 0, got {repetition_penalty}')
     do_sample = bool(cfg.do_sample if do_sample is None else do_sample)
     top_k = cfg.top_k if top_k is None else top_k             # HF: config default top_k=50 applies when the caller passes none
     top_p = cfg.top_p if top_p is None else top_p
@@ -61,7 +89,7 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
     out_ids[:, :cur] = ids
     step_scores = []
     past = None
-    fast = (use_decode_cache and not return_step_scores and generator is None and decode.supported(model, B)
+    fast = (use_decode_cache and not return_step_scores and generator is None and not typical and not penalise and decode.supported(model, B)
             and max_length - cur >= 2)
     if fast and do_sample and seed is None:
         # the reference's call carries no seed (eval.py:277-333): key the draws on torch's global generator, as HF's multinomial is
@@ -96,7 +124,16 @@ def generate(model, input_ids=None, max_length: Optional[int] = None, max_new_to
                         cur += dec.run(nxt, max_length - cur)
                     break
                 u = torch.rand(B, device=dev, generator=generator) if do_sample else None
-                nxt, _, warped = ops.sample(scores, do_sample, temperature, top_k, top_p, u, want_warped=return_step_scores and do_sample)
+                if penalise:         # processor on the raw scores (greedy search applies it too); HF renormalises after it when asked to
+                    scores = repetition_penalty_scores(scores, out_ids[:, :cur], float(repetition_penalty))
+                    if not do_sample and renormalize_logits:
+                        scores = torch.log_softmax(scores, dim=-1)
+                if do_sample and typical:
+                    # temperature / top-k / top-p in the kernel (its draw is discarded), typical filter on the warped scores, second call samples
+                    _, _, warped = ops.sample(scores, True, temperature, top_k, top_p, u, want_warped=True)
+                    nxt, _, warped = ops.sample(typical_filter_scores(warped, float(typical_p)), True, 1.0, 0, 1.0, u, want_warped=return_step_scores)
+                else:
+                    nxt, _, warped = ops.sample(scores, do_sample, temperature, top_k, top_p, u, want_warped=return_step_scores and do_sample)
                 if return_step_scores:
                     step_scores.append(warped if do_sample else scores)
                 if eos_token_id is not None:

@@ -172,6 +172,35 @@ def test_generate_sampling_and_eos(pkg):
             assert (row[z[0, 0]:] == 0).all()
 
 
+def test_generate_repetition_penalty_and_typical_p(pkg):
+    """The two remaining keys of the reference's `sample` strategy (eval.py:279).  Greedy search with a repetition penalty is deterministic:
+    token-identical to the oracle in fp32 mode.  With typical_p the first step's warped scores keep exactly the oracle's token set
+    (temperature -> top-k -> top-p -> typical -> renormalise) and every sampled token lies inside its step's kept set."""
+    ref, model = make_pair(pkg, 'fp32', mem_len=32, n_layer=2)
+    ids, _ = _batch(422, 3, 6, pad=False)
+    want = ref.generate(ids, max_length=6 + 64, eos_token_id=None, repetition_penalty=1.3)
+    got = model.generate(input_ids=ids.cuda(), max_length=6 + 64, do_sample=False, eos_token_id=None, repetition_penalty=1.3)
+    assert model.last_generate_path == 'forward_per_token' and torch.equal(got.cpu(), want)
+    g = torch.Generator(device='cuda').manual_seed(5)
+    kw = dict(do_sample=True, top_k=32, top_p=0.95, temperature=1.1, typical_p=0.6, repetition_penalty=1.1, renormalize_logits=True)
+    out, scores = model.generate(input_ids=ids.cuda(), max_length=30, generator=g, return_step_scores=True, eos_token_id=None, **kw)
+    assert out.shape == (3, 30)
+    ref.eval()
+    with torch.no_grad():
+        r = ref(input_ids=ids).logits[:, -1]
+    r = ref.repetition_penalty(r, ids, 1.1)
+    rw = torch.log_softmax(ref.typical_filter(ref.warp_scores(r, 1.1, 32, 0.95, False), 0.6), -1)
+    kept = rw > -float('inf')
+    assert torch.equal(kept, scores[0].cpu() > -float('inf')) and int(kept.sum(1).max()) < 32
+    torch.testing.assert_close(scores[0].cpu()[kept], rw[kept], rtol=1e-4, atol=1e-4)
+    for t, s in enumerate(scores):
+        tok = out[:, 6 + t]
+        assert bool((s.gather(1, tok[:, None]) > -float('inf')).all())
+        torch.testing.assert_close(s.exp().sum(-1), torch.ones(3, device='cuda'), rtol=1e-4, atol=1e-4)
+    with pytest.raises(NotImplementedError):
+        model.generate(input_ids=ids.cuda(), max_length=12, num_beams=3)
+
+
 def test_decode_cache_path_matches_generic_path_fp32(pkg):
     """generate() through the projected-K/V ring cache + CUDA graph == generate() through forward(input_ids[:, -1:], mems) each step."""
     _, model = make_pair(pkg, 'fp32', mem_len=48, n_layer=2)

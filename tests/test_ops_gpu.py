@@ -328,6 +328,64 @@ def test_sampler_keep_set_and_distribution(ops, top_k, top_p, temp):
     assert chi2 < dof + 6 * math.sqrt(2 * dof) + 10, (chi2, dof)
 
 
+@pytest.mark.parametrize('V', [32768, 40000])
+@pytest.mark.parametrize('top_k,top_p,temp', [(8, 1.0, 1.0), (0, 0.9, 1.0), (50, 0.5, 0.8), (0, 1.0, 1.3), (2000, 0.97, 1.0), (1, 1.0, 1.0)])
+def test_sampler_large_vocabulary(ops, V, top_k, top_p, temp):
+    """Vocabularies past the shared-memory sort (WordPiece 32k; reference transformer_xl.py:56-63): the radix-selection sampler keeps
+    exactly the oracle's token set (temperature -> top-k with ties -> top-p with the boundary token -> renormalise), returns its log-probs, and
+    draws by inverse CDF over the kept tokens in index order."""
+    torch.manual_seed(V + top_k)
+    B = 6
+    scores = torch.log_softmax(3.0 * torch.randn(B, V, device='cuda'), -1)
+    scores[:, 11] = scores[:, 5]                       # exact ties
+    scores[1] = torch.log_softmax(torch.round(2.0 * torch.randn(V, device='cuda')), -1)      # a row that is nearly all ties
+    scores[2, 100:200] = -float('inf')
+    u = torch.rand(B, device='cuda')
+    nxt, keep, warped = ops.sample(scores, True, temp, top_k, top_p, u, want_keep=True, want_warped=True)
+    sc = scores.double().cpu() / temp
+    if top_k:
+        kth = torch.topk(sc, min(top_k, V))[0][:, -1:]
+        sc = sc.masked_fill(sc < kth, -float('inf'))
+    if top_p < 1.0:                                    # ties ordered by index (the library's total order): stable descending sort
+        srt, order = torch.sort(sc, descending=True, stable=True)
+        cum = srt.softmax(-1).cumsum(-1)
+        remove = cum > top_p
+        remove[:, 1:] = remove[:, :-1].clone()
+        remove[:, 0] = False
+        sc = sc.masked_fill(remove.scatter(1, order, remove), -float('inf'))
+    ref = torch.log_softmax(sc, -1)
+    ref_keep = ref > -float('inf')
+    got_keep = keep.cpu().bool()
+    # the boundary of the top-p set is decided on fixed-point mass sums: allow one token of slack per row, none elsewhere
+    assert int((got_keep != ref_keep).sum(1).max()) <= (1 if top_p < 1.0 else 0), (got_keep != ref_keep).sum(1)
+    both = got_keep & ref_keep
+    torch.testing.assert_close(warped.cpu()[both].double(), ref[both], rtol=2e-4, atol=2e-4)
+    assert bool((warped.cpu()[~got_keep] == -float('inf')).all())
+    assert got_keep[torch.arange(B), nxt.cpu()].all()
+    # the draw: inverse CDF over the kept tokens in index order
+    pk = torch.where(got_keep, warped.cpu().double().exp(), torch.zeros((), dtype=torch.float64))
+    cdf = pk.cumsum(-1) / pk.sum(-1, keepdim=True)
+    want = torch.searchsorted(cdf, u.cpu().double()[:, None]).squeeze(1).clamp_(max=V - 1)
+    for b in range(B):
+        if int(nxt[b]) != int(want[b]):                # only when u sits within rounding of a boundary of the CDF
+            lo, hi = sorted((int(nxt[b]), int(want[b])))
+            assert float(pk[b, lo + 1:hi + 1].sum() if hi > lo else 0) < 1e-5 or abs(float(cdf[b, lo]) - float(u[b])) < 1e-5, (b, int(nxt[b]), int(want[b]))
+    g, _, _ = ops.sample(scores, False)
+    assert torch.equal(g, scores.argmax(-1))
+    # distribution of many draws of one row
+    n = 20000
+    row = scores[:1].expand(n, V).contiguous()
+    draws, _, _ = ops.sample(row, True, temp, top_k, top_p, torch.rand(n, device='cuda'))
+    p = ref[0].exp().float()
+    cnt = torch.bincount(draws.cpu(), minlength=V).float()
+    sel = p * n >= 5
+    if int(sel.sum()) > 1:
+        chi2 = (((cnt - p * n) ** 2) / (p * n))[sel].sum().item()
+        dof = int(sel.sum().item()) - 1
+        assert chi2 < dof + 6 * math.sqrt(2 * dof) + 10, (chi2, dof)
+    assert cnt[~(got_keep[0] | ref_keep[0])].sum() == 0
+
+
 def test_sampler_greedy(ops):
     torch.manual_seed(7)
     scores = torch.log_softmax(torch.randn(9, 422, device='cuda'), -1)

@@ -128,6 +128,33 @@ def test_warpers_equal_hf_logits_processors():
         assert torch.allclose(got[keep], want[keep], atol=1e-6)
 
 
+def test_repetition_penalty_and_typical_equal_hf_processors():
+    """`repetition_penalty` / `typical_p` (accepted keys of the reference's `sample` strategy, musicnlp/trainer/eval.py:279): the oracle's
+    row-by-row restatements and the product's batched torch versions (generation.py, host-loop path) == HF's RepetitionPenaltyLogitsProcessor /
+    TypicalLogitsWarper on the same scores."""
+    import importlib
+    from transformers.generation.logits_process import RepetitionPenaltyLogitsProcessor, TypicalLogitsWarper
+    gen = importlib.import_module('symbolic-music-generation_b200.generation')
+    torch.manual_seed(11)
+    scores = torch.log_softmax(2.5 * torch.randn(6, 83), -1)
+    scores[:, :5] += 3.0                      # some positive scores: the penalty divides those and multiplies negative ones
+    prev = torch.randint(0, 83, (6, 19))
+    prev[:, 3] = prev[:, 7]                   # repeated tokens are penalised once
+    for pen in (1.2, 0.8, 2.0):
+        want = RepetitionPenaltyLogitsProcessor(pen)(prev, scores.clone())
+        assert torch.allclose(RefTransfoXLLMHeadModel.repetition_penalty(scores, prev, pen), want, atol=1e-6)
+        assert torch.allclose(gen.repetition_penalty_scores(scores, prev, pen), want, atol=1e-6)
+    filt = scores.clone()
+    filt[:, 40:] = -float('inf')              # as it arrives from the top-k / top-p filters
+    for mass in (0.2, 0.5, 0.9, 0.95):
+        for sc in (scores, filt):
+            want = TypicalLogitsWarper(mass)(prev, sc.clone())
+            for got in (RefTransfoXLLMHeadModel.typical_filter(sc, mass), gen.typical_filter_scores(sc, mass)):
+                assert torch.equal(torch.isinf(got), torch.isinf(want)), mass
+                keep = ~torch.isinf(want)
+                assert torch.equal(got[keep], want[keep]) and int(keep.sum(1).min()) >= 1
+
+
 def test_schedule_and_decay_groups_equal_hf():
     import importlib
     import transformers
