@@ -685,19 +685,19 @@ class MyTransfoXLLMHeadModel(nn.Module):
 
     # ------------------------------------------------------------------ generation surface (reference :223-241)
     def prepare_inputs_for_generation(self, input_ids, past=None, **model_kwargs):
-        inputs = {}
-        if past:
-            assert isinstance(past, list)
-            if isinstance(past[0], list):   # contrastive-search nested lists are re-stacked (:229-234)
-                assert all(isinstance(p, list) for p in past)
-                for i, p in enumerate(past):
-                    assert all(isinstance(t, torch.Tensor) for t in p)
-                    past[i] = torch.stack(p, dim=0)
-            inputs['mems'] = past
-            inputs['input_ids'] = input_ids[:, -1].unsqueeze(-1)
-        else:
-            inputs['input_ids'] = input_ids
-        return inputs
+        """HF generation hook with the 4.25-era `past` keyword (reference transformer_xl.py:223-241): without a cache the whole prompt is fed,
+        with one only the newest token plus the mems.  Contrastive search hands `past` back as one list of tensors per layer; those are
+        stacked again, in place as the reference does."""
+        if not past:
+            return {'input_ids': input_ids}
+        if not isinstance(past, list):
+            raise TypeError(f'past must be a list of per-layer mems, got {type(past).__name__}')
+        for layer, entry in enumerate(past):
+            if isinstance(entry, (list, tuple)):
+                if not all(isinstance(t, torch.Tensor) for t in entry):
+                    raise TypeError('nested past entries must be tensors')
+                past[layer] = torch.stack(list(entry), dim=0)
+        return {'mems': past, 'input_ids': input_ids[:, -1:]}
 
     def generate(self, input_ids=None, **kwargs):
         from .generation import generate
