@@ -180,3 +180,6 @@ int txl_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t r
 int64_t txl_relattn_saved_bytes_tc(const TxlAttnDims* D);
 int64_t txl_relattn_tile_rows(const TxlAttnDims* D);
 int txl_relattn_nt_max(const TxlBand* band);
+// 1 (default): the saving forward keeps one soft-max reference per row and the backward reads the P~ tiles directly; TXL_ATTN_FROZEN_REF=0: running
+// maximum + normalised P tiles written by the dQ pass (round-1 behaviour).  Read once.
+int txl_relattn_frozen_ref();

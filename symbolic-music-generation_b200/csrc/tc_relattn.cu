@@ -32,8 +32,12 @@ struct FwdArgs {
   TxlBand band;
   int64_t ldq;
   float scale_log2;
-  float* m_tiles;      // saved-for-backward (optional): running max used by every (row, key tile), [B, H, nI, nt_max, 128] fp32
+  float* m_tiles;      // saved-for-backward (optional): the reference m used by every (row, key tile), [B, H, nI, nt_max, 128] fp32
   int nt_max;          //   ... the bf16 P~ = exp2(score - m) tiles themselves go out through tmP, [B, H, nI, nt_max][128 x 64]
+  int frozen_ref;      // saving mode: m is fixed after the row's first key tile, so P = P~ * exp2(m - lse) with ONE factor per row — the backward
+                       //   folds it into dO and reads the P~ tiles directly instead of writing and re-reading a normalised copy (0.6 GB per layer).
+                       //   Later scores may exceed m: P~ > 1 is fine in bf16 / fp32 (same exponent range); a row whose scores spread by more than
+                       //   ~88 nats around its first tile's maximum overflows to inf / NaN loudly (the exact SIMT kernels have no such limit).
 };
 
 // w[j] <- w[j + sh] for j < OUT, 0 <= sh < 32; W = OUT + 31 valid inputs.  Select ops only, static register indices.
@@ -189,7 +193,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKm, const __grid_con
     int lo_i = 1, hi_i = 0;    // rows past T: everything masked
     if (i < g.T) { lo_i = band_lo(g, i); hi_i = min(band_hi(g, i), g.klen - 1); }
     const int lo_all = band_lo(g, ilast), hi_all = band_hi(g, i0);   // keys live for EVERY row of the tile (if tile rows all < T)
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, m_ref = 0.f;
     float O[DH];
 #pragma unroll
     for (int c = 0; c < DH; ++c) O[c] = 0.f;
@@ -226,9 +230,14 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKm, const __grid_con
       float mx = t[0];
 #pragma unroll
       for (int jj = 1; jj < BKV; ++jj) mx = fmaxf(mx, t[jj]);
-      const float m_new = fmaxf(m_run, mx * a.scale_log2);
-      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = exp2f(m_run - m_safe);
+      float m_new, m_safe, corr;
+      if (a.frozen_ref && n > 0) { m_new = m_run; m_safe = m_ref; corr = 1.f; }      // reference fixed by the first key tile
+      else {
+        m_new = fmaxf(m_run, mx * a.scale_log2);
+        m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+        corr = exp2f(m_run - m_safe);
+        m_ref = m_safe;
+      }
       float sum = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -266,7 +275,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKm, const __grid_con
         o.z = pack_bf16(O[c * 8 + 4] * inv, O[c * 8 + 5] * inv); o.w = pack_bf16(O[c * 8 + 6] * inv, O[c * 8 + 7] * inv);
         dst[c] = o;
       }
-      a.lse[((int64_t)b * a.H + h) * g.T + i] = m_run * 0.6931471805599453f + logf(l_run);
+      a.lse[((int64_t)b * a.H + h) * g.T + i] = (a.frozen_ref ? m_ref : m_run) * 0.6931471805599453f + logf(l_run);
     }
   }
   tc_fence_before();
@@ -298,13 +307,14 @@ int txl_relattn_fwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
   if ((rc = txl_make_tmap_2d(&tmR, r, (uint64_t)klen, (uint64_t)HD, (uint64_t)HD, WIN, DH))) return rc;
   CUtensorMap tmP = tmR;
   FwdArgs a;
-  a.m_tiles = nullptr; a.nt_max = 0;
+  a.m_tiles = nullptr; a.nt_max = 0; a.frozen_ref = 0;
   if (saved) {
     if (!al16(saved) || txl_relattn_saved_bytes_tc(D) == 0) return TXL_OK;
     const int64_t trows = txl_relattn_tile_rows(D);
     a.nt_max = txl_relattn_nt_max(&D->band);
     a.m_tiles = reinterpret_cast<float*>(reinterpret_cast<bf16*>(saved) + trows * BKV);
     if ((rc = txl_make_tmap_2d(&tmP, saved, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
+    a.frozen_ref = txl_relattn_frozen_ref();
   }
 
   a.q = (const bf16*)q; a.rwb = rwb; a.rrb = rrb; a.out = (bf16*)out; a.lse = lse; a.B = D->B; a.H = D->H; a.band = D->band; a.ldq = D->ldq;

@@ -58,6 +58,7 @@ struct BwdArgs {
   float scale, scale_log2;
   int delta_min, n_delta;        // MODE_DR: diagonals J - 2I
   int store_tiles, nt_max;       // MODE_DQ: also write the bf16 P and dS tiles of every band tile (consumed by the lite dK/dV and dR kernels)
+  int store_p;                   // dQ pass over saved tiles: 0 = the dK/dV pass reads the forward's P~ tiles (per-row reference), only dS is written
   const float* m_tiles;          // saved by the forward kernel: the running max behind every (row, key tile) of its P~ tiles
   int abl;                       // TXL_ABL timing ablations (results invalid when non-zero)
 };
@@ -124,7 +125,8 @@ struct TileIter {
   }
 };
 
-struct Maps { CUtensorMap qw, qr, dO, km, vm, kc, vc, r, pst, dst, psv, r64, pst2, dst2; };   // pst/dst: [tiles*128, 64] bf16 tile stores (P, dS); psv: P~ saved by the forward; r64: R in 64-row boxes; pst2/dst2: two tiles per box
+struct Maps { CUtensorMap qw, qr, dO, km, vm, kc, vc, r, pst, dst, psv, r64, pst2, dst2, pkv, pkv2, dOkv; };   // pst/dst: [tiles*128, 64] bf16 tile stores (P, dS); psv: P~ saved by the forward; r64: R in 64-row boxes; pst2/dst2: two tiles per box;
+// pkv / pkv2 / dOkv: what the lite dK/dV kernels multiply for dV — (P, dO), or with the forward's per-row reference (P~, dO scaled by exp2(m - lse))
 
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_tc_kernel(const __grid_constant__ Maps M, const BwdArgs a) {
@@ -519,10 +521,10 @@ __global__ void __launch_bounds__(192, 1) relattn_bwd_dkv_lite_kernel(const __gr
         mbar_expect_tx(&full[s], LITE_STAGE);
         const int trow = ((((b * a.H + h) * nI + I) * a.nt_max) + (J - q_tile_first_kt(g, I))) * BQ;
         const int qrow = b * g.T + I * BQ;
-        tma_load_2d(st, &M.pst, &full[s], 0, trow);                    // P  (I,J)   [128 q x 64 keys]
+        tma_load_2d(st, &M.pkv, &full[s], 0, trow);                    // P  (I,J)   [128 q x 64 keys]  (or P~, with dO pre-scaled per row)
         tma_load_2d(st + SZ_Q, &M.dst, &full[s], 0, trow);             // dS (I,J)
         tma_load_2d(st + 2 * SZ_Q, &M.qw, &full[s], h * DH, qrow);     // Qw (I)     [128 q x 64]
-        tma_load_2d(st + 3 * SZ_Q, &M.dO, &full[s], h * DH, qrow);     // dO (I)
+        tma_load_2d(st + 3 * SZ_Q, &M.dOkv, &full[s], h * DH, qrow);   // dO (I)
       }
     }
   } else if (warp == 1) {
@@ -624,10 +626,10 @@ __global__ void __launch_bounds__(192, 1) relattn_bwd_dkv_pair_kernel(const __gr
         mbar_expect_tx(&full[s], PAIR_STAGE);
         const int trow = ((((b * a.H + h) * nI + I) * a.nt_max) + (J - q_tile_first_kt(g, I))) * BQ;
         const int qrow = b * g.T + I * BQ;
-        tma_load_2d(st, &M.pst2, &full[s], 0, trow);                    // P  (I,J), (I,J+1)   2 x [128 q x 64 keys]
+        tma_load_2d(st, &M.pkv2, &full[s], 0, trow);                    // P  (I,J), (I,J+1)   2 x [128 q x 64 keys]  (or P~)
         tma_load_2d(st + 2 * SZ_Q, &M.dst2, &full[s], 0, trow);         // dS (I,J), (I,J+1)
         tma_load_2d(st + 4 * SZ_Q, &M.qw, &full[s], h * DH, qrow);      // Qw (I)     [128 q x 64]
-        tma_load_2d(st + 5 * SZ_Q, &M.dO, &full[s], h * DH, qrow);      // dO (I)
+        tma_load_2d(st + 5 * SZ_Q, &M.dOkv, &full[s], h * DH, qrow);    // dO (I)
       }
     }
   } else if (warp == 1) {
@@ -1078,7 +1080,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_dq_saved_kernel(const
     if (lane == 0) {     // bf16 P and dS of every band tile -> global (consumed by the lite dK/dV and dR kernels)
       for (int n = 0; n < count; ++n) {
         mbar_wait(b_ready, n & 1);
-        tma_store_tile(&M.pst, sm + PL::P, (tile0 + n) * BQ);
+        if (a.store_p) tma_store_tile(&M.pst, sm + PL::P, (tile0 + n) * BQ);
         tma_store_tile(&M.dst, sm + PL::DS, (tile0 + n) * BQ);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1160,7 +1162,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_dq_saved_kernel(const
       for (int c = 0; c < KPT / 8; ++c) {
         uint4 o; o.x = pack2(p[c * 8], p[c * 8 + 1]); o.y = pack2(p[c * 8 + 2], p[c * 8 + 3]); o.z = pack2(p[c * 8 + 4], p[c * 8 + 5]); o.w = pack2(p[c * 8 + 6], p[c * 8 + 7]);
         uint4 d; d.x = pack2(ds[c * 8], ds[c * 8 + 1]); d.y = pack2(ds[c * 8 + 2], ds[c * 8 + 3]); d.z = pack2(ds[c * 8 + 4], ds[c * 8 + 5]); d.w = pack2(ds[c * 8 + 6], ds[c * 8 + 7]);
-        *reinterpret_cast<uint4*>(sm + PL::P + tile_off[c]) = o;
+        if (a.store_p) *reinterpret_cast<uint4*>(sm + PL::P + tile_off[c]) = o;
         *reinterpret_cast<uint4*>(sm + PL::DS + tile_off[c]) = d;
       }
       fence_proxy_async_smem();
@@ -1199,11 +1201,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) relattn_bwd_dq_saved_kernel(const
   if (warp == W_MMA) tmem_dealloc<TS_COLS>(tmem_base);
 }
 
-// qw = q + r_w_bias, qr = q + r_r_bias (bf16, [B*T, HD]); delta[b,h,i] = sum_c dO.O
+// qw = q + r_w_bias, qr = q + r_r_bias (bf16, [B*T, HD]); delta[b,h,i] = sum_c dO.O;
+// dos (optional) = dO * exp2(m - lse) per (row, head), m = the forward's per-row soft-max reference: P^T dO = P~^T dos, so the dK/dV pass
+// multiplies the forward's P~ tiles as they are.
 // One thread per 8 adjacent columns (16-byte loads / stores), the 8 threads of a (row, head) meet in three shuffles.
 __global__ void __launch_bounds__(256) relattn_bwd_prep_kernel(const bf16* __restrict__ q, int64_t ldq, const float* __restrict__ rwb, const float* __restrict__ rrb,
                                         const bf16* __restrict__ out, const bf16* __restrict__ dout, bf16* __restrict__ qw, bf16* __restrict__ qr,
-                                        float* __restrict__ delta, int B, int T, int H) {
+                                        float* __restrict__ delta, int B, int T, int H, bf16* __restrict__ dos, const float* __restrict__ lse,
+                                        const float* __restrict__ m_tiles, int nt_max) {
   const int HD = H * DH, tpr = HD / 8;                         // threads per row
   const int64_t total = (int64_t)B * T * tpr;
   for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {   // total is a multiple of 8: groups stay whole
@@ -1227,7 +1232,17 @@ __global__ void __launch_bounds__(256) relattn_bwd_prep_kernel(const bf16* __res
     *reinterpret_cast<uint4*>(qw + n * HD + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     *reinterpret_cast<uint4*>(qr + n * HD + c) = make_uint4(orr[0], orr[1], orr[2], orr[3]);
     s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);   // DH = 64 = 8 threads
-    if ((c & (DH - 1)) == 0) { const int64_t b = n / T, i = n % T; delta[(b * H + c / DH) * T + i] = s; }
+    const int64_t b = n / T, i = n % T; const int hh = c / DH;
+    if ((c & (DH - 1)) == 0) delta[(b * H + hh) * T + i] = s;
+    if (dos) {
+      const int nI = (T + BQ - 1) / BQ;
+      const float m = m_tiles[(((b * H + hh) * nI + i / BQ) * (int64_t)nt_max) * BQ + (i % BQ)];
+      const float f = exp2f(m - lse[(b * H + hh) * T + i] * 1.4426950408889634f);
+      uint32_t od[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) od[k] = pack2(__uint_as_float(ds[k] << 16) * f, __uint_as_float(ds[k] & 0xFFFF0000u) * f);
+      *reinterpret_cast<uint4*>(dos + n * HD + c) = make_uint4(od[0], od[1], od[2], od[3]);
+    }
   }
 }
 
@@ -1288,6 +1303,12 @@ int64_t txl_relattn_bwd_tc_workspace(const TxlAttnDims* D) {
   return base + 2 * bwd_tile_rows(D) * BKV * 2 + 2048;     // + bf16 P and dS tile stores
 }
 
+int txl_relattn_frozen_ref() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("TXL_ATTN_FROZEN_REF"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on;
+}
+
 // Probe switches of the backward (profiling only; never set on the product path): read from TXL_DBG / TXL_ABL ONCE at load time, changed
 // afterwards only through txl_relattn_bwd_probe — no getenv on the per-call path.
 static int env_int_once(const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; }
@@ -1319,9 +1340,18 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
   const int dbg = g_bwd_probe_dbg;   // timing probes only (txl_relattn_bwd_probe): 16 = run the dQ pass alone, 32 = skip the prep kernel
   const int64_t n = (int64_t)D->B * T * HD;
   bf16* qw = (bf16*)ws; bf16* qr = qw + n; float* delta = (float*)(qr + n);
+  // the forward's saved tiles carry ONE soft-max reference per row (frozen_ref): the dK/dV pass reads them directly against dO scaled per row,
+  // and the dQ pass writes no normalised P tiles.  The scaled dO lives where those P tiles would have gone.
+  const int64_t trows_ = bwd_tile_rows(D);
+  const bool saved_ok = saved && txl_relattn_saved_bytes_tc(D) > 0 && al16(saved) && trows_ < (1ll << 31);
+  const bool frozen = saved_ok && txl_relattn_frozen_ref();
+  bf16* dos = nullptr;
+  const float* m_saved = saved_ok ? reinterpret_cast<const float*>(reinterpret_cast<const bf16*>(saved) + trows_ * BKV) : nullptr;
+  if (frozen) dos = (bf16*)((((uintptr_t)(delta + (int64_t)D->B * D->H * T)) + 1023) & ~(uintptr_t)1023);
   if (!(dbg & 32)) {
     const int64_t items = (int64_t)D->B * T * (HD / 8);
-    relattn_bwd_prep_kernel<<<(unsigned)imin64(cdiv64(items, 256), (int64_t)txl_num_sms() * 16), 256, 0, st>>>((const bf16*)q, D->ldq, rwb, rrb, (const bf16*)out, (const bf16*)dout, qw, qr, delta, D->B, T, D->H);
+    relattn_bwd_prep_kernel<<<(unsigned)imin64(cdiv64(items, 256), (int64_t)txl_num_sms() * 16), 256, 0, st>>>((const bf16*)q, D->ldq, rwb, rrb, (const bf16*)out, (const bf16*)dout, qw, qr, delta, D->B, T, D->H,
+                                                                                                                     dos, lse, m_saved, bwd_nt_max(D->band));
     TXL_LAUNCH_CHECK();
   }
   Maps M;
@@ -1364,11 +1394,17 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
     if ((rc = txl_make_tmap_2d(&M.dst, dstore, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
   } else { M.pst = M.qw; M.dst = M.qw; }
   a.m_tiles = nullptr; M.psv = M.qw; M.r64 = M.r; M.pst2 = M.qw; M.dst2 = M.qw;
+  M.pkv = M.pst; M.pkv2 = M.qw; M.dOkv = M.dO; a.store_p = 1;
   a.abl = g_bwd_probe_abl;
   if (saved && a.store_tiles && txl_relattn_saved_bytes_tc(D) > 0 && al16(saved)) {
     a.m_tiles = reinterpret_cast<const float*>(reinterpret_cast<const bf16*>(saved) + trows * BKV);
     if ((rc = txl_make_tmap_2d(&M.psv, saved, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, BQ, BKV))) return rc;
     if ((rc = txl_make_tmap_2d(&M.r64, r, (uint64_t)klen, (uint64_t)HD, (uint64_t)HD, BKV, DH))) return rc;
+    if (frozen) {
+      a.store_p = 0;
+      M.pkv = M.psv;
+      if ((rc = txl_make_tmap_2d(&M.dOkv, dos, (uint64_t)D->B * T, (uint64_t)HD, (uint64_t)HD, BQ, DH))) return rc;
+    }
     static bool attr_s = false;
     if (!attr_s) { TXL_CUDA(cudaFuncSetAttribute(relattn_bwd_dq_saved_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PlanS::SMEM)); attr_s = true; }
     relattn_bwd_dq_saved_kernel<<<dim3(nI, D->H, D->B), NTHREADS, PlanS::SMEM, st>>>(M, a);
@@ -1411,6 +1447,8 @@ int txl_relattn_bwd_tc(const void* q, const void* k_mem, const void* v_mem, cons
       bf16* pstore2 = (bf16*)pws2; bf16* dstore2 = pstore2 + trows * BKV;
       if ((rc = txl_make_tmap_2d(&M.pst2, pstore2, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, 2 * BQ, BKV))) return rc;
       if ((rc = txl_make_tmap_2d(&M.dst2, dstore2, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, 2 * BQ, BKV))) return rc;
+      M.pkv2 = M.pst2;
+      if (!a.store_p) { if ((rc = txl_make_tmap_2d(&M.pkv2, saved, (uint64_t)trows, (uint64_t)BKV, (uint64_t)BKV, 2 * BQ, BKV))) return rc; }
       static bool attr_p = false;
       if (!attr_p) { TXL_CUDA(cudaFuncSetAttribute(relattn_bwd_dkv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM)); attr_p = true; }
       relattn_bwd_dkv_pair_kernel<<<dim3(klen / (2 * BKV), D->H, D->B), 192, PAIR_SMEM, st>>>(M, a);
