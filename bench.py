@@ -461,9 +461,9 @@ def decode_probe(torch, pkg, pdist, cfg_train, args, dev, rank, world):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dQ pass (ncu --set full, cfg2 shape, 32 sequences)
-DQ_TRAFFIC = 2006.7e6
-DQ_TRAFFIC_SRC = ('dram__bytes_read.sum + dram__bytes_write.sum of one launch (817 MB read: saved P~ tiles + operands; 1190 MB written: bf16 P/dS tiles), '
-                  'profiles/r01_ncu_full_attention_final.txt')
+DQ_TRAFFIC = 1408.2e6
+DQ_TRAFFIC_SRC = ('dram__bytes_read.sum + dram__bytes_write.sum of one launch (809 MB read: saved P~ tiles + operands; 600 MB written: bf16 dS tiles), '
+                  'profiles/r02_ncu_full_attention.txt')
 
 
 def dominant_kernel_probe(torch, ops, model, cfg, B, T, M, dev):
@@ -515,13 +515,13 @@ def dominant_kernel_probe(torch, ops, model, cfg, B, T, M, dev):
     unit = 2.0 * T * Kb * d * B                      # one score-sized contraction over the live band, per launch
     tf = lambda units, ms: units * unit / (ms / 1e3) / 1e12
     dq = tf(3, ms_dq)                                # dP, dQw, dQr
-    return {'kernel': 'relattn_bwd_dq_saved_kernel (dQ pass of the attention backward: P from the saved P~ tiles, dP, dS, dQw, dQr; writes bf16 P/dS tiles)',
+    return {'kernel': 'relattn_bwd_dq_saved_kernel (dQ pass of the attention backward: P from the saved P~ tiles, dP, dS, dQw, dQr; writes bf16 dS tiles)',
             'bound': 'tensor', 'achieved': dq, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': dq / peaks['tf_burst'],
             'traffic': DQ_TRAFFIC, 'traffic_source': DQ_TRAFFIC_SRC,
             'ms_per_launch': ms_dq, 'algorithmic_flops_per_launch': 3 * unit, 'peak_source': 'burst bf16, ' + peaks['src'],
             'other_kernels': {
                 'relattn_fwd_tc_kernel (AC+BD+rel_shift+band mask+softmax+PV)': {'ms_per_launch': ms_fwd, 'achieved': tf(3, ms_fwd), 'frac': tf(3, ms_fwd) / peaks['tf_burst'],
-                                                                                  'algorithmic_flops_per_launch': 3 * unit, 'traffic': 788.7e6},
+                                                                                  'algorithmic_flops_per_launch': 3 * unit, 'traffic': 787.6e6},
                 'attention backward, all passes (prep + dQ + lite dK/dV + lite dR)': {'ms_per_call': ms_bwd_all, 'achieved': tf(6, ms_bwd_all),
                                                                                       'frac': tf(6, ms_bwd_all) / peaks['tf_burst'], 'algorithmic_flops_per_call': 6 * unit}}}
 
