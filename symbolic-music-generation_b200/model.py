@@ -285,9 +285,10 @@ class MyTransfoXLLMHeadModel(nn.Module):
         self.monitor_greedy = False
         self.last_greedy = None
         # optional range check (HF raises an index error for ids / labels outside the vocabulary; the kernels here would embed zeros / score
-        # loss 0): with check_ranges the label-shift kernel counts offending labels on the device, `assert_ranges_ok()` reads the counter
+        # loss 0): with check_ranges offending ids and labels are counted on the device (the labels by the label-shift kernel), `assert_ranges_ok()` reads the counters
         self.check_ranges = False
         self._bad_labels = None
+        self._bad_ids = None
         self.last_generate_path = None
         self._backwards_since_step = 0
         self._grad_accum_base = None
@@ -598,6 +599,9 @@ class MyTransfoXLLMHeadModel(nn.Module):
             ids = ids.long()
         ids = ids.contiguous()
         bsz, tgt_len = ids.shape
+        if self.check_ranges:          # counted on the device (no host wait); HF's embedding lookup would raise for these
+            bad = ((ids < 0) | (ids >= self.config.vocab_size)).sum(dtype=torch.int32).view(1)
+            self._bad_ids = bad if self._bad_ids is None else self._bad_ids + bad
         labels_shift = None
         if labels is not None:
             if tuple(labels.shape) != (bsz, tgt_len):
@@ -655,7 +659,9 @@ class MyTransfoXLLMHeadModel(nn.Module):
                                           hidden_states=None, attentions=None)
 
     def assert_ranges_ok(self):
-        """One host read: raises if any label seen since `check_ranges = True` was outside [0, vocab_size) (and not -100)."""
+        """Two host reads: raises if any input id or label seen since `check_ranges = True` was outside [0, vocab_size) (labels: and not -100)."""
+        if self._bad_ids is not None and int(self._bad_ids.item()) != 0:
+            raise IndexError(f'{int(self._bad_ids.item())} input id(s) outside [0, {self.config.vocab_size}) were passed to forward')
         if self._bad_labels is not None and int(self._bad_labels.item()) != 0:
             raise IndexError(f'{int(self._bad_labels.item())} label(s) outside [0, {self.config.vocab_size}) were passed to forward')
 

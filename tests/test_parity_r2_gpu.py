@@ -304,5 +304,11 @@ def test_device_label_fixup_and_range_check(pkg):
     bad = ids.clone()
     bad[1, 3] = 422
     model(input_ids=ids.cuda(), labels=bad.cuda())
-    with pytest.raises(IndexError):
+    with pytest.raises(IndexError, match='label'):
+        model.assert_ranges_ok()
+    model._bad_labels = None
+    bad_ids = ids.clone()
+    bad_ids[0, 2] = 500
+    model(input_ids=bad_ids.cuda(), labels=ok.cuda())
+    with pytest.raises(IndexError, match='input id'):
         model.assert_ranges_ok()
