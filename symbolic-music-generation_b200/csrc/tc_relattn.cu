@@ -34,7 +34,7 @@ struct FwdArgs {
   float scale_log2;
   float* m_tiles;      // saved-for-backward (optional): the reference m used by every (row, key tile), [B, H, nI, nt_max, 128] fp32
   int nt_max;          //   ... the bf16 P~ = exp2(score - m) tiles themselves go out through tmP, [B, H, nI, nt_max][128 x 64]
-  int frozen_ref;      // saving mode: m is fixed after the row's first key tile, so P = P~ * exp2(m - lse) with ONE factor per row — the backward
+  int frozen_ref;      // saving mode: m is fixed by the row's first key tile that holds a live key, so P = P~ * exp2(m - lse) with ONE factor per row — the backward
                        //   folds it into dO and reads the P~ tiles directly instead of writing and re-reading a normalised copy (0.6 GB per layer).
                        //   Later scores may exceed m: P~ > 1 is fine in bf16 / fp32 (same exponent range); a row whose scores spread by more than
                        //   ~88 nats around its first tile's maximum overflows to inf / NaN loudly (the exact SIMT kernels have no such limit).
@@ -227,12 +227,12 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKm, const __grid_con
           if (j < lo_i || j > hi_i) t[jj] = -INFINITY;
         }
       }
-      float mx = t[0];
-#pragma unroll
-      for (int jj = 1; jj < BKV; ++jj) mx = fmaxf(mx, t[jj]);
       float m_new, m_safe, corr;
-      if (a.frozen_ref && n > 0) { m_new = m_run; m_safe = m_ref; corr = 1.f; }      // reference fixed by the first key tile
+      if (a.frozen_ref && m_run != -INFINITY) { m_new = m_run; m_safe = m_ref; corr = 1.f; }   // reference fixed by the row's first key tile with a live key: no maximum needed
       else {
+        float mx = t[0];
+#pragma unroll
+        for (int jj = 1; jj < BKV; ++jj) mx = fmaxf(mx, t[jj]);
         m_new = fmaxf(m_run, mx * a.scale_log2);
         m_safe = (m_new == -INFINITY) ? 0.f : m_new;
         corr = exp2f(m_run - m_safe);
@@ -276,6 +276,9 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKm, const __grid_con
         dst[c] = o;
       }
       a.lse[((int64_t)b * a.H + h) * g.T + i] = (a.frozen_ref ? m_ref : m_run) * 0.6931471805599453f + logf(l_run);
+      // the row's reference where the backward's prep kernel looks for it: the first tile's slot (a row whose first tile was fully masked has
+      // P~ = 0 there, so any m serves that tile)
+      if (a.m_tiles && a.frozen_ref) a.m_tiles[(int64_t)tile0 * BQ + r] = m_ref;
     }
   }
   tc_fence_before();
