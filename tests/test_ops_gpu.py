@@ -235,13 +235,40 @@ def _ref_attention(q, k, v, r, rwb, rrb, T, M, ML, C, same):
 def test_relattn_fwd_bwd(ops, mode, B, H, dh, T, M, ML, C, same, save):
     """save=True: the forward call also leaves its soft-max numerators for the backward (tensor-core shapes with a dense band);
     where no kernel uses them the wrapper returns None and the call is the recompute path again."""
+    _relattn_case(ops, mode, B, H, dh, T, M, ML, C, same, save)
+
+
+@pytest.mark.parametrize('ramp', [12.0, 20.0])
+@pytest.mark.parametrize('B,H,dh,T,M,ML,C,same', [(1, 2, 64, 256, 256, 256, 1024, 1), (2, 1, 64, 128, 128, 128, 1024, 1)])
+def test_relattn_saved_path_wide_score_range(ops, B, H, dh, T, M, ML, C, same, ramp):
+    """The saving forward fixes a row's soft-max reference at its first live key tile (one factor per row lets the backward read the P~ tiles
+    directly).  Here the scores GROW towards the later key tiles — a row's maximum lies up to 14 nats above its first tile's at ramp 20 — so
+    the stored numerators exceed 1 by up to six orders of magnitude: forward output and every gradient must still match the literal
+    fp32 computation.  (At ramp 40 the bf16 inputs themselves cost 2.6-2.8e-2 on dq with the round-1 running-maximum path and 2.8-3.0e-2 with
+    the per-row reference: the tolerance of this file is then the binding one, not the reference scheme.)"""
+    _relattn_case(ops, 'bf16', B, H, dh, T, M, ML, C, same, True, qscale=2.0, ramp=ramp)
+
+
+def _relattn_case(ops, mode, B, H, dh, T, M, ML, C, same, save, qscale=0.5, ramp=0.0):
     torch.manual_seed(5)
     dt = DT[mode]
     d = H * dh
     klen = M + T
     P = ops.num_r(T, M, C)
-    qkv = (0.5 * torch.randn(B * T, 3 * d, device='cuda')).to(dt)
-    kvm = (0.5 * torch.randn(B * M, 2 * d, device='cuda')).to(dt) if M > 0 else None
+    qkv = (0.5 * torch.randn(B * T, 3 * d, device='cuda'))
+    kvm = (0.5 * torch.randn(B * M, 2 * d, device='cuda')) if M > 0 else None
+    if qscale != 0.5 or ramp:
+        qkv[:, :d] *= qscale / 0.5
+        # keys aligned with a common direction whose weight grows with the key position: later key tiles hold the larger scores
+        u = torch.nn.functional.normalize(torch.randn(d, device='cuda'), dim=0) * math.sqrt(d)
+        qkv[:, :d] += 0.5 * u
+        pos_c = (torch.arange(B * T, device='cuda') % T).float() + M
+        qkv[:, d:2 * d] += (ramp * pos_c / klen)[:, None] * u * 0.25
+        if M > 0:
+            pos_m = (torch.arange(B * M, device='cuda') % M).float()
+            kvm[:, :d] += (ramp * pos_m / klen)[:, None] * u * 0.25
+    qkv = qkv.to(dt)
+    kvm = kvm.to(dt) if M > 0 else None
     r = (0.5 * torch.randn(P, d, device='cuda')).to(dt)
     rwb, rrb = 0.3 * torch.randn(d, device='cuda'), 0.3 * torch.randn(d, device='cuda')
     band = ops.make_band(T, M, ML, C, same)
