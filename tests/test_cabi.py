@@ -176,4 +176,12 @@ def test_argument_errors_are_reported_before_any_launch(built_lib):
     refused(lib.txl_clm_labels(one, None, 8, 1, None), 'clm_labels')
     refused(lib.txl_last_index_of(one, 4, 2, 8, 9, one, None), 'last_index_of')                                             # row pitch < T
     refused(lib.txl_sample(one, 2, 16, 1, 0.0, 8, 1.0, one, one, None, None, None), 'sample')                               # temperature 0
+    handled = ctypes.c_int(7)
+    refused(lib.txl_gemm_add_ln_fwd(None, one, None, one, one, one, one, None, None, None, 512, 512, 512, 512, 512, 1e-5, 0.0, 0, 0, None, ctypes.byref(handled)),
+            'gemm_add_ln_fwd')                                                                                               # null operand
+    assert handled.value == 0
+    refused(lib.txl_gemm_add_ln_fwd(one, one, None, one, one, one, one, one, None, None, 512, 512, 512, 512, 512, 1e-5, 0.0, 0, 0, None, ctypes.byref(handled)),
+            'saved together')                                                                                                # z without mean / rstd
+    refused(lib.txl_gemm_add_ln_fwd(one, one, None, one, one, one, one, None, None, None, 512, 512, 512, 512, 512, 1e-5, 1.0, 0, 0, None, ctypes.byref(handled)),
+            'drop_p')                                                                                                        # drop_p = 1
     assert lib.txl_decode_attn_pipe_ws_bytes(2, 3, 64, 1) == 0 and lib.txl_decode_attn_pipe_ws_bytes(2, 3, 64, 4) == 2 * 3 * 4 * 66 * 4
