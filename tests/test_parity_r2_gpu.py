@@ -312,3 +312,65 @@ def test_device_label_fixup_and_range_check(pkg):
     model(input_ids=bad_ids.cuda(), labels=ok.cuda())
     with pytest.raises(IndexError, match='input id'):
         model.assert_ranges_ok()
+
+
+# ----------------------------------------------------------------------------------------------------------------- full BASELINE sizes: properties
+@pytest.mark.parametrize('B,T', [(32, 1024), (16, 2048)])
+def test_cfg2_cfg5_full_size_properties(pkg, B, T):
+    """BASELINE configs[1] and configs[4] at their FULL sizes (12 layers, V 1190, bf16; 32 sequences of 1024 tokens with mem_len 1024, and 16 of
+    2048 with mem_len 2048 / clamp_len 1024), where the CPU oracle takes minutes: size-independent properties of the path instead.  (1) Sequences are independent: the first half of the batch gives
+    bit-identical losses, log-probs and mems to the same sequences run alone — in evaluation and, for the losses, in training mode with dropout
+    (the counter-based masks are keyed by element index, identical for the leading rows).  (2) `losses` is exactly 0 at ignored labels and
+    `loss == losses[losses != 0].mean()` (reference transformer_xl.py:197-200).  (3) new mems are the layer INPUTS of the last mem_len
+    positions: `mems[0]` is the scaled embedding of the ids (HF `_update_mems`, Appendix A.8').  (4) The call is deterministic."""
+    cfg = pkg.MyTransfoXLConfig('small', vocab_size=1190, max_length=T, mem_len=T, cutoffs=[], compute_dtype='bf16')
+    assert cfg.clamp_len == 1024
+    torch.manual_seed(77)
+    model = pkg.MyTransfoXLLMHeadModel(cfg).cuda()
+    H = B // 2
+    ids1, _ = _batch(1190, B, T, seed=77, pad=False)
+    ids2, labels2 = _batch(1190, B, T, seed=78)
+    labels2[5, T - 300:] = -100
+    labels2[H + 2, :300] = -100
+    ids1, ids2, labels2 = ids1.cuda(), ids2.cuda(), labels2.cuda()
+    model.eval()
+    with torch.no_grad():
+        m_full = model(input_ids=ids1).mems
+        full = model(input_ids=ids2, mems=m_full, labels=labels2)
+        again = model(input_ids=ids2, mems=m_full, labels=labels2)
+        m_half = model(input_ids=ids1[:H]).mems
+        half = model(input_ids=ids2[:H], mems=m_half, labels=labels2[:H])
+    assert torch.equal(full.losses, again.losses) and torch.equal(full.logits, again.logits)                      # (4)
+    assert torch.equal(full.losses[:H], half.losses) and torch.equal(full.logits[:H], half.logits)                # (1)
+    for l in range(cfg.n_layer):
+        assert torch.equal(full.mems[l][:, :H], half.mems[l])
+    ignored = labels2[:, 1:] == -100
+    assert bool((full.losses[ignored] == 0).all()) and bool((full.losses[~ignored] > 0).all())                    # (2)
+    assert abs(full.loss.item() - full.losses[full.losses != 0].mean().item()) < 1e-5 * full.loss.item()
+    emb = model.transformer.word_emb.emb_layers[0].weight
+    want = (emb[ids2].to(torch.bfloat16).float() * (cfg.d_model ** 0.5)).to(torch.bfloat16).transpose(0, 1)      # (3) (mem_len, B, d)
+    assert full.mems[0].shape == (T, B, 512) and torch.equal(full.mems[0].to(torch.bfloat16), want)
+    model.train()
+    torch.manual_seed(5)
+    t_full = model(input_ids=ids2, mems=m_full, labels=labels2)
+    torch.manual_seed(5)
+    model._step_seed -= 1              # same dropout stream for the second call
+    t_half = model(input_ids=ids2[:H], mems=m_half, labels=labels2[:H])
+    assert torch.equal(t_full.losses[:H], t_half.losses) and not torch.equal(t_full.losses, full.losses)
+
+
+def test_cfg4_full_size_decode_sharding_invariance(pkg):
+    """BASELINE configs[3] at its full shape (64 sequences, 12 layers, mems 1024, top-k 8 sampling): decoding the 64 sequences in one call equals
+    decoding them as two shards of 32 with `seq_offset` (how the sequences spread over GPUs — SURVEY 8e: no collective), token for token;
+    the draws are keyed by (seed, global sequence index, step).  Both runs take the launch-chain engine (groups of 16 sequences)."""
+    cfg = pkg.MyTransfoXLConfig('small', vocab_size=1190, max_length=1024, mem_len=1024, cutoffs=[], compute_dtype='bf16', dropout=0.0)
+    torch.manual_seed(77)
+    model = pkg.MyTransfoXLLMHeadModel(cfg).cuda().eval()
+    prompt = torch.randint(1, 1190, (64, 16), generator=torch.Generator().manual_seed(3)).cuda()
+    kw = dict(max_length=16 + 40, do_sample=True, top_k=8, renormalize_logits=True, eos_token_id=None, seed=4242)
+    whole = model.generate(input_ids=prompt, **kw)
+    lo = model.generate(input_ids=prompt[:32], seq_offset=0, **kw)
+    hi = model.generate(input_ids=prompt[32:], seq_offset=32, **kw)
+    assert model.last_generate_path == 'decode_cache'
+    assert whole.shape == (64, 56) and torch.equal(whole, torch.cat([lo, hi], 0))
+    assert len({tuple(r.tolist()) for r in whole[:, 16:]}) > 32          # the sequences really differ
